@@ -1,0 +1,159 @@
+/* yv_b200.h — C ABI of the B200-native SVO ray caster (libyv_b200.so).
+ *
+ * Drop-in boundary for the reference's renderer path. Plain C types only; every entry point
+ * returns 0 on success or a negative status, with a message available from yv_last_error().
+ * Each declaration cites the reference interface it replaces (paths relative to the
+ * znah/yoxel-voxel tree). INTEGRATION.md shows the reference-side binding.
+ *
+ * There is no CPU fallback: every render entry point fails with YV_ERR_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef YV_B200_H
+#define YV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "yv_format.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YV_OK            0
+#define YV_ERR_ARG      (-1)   /* bad argument                                              */
+#define YV_ERR_IO       (-2)   /* file could not be read / written                          */
+#define YV_ERR_FORMAT   (-3)   /* malformed node pool                                       */
+#define YV_ERR_CUDA     (-4)   /* CUDA runtime failure or no usable device                  */
+#define YV_ERR_NOSCENE  (-5)   /* RenderFrame without SetScene (reference returns NULL,
+                                  cell/ppu_renderer.cpp:78-79)                              */
+#define YV_ERR_NOMEM    (-6)
+
+typedef struct yv_svo yv_svo;             /* SVOData        (cell/svodata.h:22-55)          */
+typedef struct yv_renderer yv_renderer;   /* ISVORenderer   (cell/svorenderer.h:5-24)       */
+
+const char *yv_last_error(void);          /* thread-local message of the last failure       */
+int yv_abi_version(void);
+
+/* ---- scene: SVOData (cell/svodata.h) --------------------------------------------------- */
+
+/* SVOData::Load(const char*)  (cell/svodata.h:31-50) */
+int yv_svo_load(const char *path, yv_svo **out);
+/* scene built elsewhere (demo/SVORenderer.h:14 SetScene(DynamicSVO*)): copies the pool */
+int yv_svo_from_memory(yv_node_id root, const yv_vox_node *nodes, uint32_t count, yv_svo **out);
+/* DynamicSVO::Save (ore/src/main.cpp:123) */
+int yv_svo_save(const yv_svo *svo, const char *path);
+void yv_svo_free(yv_svo *svo);
+/* SVOData::GetRoot / operator[] (cell/svodata.h:52-54) */
+yv_node_id yv_svo_root(const yv_svo *svo);
+uint32_t yv_svo_node_count(const yv_svo *svo);          /* DynamicSVO::GetNodeCount            */
+uint32_t yv_svo_depth(const yv_svo *svo);
+const yv_vox_node *yv_svo_nodes(const yv_svo *svo);     /* host pool, reference layout         */
+
+/* procedural scenes: gen_spheres.py:5-35, gen_largevol.py:8-40 (dataset replaced by seeded
+ * noise), MakeSphereSource + BuildRange (ore/src/main.cpp:69,121), MakeRawSource (:37-52) */
+int yv_svo_build_sphere_fractal(int depth, int threads, yv_svo **out);
+int yv_svo_build_iso_volume(int depth, uint32_t seed, int iso_level, int threads, yv_svo **out);
+int yv_svo_build_single_sphere(int depth, int cx, int cy, int cz, int radius,
+                               uint8_t r, uint8_t g, uint8_t b, yv_svo **out);
+int yv_svo_build_from_dense(int depth, const uint32_t *voxdata, yv_svo **out);
+uint32_t yv_pack_voxdata(uint8_t r, uint8_t g, uint8_t b, float nx, float ny, float nz);
+
+/* CudaSVO::Update (demo/SVORenderer.cpp:33-53): repack the pool into the 16-byte GPU record
+ * form and copy it to `device`. Implicit at the first render if not called. */
+int yv_svo_upload(yv_svo *svo, int device);
+/* bytes resident on `device` for this scene (0 if not uploaded) */
+uint64_t yv_svo_device_bytes(const yv_svo *svo, int device);
+/* repacked record / leaf counts, for roofline arithmetic and tests */
+int yv_svo_packed_counts(yv_svo *svo, uint32_t *records, uint32_t *leaves);
+/* copy of the repacked host arrays (tests): records = 4 u32 each, leaves = 1 u32 each */
+int yv_svo_packed_copy(yv_svo *svo, uint32_t *records_out, uint32_t *leaves_out);
+
+/* ---- renderer: ISVORenderer (cell/svorenderer.h:5-24) + SVORenderer (demo/SVORenderer.h) -- */
+
+/* CreateSimpleRenderer / CreateThreadedRenderer / CreateSPURenderer (cell/svorenderer.h:26-30) */
+int yv_renderer_create(int device, yv_renderer **out);
+void yv_renderer_destroy(yv_renderer *r);
+
+int yv_set_scene(yv_renderer *r, yv_svo *svo);                 /* SetScene      (:12) borrowed   */
+int yv_set_view_pos(yv_renderer *r, const float pos[3]);       /* SetViewPos    (:14) also moves
+                                                                  the head light (renderer_base.h:30-35) */
+int yv_set_view_dir(yv_renderer *r, const float dir[3]);       /* SetViewDir    (:15)            */
+int yv_set_view_up(yv_renderer *r, const float up[3]);         /* SetViewUp     (:16)            */
+int yv_set_resolution(yv_renderer *r, int width, int height);  /* SetResolution (:18) / SetViewSize */
+int yv_get_resolution(const yv_renderer *r, int *width, int *height);   /* GetResolution (:19)   */
+int yv_set_fov(yv_renderer *r, float fov_deg);                 /* SetFOV        (:21)            */
+int yv_get_fov(const yv_renderer *r, float *fov_deg);          /* GetFOV (demo/SVORenderer.h:23) */
+
+/* const Color32* RenderFrame()  (cell/svorenderer.h:23): synchronous; *rgba aliases
+ * renderer-owned pinned host memory (width*height*4 bytes, R,G,B,A), valid until the next
+ * yv_set_resolution / yv_render_frame* / destroy on this handle. */
+int yv_render_frame(yv_renderer *r, const uint8_t **rgba);
+/* void Render(void* d_dstBuf)  (demo/SVORenderer.h:36): writes uchar4 pixels of the current
+ * row band into a DEVICE pointer addressed as a full frame (base + (y*width+x)*4). The pointer
+ * may be a peer / IPC mapping of another GPU's frame buffer. Synchronous. */
+int yv_render_frame_device(yv_renderer *r, void *d_rgba);
+/* same, asynchronous on the renderer's stream (pair with yv_sync) */
+int yv_render_frame_device_async(yv_renderer *r, void *d_rgba);
+int yv_sync(yv_renderer *r);
+/* renderer-owned device frame buffer (full frame), for callers that have none */
+int yv_device_framebuffer(yv_renderer *r, void **d_rgba);
+
+/* Screen-space partition for multi-GPU rendering (SPURenderer splits blocks across SPEs,
+ * cell/spu_renderer.cpp:73-87): render only rows [y0,y1). Default: the whole frame. */
+int yv_set_rows(yv_renderer *r, int y0, int y1);
+
+/* Secondary rays (BASELINE config 4). shadow: 0/1; ao_samples: 0..16. light_pos is used for
+ * the Lambert term and the shadow ray when shadow != 0 (otherwise the light rides on the eye). */
+int yv_set_secondary(yv_renderer *r, int shadow, int ao_samples, uint32_t seed,
+                     const float light_pos[3], float voxel_size, float ao_max_t);
+
+/* TraceResult per pixel (cell/ppu_renderer.cpp:7-12). Hit buffers cost 12 B/ray of extra
+ * stores, so they are off unless enabled. yv_get_hits copies the last frame's records to host
+ * arrays of width*height entries (any pointer may be NULL). */
+int yv_enable_hits(yv_renderer *r, int enable);
+int yv_get_hits(yv_renderer *r, uint32_t *node, int32_t *child, float *t);
+/* optional per-ray counters (node fetches incl. re-fetches after a pop) for profiling */
+int yv_enable_counters(yv_renderer *r, int enable);
+int yv_get_counters(yv_renderer *r, uint32_t *fetches_per_ray);
+
+/* device time of the last frame's kernels (CUDA events on the renderer's stream), ms */
+float yv_last_frame_ms(const yv_renderer *r);
+/* kernels launched by the last frame */
+int yv_last_frame_launches(const yv_renderer *r);
+
+/* Run the renderer on a caller-owned CUDA stream (cudaStream_t as void*; NULL = own stream) */
+int yv_set_stream(yv_renderer *r, void *cuda_stream);
+
+/* Kernel variant knobs (for ablation runs; defaults are the tuned ones):
+ *   "smem_nodes"  number of top-of-tree records staged in shared memory per CTA
+ *   "persistent"  1 = persistent CTAs pulling tiles from an atomic counter, 0 = one CTA per tile
+ *   "refill"      1 = warp-level ray refill (ballot/shuffle compaction) in the persistent kernel */
+int yv_set_option(yv_renderer *r, const char *name, int value);
+int yv_get_option(const yv_renderer *r, const char *name, int *value);
+
+/* DynamicSVO::TraceRay (ore/src/main.cpp:125): trace `count` arbitrary rays on the device.
+ * pos/dir are count*3 floats; outputs are count entries (any may be NULL). */
+int yv_trace_rays(yv_renderer *r, const float *pos, const float *dir, uint32_t count,
+                  uint32_t *node, int32_t *child, float *t);
+
+/* ---- multi-process frame gather over NVLink (one process per GPU) ------------------------ */
+/* Export a device allocation made by this library (yv_device_framebuffer) as a 64-byte CUDA
+ * IPC handle; open it in another process; the mapping is a valid target for
+ * yv_render_frame_device there (direct peer stores into GPU 0's frame). */
+int yv_ipc_export(void *d_ptr, uint8_t handle[64]);
+int yv_ipc_open(int device, const uint8_t handle[64], void **d_ptr);
+int yv_ipc_close(void *d_ptr);
+
+/* RendererBase::InitRayDir (cell/renderer_base.h:50-61): the per-frame ray basis the kernel
+ * consumes, computed on the host (pure function; exposed for tests and external ray generators) */
+int yv_init_ray_dir(const float dir[3], const float up[3], float fov_deg, int width, int height,
+                    float dir0[3], float du[3], float dv[3]);
+
+int yv_device_count(void);
+int yv_device_name(int device, char *buf, size_t len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YV_B200_H */

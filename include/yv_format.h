@@ -1,0 +1,107 @@
+/* yv_format.h — data formats and numeric conventions of the SVO ray-caster path.
+ *
+ * Definitions only (struct layouts, bit positions, constants, and the prose spec of the
+ * arithmetic the reference snapshot does not pin). Both the CUDA product
+ * (yoxel-voxel_b200/csrc) and the CPU oracle (oracle/) include this file; each implements
+ * the arithmetic described here on its own, so that a parity test compares two
+ * independent implementations of one written spec.
+ *
+ * Reference pointers (relative to /root/reference):
+ *   node record ............ reaction/report/main.tex:38-55  (cpp/vox_node.h is absent)
+ *   .vox file .............. cell/svodata.h:31-50
+ *   hit record ............. cell/ppu_renderer.cpp:7-12
+ *   frame buffer ........... cell/renderer_base.h:22,42 ; cell/main.cpp:36 ("RGBA", CharPixel)
+ *   near-zero clamp ........ reaction/report/voxel.tex:316-318
+ */
+#ifndef YV_FORMAT_H
+#define YV_FORMAT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- node pool (main.tex:38-55) ------------------------------------------------------ */
+
+typedef uint32_t yv_node_id;              /* VoxNodeId                                      */
+typedef uint32_t yv_vox_data;             /* VoxData: 16-bit colour + 16-bit normal         */
+
+#define YV_NULL_BIT    0x80000000u        /* IsNull(id): top bit set (main.tex:62)          */
+#define YV_EMPTY_NODE  0x80000000u        /* EmptyNode  (main.tex:54)                       */
+#define YV_FULL_NODE   0x80000001u        /* FullNode   (main.tex:55)                       */
+
+/* VoxNode, #pragma pack(4): 40 bytes, array-of-structs, little-endian on disk.            */
+typedef struct yv_vox_node {
+  uint32_t flags;                         /* bits 0..7 leaf flags, 8..15 null flags,
+                                             bit 19 empty flag (main.tex:40-42)             */
+  yv_vox_data data;                       /* sub-tree average (coarser LOD)                 */
+  uint32_t child[8];                      /* node id | inline VoxData (leaf bit set) |
+                                             id with top bit set = empty/full               */
+} yv_vox_node;
+
+#define YV_NODE_BYTES 40u
+#define YV_LEAF_FLAG(flags, i)  (((flags) >> (i)) & 1u)          /* GetLeafFlag              */
+#define YV_NULL_FLAG(flags, i)  (((flags) >> (8 + (i))) & 1u)
+#define YV_IS_NULL(id)          (((id) & YV_NULL_BIT) != 0u)     /* IsNull                   */
+
+/* Child index bit i (0=x,1=y,2=z) set = upper half of the node along that axis
+ * (trace_spu.cpp:62-64 builds childId that way and XORs it with dirFlags).                 */
+
+/* ---- .vox container (svodata.h:31-50) ------------------------------------------------- */
+/* header = 4 little-endian u32: root id, two words the loader discards, node count;
+ * then count * 40 bytes of raw nodes. We write the two ignored words as
+ * YV_VOX_MAGIC and the tree depth (levels below the root cube); readers ignore them.       */
+#define YV_VOX_HEADER_BYTES 16u
+#define YV_VOX_MAGIC        0x31584f56u   /* "VOX1" */
+
+/* ---- hit record (ppu_renderer.cpp:7-12) ----------------------------------------------- */
+/* Stored as three planar per-pixel arrays: node (u32), child (i32), t (f32).
+ * A ray that hits nothing has node = YV_EMPTY_NODE, child = -1, t = 0.                     */
+#define YV_MISS_NODE   YV_EMPTY_NODE
+#define YV_MISS_CHILD  (-1)
+
+/* ---- frame buffer (Color32) ------------------------------------------------------------ */
+/* 4 bytes per pixel in memory order R,G,B,A; row-major; row 0 is the top row.
+ * Miss = (0,0,0,0) (ppu_renderer.cpp:54). Hit alpha = 255.                                  */
+
+/* ---- builder decisions: things the snapshot does not pin ------------------ */
+
+/* AdjustDir: |d_i| < eps  =>  d_i = copysign(eps, d_i)   (voxel.tex:316-318)               */
+#define YV_DIR_EPS 1e-6f
+
+/* VoxData bit packing:
+ *   bits  0..15  colour, RGB565: r5 = bits 11..15, g6 = bits 5..10, b5 = bits 0..4
+ *   bits 16..23  normal octahedral u (0..255)
+ *   bits 24..31  normal octahedral v (0..255)
+ * Colour decode to 8 bits (integer): r8=(r5<<3)|(r5>>2), g8=(g6<<2)|(g6>>4), b8=(b5<<3)|(b5>>2).
+ * Normal decode (float32, round-to-nearest, no FMA, in this order):
+ *   fx = (float)u / 127.5f - 1.0f;  fy = (float)v / 127.5f - 1.0f;
+ *   fz = (1.0f - |fx|) - |fy|;
+ *   if (fz < 0) { ox = (1.0f - |fy|) * sgn(fx); oy = (1.0f - |fx|) * sgn(fy); fx = ox; fy = oy; }
+ *       with sgn(a) = (a >= 0) ? 1.0f : -1.0f
+ *   len = sqrt((fx*fx + fy*fy) + fz*fz);  n = (fx/len, fy/len, fz/len)
+ * Normal encode (builder side, any precision): p = n.xy / (|nx|+|ny|+|nz|); fold if nz < 0;
+ *   u = round((p.x*0.5+0.5)*255), v likewise, clamped to 0..255.                             */
+#define YV_PACK_RGB565(r8, g8, b8) \
+  ((uint32_t)((((r8) >> 3) << 11) | (((g8) >> 2) << 5) | ((b8) >> 3)))
+
+/* SimpleShader::Shade(VoxData, dir, t) (ppu_renderer.cpp:67; body absent) is restated as a
+ * head-light Lambert term (north_star: "Lambert"), float32, no FMA, in this order:
+ *   P   = viewer + dir * t                       (component-wise: mul, then add)
+ *   Lv  = light - P
+ *   len = sqrt((Lv.x*Lv.x + Lv.y*Lv.y) + Lv.z*Lv.z)
+ *   L   = len > 0 ? Lv / len : (0,0,0)
+ *   ndl = (n.x*L.x + n.y*L.y) + n.z*L.z ;  d = ndl > 0 ? ndl : 0
+ *   k   = YV_SHADE_AMBIENT + YV_SHADE_DIFFUSE * d      (mul, then add)
+ *   c8' = (uint8) min(255.0f, floorf(c8 * k + 0.5f))    per channel (mul, add, floor)
+ *   k is multiplied by the visibility terms of the secondary rays when they are enabled
+ *   (see yv_b200.h, YV_SECONDARY_*).
+ * ambient 0.1 follows the CUDA variant's rp.ambient (demo/SVORenderer.cpp:113).             */
+#define YV_SHADE_AMBIENT 0.1f
+#define YV_SHADE_DIFFUSE 0.9f
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YV_FORMAT_H */

@@ -1,0 +1,415 @@
+/* yv_oracle.c — CPU oracle for the SVO ray-caster path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C restatement of the reference CPU tracer. PARITY UNPINNED (see yv_oracle.h):
+ * the reference holds no golden vectors for this path and its tracer does not build here.
+ *
+ * Every function cites the reference lines whose behaviour it restates (paths relative to
+ * /root/reference). All ray arithmetic is IEEE-754 binary32, round-to-nearest, and this file
+ * must be compiled with -ffp-contract=off so that no FMA is formed (oracle/Makefile).
+ */
+#include "yv_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct { float x, y, z; } v3;
+
+/* cg::point_t operators (nest/include/geometry/primitives/point.h) ----------------------- */
+
+/* scalar product: res = 0; res += a[n]*b[n] for n = 0..2 (point.h:416-425) */
+static inline float v3_dot(v3 a, v3 b) {
+  float r = 0.0f;
+  r += a.x * b.x;
+  r += a.y * b.y;
+  r += a.z * b.z;
+  return r;
+}
+/* vector product (point.h:435-440) */
+static inline v3 v3_cross(v3 a, v3 b) {
+  v3 r = { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x };
+  return r;
+}
+/* normalized(): norm = sqrt(a*a); point /= norm (point.h:462-466,485-499,726-733) */
+static inline v3 v3_normalized(v3 a) {
+  float n = sqrtf(v3_dot(a, a));
+  v3 r = { a.x / n, a.y / n, a.z / n };
+  return r;
+}
+static inline v3 v3_scale(v3 a, float s) { v3 r = { a.x * s, a.y * s, a.z * s }; return r; }
+static inline v3 v3_add(v3 a, v3 b) { v3 r = { a.x + b.x, a.y + b.y, a.z + b.z }; return r; }
+static inline v3 v3_sub(v3 a, v3 b) { v3 r = { a.x - b.x, a.y - b.y, a.z - b.z }; return r; }
+static inline v3 v3_from(const float p[3]) { v3 r = { p[0], p[1], p[2] }; return r; }
+
+static inline float max3(v3 a) { float m = a.x > a.y ? a.x : a.y; return m > a.z ? m : a.z; }
+static inline float min3(v3 a) { float m = a.x < a.y ? a.x : a.y; return m < a.z ? m : a.z; }
+
+/* RendererBase::InitRayDir (cell/renderer_base.h:50-61).
+ * grad2rad(float) = grad * float(pi/180) (nest/include/geometry/xmath.h:47,57).
+ * The one transcendental (tan) is evaluated in double and rounded once; the product's host
+ * side does the same (see DESIGN.md "numeric contract"). */
+void yvo_init_ray_dir(const yvo_camera *cam, yvo_raydir *out) {
+  const double pi = 3.14159265358979323846;
+  v3 vfwd = v3_normalized(v3_from(cam->dir));
+  v3 vright = v3_normalized(v3_cross(vfwd, v3_from(cam->up)));
+  v3 vup = v3_cross(vright, vfwd);
+
+  float half_deg = cam->fov_deg / 2;
+  float half_rad = half_deg * (float)(pi / 180.0);
+  float da = (float)(tan((double)half_rad) / (double)cam->width);
+
+  v3 du = v3_scale(v3_scale(vright, 2.0f), da);     /* 2 * vright * da   (:58) */
+  v3 dv = v3_scale(v3_scale(vup, -2.0f), da);       /* -2 * vup * da     (:59) */
+  float w = (float)cam->width, h = (float)cam->height;
+  /* vfwd - du*W/2 - dv*H/2 (:60) */
+  v3 a = v3_scale(du, w); a.x /= 2.0f; a.y /= 2.0f; a.z /= 2.0f;
+  v3 b = v3_scale(dv, h); b.x /= 2.0f; b.y /= 2.0f; b.z /= 2.0f;
+  v3 d0 = v3_sub(v3_sub(vfwd, a), b);
+  out->dir0[0] = d0.x; out->dir0[1] = d0.y; out->dir0[2] = d0.z;
+  out->du[0] = du.x; out->du[1] = du.y; out->du[2] = du.z;
+  out->dv[0] = dv.x; out->dv[1] = dv.y; out->dv[2] = dv.z;
+}
+
+/* AdjustDir (call: ppu_renderer.cpp:57; rule: reaction/report/voxel.tex:316-318) */
+static inline float adjust1(float d) {
+  return fabsf(d) < YV_DIR_EPS ? copysignf(YV_DIR_EPS, d) : d;
+}
+static inline v3 adjust_dir(v3 d) {
+  v3 r = { adjust1(d.x), adjust1(d.y), adjust1(d.z) };
+  return r;
+}
+
+/* SetupTrace (call: ppu_renderer.cpp:60; rule: voxel.tex:319-326, trace_spu.c_:84-93) */
+static inline int setup_trace(v3 p, v3 d, v3 *t1, v3 *t2, uint32_t *dir_flags) {
+  uint32_t f = 0;
+  if (d.x < 0) { p.x = 1.0f - p.x; d.x = -d.x; f |= 1u; }
+  if (d.y < 0) { p.y = 1.0f - p.y; d.y = -d.y; f |= 2u; }
+  if (d.z < 0) { p.z = 1.0f - p.z; d.z = -d.z; f |= 4u; }
+  t1->x = (0.0f - p.x) / d.x; t2->x = (1.0f - p.x) / d.x;
+  t1->y = (0.0f - p.y) / d.y; t2->y = (1.0f - p.y) / d.y;
+  t1->z = (0.0f - p.z) / d.z; t2->z = (1.0f - p.z) / d.z;
+  *dir_flags = f;
+  return max3(*t1) < min3(*t2);
+}
+
+/* FindFirstChild (scalar form of cell/spu/trace_spu.cpp:48-68) */
+static inline int find_first_child(v3 *t1, v3 *t2) {
+  float tmx = 0.5f * (t1->x + t2->x);
+  float tmy = 0.5f * (t1->y + t2->y);
+  float tmz = 0.5f * (t1->z + t2->z);
+  float t_enter = max3(*t1);
+  int ch = 0;
+  if (t_enter > tmx) { ch |= 1; t1->x = tmx; } else t2->x = tmx;
+  if (t_enter > tmy) { ch |= 2; t1->y = tmy; } else t2->y = tmy;
+  if (t_enter > tmz) { ch |= 4; t1->z = tmz; } else t2->z = tmz;
+  return ch;
+}
+
+/* GoNext (scalar form of cell/spu/trace_spu.cpp:70-93) */
+static inline int go_next(int *ch, v3 *t1, v3 *t2) {
+  int e;
+  if (t2->x > t2->y) e = (t2->y < t2->z) ? 1 : 2;
+  else               e = (t2->x < t2->z) ? 0 : 2;
+  int mask = 1 << e;
+  if (*ch & mask) return 0;
+  *ch ^= mask;
+  float *a = e == 0 ? &t1->x : (e == 1 ? &t1->y : &t1->z);
+  float *b = e == 0 ? &t2->x : (e == 1 ? &t2->y : &t2->z);
+  float dt = *b - *a;
+  *a = *b;
+  *b += dt;
+  return 1;
+}
+
+typedef struct {
+  const yv_vox_node *nodes;
+  uint32_t count;
+  uint32_t dir_flags;
+  int front_only;        /* 0 = reference behaviour; 1 = secondary rays: a leaf counts only
+                            if its own min(t2) > 0 (no hits behind the origin)              */
+  /* result (TraceResult, ppu_renderer.cpp:7-12) */
+  yv_node_id node;
+  int child;
+  float t;
+  /* counters */
+  uint64_t visits, iters;
+} trace_ctx;
+
+/* PPURendererBase::RecTrace (cell/ppu_renderer.cpp:18-41) */
+static int rec_trace(trace_ctx *c, yv_node_id id, v3 t1, v3 t2) {
+  if (YV_IS_NULL(id) || min3(t2) <= 0) return 0;            /* :20 */
+  if (id >= c->count) return 0;                             /* malformed pool: assert in ref (:54) */
+  const yv_vox_node *node = &c->nodes[id];                  /* :23  <- counted node fetch */
+  c->visits++;
+  int ch = find_first_child(&t1, &t2);                      /* :24 */
+  for (;;) {
+    int cc = ch ^ (int)c->dir_flags;
+    c->iters++;
+    if (YV_LEAF_FLAG(node->flags, cc) && (!c->front_only || min3(t2) > 0)) {   /* :27 */
+      c->node = id; c->child = cc; c->t = max3(t1);         /* :29-31 */
+      return 1;
+    }
+    if (!YV_LEAF_FLAG(node->flags, cc) && rec_trace(c, node->child[cc], t1, t2))  /* :35 */
+      return 1;
+    if (!go_next(&ch, &t1, &t2)) return 0;                  /* :38 */
+  }
+}
+
+static int trace_ray(trace_ctx *c, yv_node_id root, v3 pos, v3 dir) {
+  v3 t1, t2;
+  dir = adjust_dir(dir);
+  if (!setup_trace(pos, dir, &t1, &t2, &c->dir_flags)) return 0;
+  return rec_trace(c, root, t1, t2);
+}
+
+/* ---- VoxData unpack + SimpleShader::Shade restatement (spec: include/yv_format.h) ------- */
+
+void yvo_unpack_normal(yv_vox_data data, float n[3]) {
+  float fx = (float)((data >> 16) & 255u) / 127.5f - 1.0f;
+  float fy = (float)((data >> 24) & 255u) / 127.5f - 1.0f;
+  float fz = (1.0f - fabsf(fx)) - fabsf(fy);
+  if (fz < 0) {
+    float ox = (1.0f - fabsf(fy)) * (fx >= 0 ? 1.0f : -1.0f);
+    float oy = (1.0f - fabsf(fx)) * (fy >= 0 ? 1.0f : -1.0f);
+    fx = ox; fy = oy;
+  }
+  float len = sqrtf((fx * fx + fy * fy) + fz * fz);
+  n[0] = fx / len; n[1] = fy / len; n[2] = fz / len;
+}
+
+static inline void unpack_color(yv_vox_data data, uint32_t c[3]) {
+  uint32_t r5 = (data >> 11) & 31u, g6 = (data >> 5) & 63u, b5 = data & 31u;
+  c[0] = (r5 << 3) | (r5 >> 2);
+  c[1] = (g6 << 2) | (g6 >> 4);
+  c[2] = (b5 << 3) | (b5 >> 2);
+}
+
+static inline float lambert(const float n[3], v3 P, v3 light) {
+  v3 Lv = v3_sub(light, P);
+  float len = sqrtf((Lv.x * Lv.x + Lv.y * Lv.y) + Lv.z * Lv.z);
+  v3 L = { 0, 0, 0 };
+  if (len > 0) { L.x = Lv.x / len; L.y = Lv.y / len; L.z = Lv.z / len; }
+  float ndl = (n[0] * L.x + n[1] * L.y) + n[2] * L.z;
+  return ndl > 0 ? ndl : 0.0f;
+}
+
+static inline void write_color(yv_vox_data data, float k, uint8_t out[4]) {
+  uint32_t c[3];
+  unpack_color(data, c);
+  for (int i = 0; i < 3; ++i) {
+    float v = floorf((float)c[i] * k + 0.5f);
+    out[i] = (uint8_t)(v < 255.0f ? v : 255.0f);
+  }
+  out[3] = 255;
+}
+
+void yvo_shade(yv_vox_data data, const float dir[3], float t,
+               const float viewer[3], const float light[3], float visibility, uint8_t out[4]) {
+  float n[3];
+  yvo_unpack_normal(data, n);
+  v3 P = { viewer[0] + dir[0] * t, viewer[1] + dir[1] * t, viewer[2] + dir[2] * t };
+  float d = lambert(n, P, v3_from(light));
+  float k = YV_SHADE_AMBIENT + YV_SHADE_DIFFUSE * (d * visibility);
+  write_color(data, k, out);
+}
+
+/* ---- secondary rays (BASELINE config 4; our definition, mirrored by the kernel) ---------- */
+
+static inline uint32_t hash_u32(uint32_t x) {           /* lowbias32 */
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+
+/* Unit vector from integer hashes by rejection in the cube: no transcendental functions, so
+ * the CPU and GPU agree bit for bit. Up to 8 tries, then +z. */
+static v3 hash_unit_vector(uint32_t key) {
+  for (int k = 0; k < 8; ++k) {
+    uint32_t h = hash_u32(key + 0x9e3779b9U * (uint32_t)k);
+    float x = (float)(int)(h & 1023u) - 511.5f;
+    float y = (float)(int)((h >> 10) & 1023u) - 511.5f;
+    float z = (float)(int)((h >> 20) & 1023u) - 511.5f;
+    float l2 = (x * x + y * y) + z * z;
+    if (l2 <= 261632.25f && l2 >= 1.0f) {             /* inside the ball of radius 511.5 */
+      float l = sqrtf(l2);
+      v3 r = { x / l, y / l, z / l };
+      return r;
+    }
+  }
+  v3 up = { 0, 0, 1 };
+  return up;
+}
+
+typedef struct {
+  const yv_vox_node *nodes; uint32_t count; yv_node_id root;
+  const yvo_camera *cam; const yvo_secondary *sec; yvo_raydir rdd;
+  int32_t y0, y1;
+  uint32_t *hit_node; int32_t *hit_child; float *hit_t; uint8_t *rgba; uint32_t *visits;
+  yvo_stats stats;
+} strip_job;
+
+/* PPURendererBase::RenderRect (cell/ppu_renderer.cpp:43-70) over rows [y0,y1) */
+static void *render_strip(void *arg) {
+  strip_job *j = (strip_job *)arg;
+  const int W = j->cam->width;
+  const v3 pos = v3_from(j->cam->pos);
+  const v3 dir0 = v3_from(j->rdd.dir0), du = v3_from(j->rdd.du), dv = v3_from(j->rdd.dv);
+  const yvo_secondary *sec = j->sec;
+  const int want_sec = sec && (sec->shadow || sec->ao_samples > 0);
+  trace_ctx c;
+  memset(&c, 0, sizeof c);
+  c.nodes = j->nodes; c.count = j->count;
+
+  for (int y = j->y0; y < j->y1; ++y) {
+    for (int x = 0; x < W; ++x) {
+      size_t offs = (size_t)y * (size_t)W + (size_t)x;                       /* :53 */
+      uint8_t px[4] = { 0, 0, 0, 0 };                                       /* :54 */
+      uint32_t hn = YV_MISS_NODE; int32_t hc = YV_MISS_CHILD; float ht = 0.0f;
+      uint64_t v0 = c.visits;
+
+      v3 d = v3_add(v3_add(dir0, v3_scale(du, (float)x)), v3_scale(dv, (float)y));
+      d = v3_normalized(d);                                                  /* :56 */
+      d = adjust_dir(d);                                                     /* :57 */
+      j->stats.rays++;
+      c.front_only = 0;
+      if (trace_ray(&c, j->root, pos, d)) {                                  /* :60-65 */
+        hn = c.node; hc = c.child; ht = c.t;
+        j->stats.hits++;
+        yv_vox_data data = j->nodes[hn].child[hc];                           /* :67 */
+        float dd[3] = { d.x, d.y, d.z };
+        if (!want_sec) {
+          yvo_shade(data, dd, ht, j->cam->pos, j->cam->pos, 1.0f, px);       /* light = eye (:33-34) */
+        } else {
+          float n[3];
+          yvo_unpack_normal(data, n);
+          v3 P = { pos.x + d.x * ht, pos.y + d.y * ht, pos.z + d.z * ht };
+          v3 O = { P.x + n[0] * sec->voxel_size, P.y + n[1] * sec->voxel_size,
+                   P.z + n[2] * sec->voxel_size };
+          v3 light = sec->shadow ? v3_from(sec->light_pos) : pos;   /* no shadow: head light */
+          float dl = lambert(n, P, light);
+          float vis = 1.0f;
+          c.front_only = 1;
+          if (sec->shadow) {
+            v3 Lv = v3_sub(light, O);
+            float len = sqrtf(v3_dot(Lv, Lv));
+            if (len > 0) {
+              v3 sd = { Lv.x / len, Lv.y / len, Lv.z / len };
+              j->stats.rays++;
+              if (trace_ray(&c, j->root, O, sd) && c.t > 0 && c.t < len) vis = 0.0f;
+            }
+          }
+          float ao = 1.0f;
+          if (sec->ao_samples > 0) {
+            int occ = 0;
+            for (int s = 0; s < sec->ao_samples; ++s) {
+              uint32_t key = hash_u32((uint32_t)offs * 16u + (uint32_t)s) ^ hash_u32(sec->seed);
+              v3 U = hash_unit_vector(key);
+              v3 D = { n[0] + U.x, n[1] + U.y, n[2] + U.z };
+              float l2 = v3_dot(D, D);
+              if (l2 < 1e-6f) { D.x = n[0]; D.y = n[1]; D.z = n[2]; }
+              else { float l = sqrtf(l2); D.x /= l; D.y /= l; D.z /= l; }
+              j->stats.rays++;
+              if (trace_ray(&c, j->root, O, D) && c.t > 0 && c.t < sec->ao_max_t) occ++;
+            }
+            ao = 1.0f - (float)occ / (float)sec->ao_samples;
+          }
+          float k = (YV_SHADE_AMBIENT + YV_SHADE_DIFFUSE * (dl * vis)) * ao;
+          write_color(data, k, px);
+        }
+      }
+      if (j->hit_node)  j->hit_node[offs] = hn;
+      if (j->hit_child) j->hit_child[offs] = hc;
+      if (j->hit_t)     j->hit_t[offs] = ht;
+      if (j->rgba)      memcpy(j->rgba + 4 * offs, px, 4);
+      if (j->visits)    j->visits[offs] = (uint32_t)(c.visits - v0);
+    }
+  }
+  j->stats.node_visits = c.visits;
+  j->stats.iterations = c.iters;
+  return NULL;
+}
+
+int yvo_render(const yv_vox_node *nodes, uint32_t node_count, yv_node_id root,
+               const yvo_camera *cam, const yvo_secondary *sec,
+               int32_t y0, int32_t y1, int32_t threads,
+               uint32_t *hit_node, int32_t *hit_child, float *hit_t,
+               uint8_t *rgba, uint32_t *visits_per_ray, yvo_stats *stats) {
+  if (!cam || cam->width <= 0 || cam->height <= 0) return -1;
+  if (!nodes && !YV_IS_NULL(root)) return -1;
+  if (y0 < 0) y0 = 0;
+  if (y1 > cam->height) y1 = cam->height;
+  if (threads < 1) threads = 1;
+  if (threads > 256) threads = 256;
+  int rows = y1 - y0;
+  if (rows <= 0) { if (stats) memset(stats, 0, sizeof *stats); return 0; }
+  if (threads > rows) threads = rows;
+
+  strip_job *jobs = (strip_job *)calloc((size_t)threads, sizeof(strip_job));
+  pthread_t *tids = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
+  yvo_raydir rdd;
+  yvo_init_ray_dir(cam, &rdd);
+  int ystep = rows / threads;                                   /* ppu_renderer.cpp:130 */
+  for (int i = 0; i < threads; ++i) {
+    strip_job *j = &jobs[i];
+    j->nodes = nodes; j->count = node_count; j->root = root; j->cam = cam; j->sec = sec; j->rdd = rdd;
+    j->y0 = y0 + ystep * i;
+    j->y1 = (i == threads - 1) ? y1 : y0 + ystep * (i + 1);
+    j->hit_node = hit_node; j->hit_child = hit_child; j->hit_t = hit_t; j->rgba = rgba;
+    j->visits = visits_per_ray;
+  }
+  if (threads == 1) render_strip(&jobs[0]);
+  else {
+    for (int i = 0; i < threads; ++i) pthread_create(&tids[i], NULL, render_strip, &jobs[i]);
+    for (int i = 0; i < threads; ++i) pthread_join(tids[i], NULL);
+  }
+  if (stats) {
+    memset(stats, 0, sizeof *stats);
+    for (int i = 0; i < threads; ++i) {
+      stats->rays += jobs[i].stats.rays; stats->node_visits += jobs[i].stats.node_visits;
+      stats->iterations += jobs[i].stats.iterations; stats->hits += jobs[i].stats.hits;
+    }
+  }
+  free(jobs); free(tids);
+  return 0;
+}
+
+/* TreadedRenderer::RenderFrame exactly as written (ppu_renderer.cpp:121-144) */
+int yvo_render_threaded_ref(const yv_vox_node *nodes, uint32_t node_count, yv_node_id root,
+                            const yvo_camera *cam, uint8_t *rgba) {
+  const int ThreadNum = 4;
+  int ystep = cam->height / ThreadNum;
+  return yvo_render(nodes, node_count, root, cam, NULL, 0, ystep * ThreadNum, ThreadNum,
+                    NULL, NULL, NULL, rgba, NULL, NULL);
+}
+
+int yvo_trace_ray(const yv_vox_node *nodes, uint32_t node_count, yv_node_id root,
+                  const float pos[3], const float dir[3],
+                  uint32_t *hit_node, int32_t *hit_child, float *hit_t) {
+  trace_ctx c;
+  memset(&c, 0, sizeof c);
+  c.nodes = nodes; c.count = node_count;
+  int hit = trace_ray(&c, root, v3_from(pos), v3_from(dir));
+  if (hit_node)  *hit_node = hit ? c.node : YV_MISS_NODE;
+  if (hit_child) *hit_child = hit ? c.child : YV_MISS_CHILD;
+  if (hit_t)     *hit_t = hit ? c.t : 0.0f;
+  return hit;
+}
+
+/* SVOData::Load (cell/svodata.h:31-50): root, two discarded words, count, raw nodes. */
+int yvo_load_vox(const char *path, yv_node_id *root, uint32_t *count, yv_vox_node **nodes) {
+  FILE *f = fopen(path, "rb");
+  if (!f) return -1;
+  uint32_t hdr[4];
+  if (fread(hdr, 4, 4, f) != 4) { fclose(f); return -2; }
+  *root = hdr[0];
+  *count = hdr[3];
+  *nodes = (yv_vox_node *)malloc((size_t)hdr[3] * sizeof(yv_vox_node) + 1);
+  if (!*nodes) { fclose(f); return -3; }
+  size_t got = fread(*nodes, sizeof(yv_vox_node), hdr[3], f);
+  fclose(f);
+  if (got != hdr[3]) { free(*nodes); *nodes = NULL; return -4; }
+  return 0;
+}
+
+void yvo_free(void *p) { free(p); }

@@ -1,0 +1,91 @@
+/* yv_oracle.h — CPU oracle for the SVO ray-caster path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This is a plain-C restatement of the reference's CPU tracer. Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it;
+ * the product (yoxel-voxel_b200/) never links, imports or calls anything in oracle/.
+ *
+ * PARITY UNPINNED: the reference snapshot ships no golden vectors, no scene files and no
+ * test for this path, and its own tracer does not compile (the cpp/ directory with
+ * trace_utils.h, vox_node.h, shader.h, rdd.h is absent — SURVEY.md §0.2, §8c). The oracle
+ * is therefore validated independently (hand-computed rays, a brute-force voxel-grid
+ * marcher, structural properties — see tests/test_oracle_*.py), not against reference output.
+ */
+#ifndef YV_ORACLE_H
+#define YV_ORACLE_H
+
+#include "../include/yv_format.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* camera state of RendererBase (cell/renderer_base.h:7-47) */
+typedef struct yvo_camera {
+  float pos[3];
+  float dir[3];
+  float up[3];
+  float fov_deg;      /* horizontal, degrees; default 70 (renderer_base.h:25) */
+  int32_t width;
+  int32_t height;
+} yvo_camera;
+
+/* RayDirData{dir0,du,dv} (cell/renderer_base.h:50-61) */
+typedef struct yvo_raydir {
+  float dir0[3];
+  float du[3];
+  float dv[3];
+} yvo_raydir;
+
+/* secondary-ray options (BASELINE config 4); all zero = primary + Lambert only */
+typedef struct yvo_secondary {
+  int32_t shadow;     /* 1: one shadow ray from the hit point towards light_pos            */
+  int32_t ao_samples; /* 0..16 cosine-weighted hemisphere rays                             */
+  uint32_t seed;      /* per-pixel hash seed                                               */
+  float light_pos[3]; /* light used for shadow + Lambert when `shadow` is set              */
+  float voxel_size;   /* origin offset along the normal (one voxel = 2^-depth)             */
+  float ao_max_t;     /* AO rays count as occluded only if they hit within this distance   */
+} yvo_secondary;
+
+typedef struct yvo_stats {
+  uint64_t rays;         /* rays traced (primary + secondary)                              */
+  uint64_t node_visits;  /* executions of the node fetch at ppu_renderer.cpp:23            */
+  uint64_t iterations;   /* child-loop iterations (leaf test at ppu_renderer.cpp:27)       */
+  uint64_t hits;         /* primary rays that hit a leaf                                   */
+} yvo_stats;
+
+void yvo_init_ray_dir(const yvo_camera *cam, yvo_raydir *out);
+
+/* Render rows [y0,y1) of the frame with `threads` horizontal strips
+ * (SimpleRenderer when threads==1, TreadedRenderer's strip split otherwise;
+ * the last strip takes the remainder rows so that every row in [y0,y1) is rendered).
+ * Output arrays are full-frame sized (width*height); any may be NULL.                      */
+int yvo_render(const yv_vox_node *nodes, uint32_t node_count, yv_node_id root,
+               const yvo_camera *cam, const yvo_secondary *sec,
+               int32_t y0, int32_t y1, int32_t threads,
+               uint32_t *hit_node, int32_t *hit_child, float *hit_t,
+               uint8_t *rgba, uint32_t *visits_per_ray, yvo_stats *stats);
+
+/* Reference quirk mode: TreadedRenderer exactly as written (4 strips of H/4 rows, rows
+ * 4*(H/4)..H-1 left untouched; ppu_renderer.cpp:129-142). rgba must be pre-filled by caller. */
+int yvo_render_threaded_ref(const yv_vox_node *nodes, uint32_t node_count, yv_node_id root,
+                            const yvo_camera *cam, uint8_t *rgba);
+
+/* Trace one arbitrary ray (DynamicSVO::TraceRay-like; ore/src/main.cpp:125).
+ * Returns 1 on hit. */
+int yvo_trace_ray(const yv_vox_node *nodes, uint32_t node_count, yv_node_id root,
+                  const float pos[3], const float dir[3],
+                  uint32_t *hit_node, int32_t *hit_child, float *hit_t);
+
+/* SimpleShader::Shade restatement, exposed for unit tests */
+void yvo_shade(yv_vox_data data, const float dir[3], float t,
+               const float viewer[3], const float light[3], float visibility, uint8_t out_rgba[4]);
+void yvo_unpack_normal(yv_vox_data data, float n[3]);
+
+/* SVOData::Load (cell/svodata.h:31-50). Caller frees *nodes with yvo_free. */
+int yvo_load_vox(const char *path, yv_node_id *root, uint32_t *count, yv_vox_node **nodes);
+void yvo_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,104 @@
+// yv_emu.cpp — HOST build of the kernel's per-ray code (yoxel-voxel_b200/csrc/trace_core.cuh).
+// TEST INFRASTRUCTURE ONLY: lets the explicit-stack state machine, the packed-record addressing
+// and the shading helpers be checked against the oracle in a container without a GPU. It is never
+// linked into libyv_b200.so and no product path can reach it.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../yoxel-voxel_b200/csrc/trace_core.cuh"
+
+using namespace yv;
+
+namespace {
+struct HostStack {
+  StackEntry e[kMaxStack];
+  int max_sp = 0;
+  void push(int sp, const StackEntry &en) { e[sp] = en; if (sp + 1 > max_sp) max_sp = sp + 1; }
+  StackEntry pop(int sp) const { return e[sp]; }
+};
+struct HostFetch {
+  const Rec *recs;
+  mutable uint64_t fetches = 0;
+  Rec operator()(uint32_t idx) const { ++fetches; return recs[idx]; }
+};
+
+bool trace(const HostFetch &fetch, bool root_valid, HostStack &stk, float ox, float oy, float oz,
+           float dx, float dy, float dz, bool front_only, RayState &s, Rec &rec, uint64_t &steps) {
+  dx = adjust_dir1(dx); dy = adjust_dir1(dy); dz = adjust_dir1(dz);
+  if (!setup_trace(ox, oy, oz, dx, dy, dz, s)) return false;
+  if (!trace_enter_root(s, rec, fetch, root_valid)) return false;
+  for (;;) {
+    ++steps;
+    int r = trace_step(s, rec, fetch, stk, front_only);
+    if (r == kStepHit) return true;
+    if (r == kStepMiss) return false;
+  }
+}
+}  // namespace
+
+extern "C" int yve_render(const uint32_t *records, const uint32_t *leaves, int root_valid,
+                          const float pos[3], const float dir0[3], const float du[3], const float dv[3],
+                          const float light[3], int width, int height,
+                          int shadow, int ao_samples, uint32_t seed, float voxel_size, float ao_max_t,
+                          uint32_t *hit_node, int32_t *hit_child, float *hit_t, uint32_t *rgba,
+                          uint64_t *out_fetches, int *out_max_sp) {
+  const Rec *recs = reinterpret_cast<const Rec *>(records);
+  HostFetch fetch{ recs };
+  HostStack stk;
+  uint64_t steps = 0;
+  const bool sec = shadow || ao_samples > 0;
+  for (int y = 0; y < height; ++y)
+    for (int x = 0; x < width; ++x) {
+      const uint32_t pixel = (uint32_t)y * (uint32_t)width + (uint32_t)x;
+      float dx, dy, dz;
+      primary_dir(dir0, du, dv, x, y, dx, dy, dz);
+      dx = adjust_dir1(dx); dy = adjust_dir1(dy); dz = adjust_dir1(dz);
+      RayState s; Rec rec;
+      uint32_t out = 0, hn = YV_MISS_NODE; int32_t hc = YV_MISS_CHILD; float ht = 0.0f;
+      if (trace(fetch, root_valid != 0, stk, pos[0], pos[1], pos[2], dx, dy, dz, false, s, rec, steps)) {
+        const uint32_t c = s.ch ^ s.flags;
+        hn = rec.orig_id; hc = (int32_t)c; ht = max3f(s.t1x, s.t1y, s.t1z);
+        const uint32_t data = leaves[rec.leaf_base + (uint32_t)YV_POPC(rec.masks & 0xffu & ((1u << c) - 1u))];
+        float nx, ny, nz;
+        unpack_normal(data, nx, ny, nz);
+        const float Px = YV_FADD(pos[0], YV_FMUL(dx, ht)), Py = YV_FADD(pos[1], YV_FMUL(dy, ht)), Pz = YV_FADD(pos[2], YV_FMUL(dz, ht));
+        const float dl = lambert(nx, ny, nz, Px, Py, Pz, light[0], light[1], light[2]);
+        float vis = 1.0f, ao = 1.0f;
+        if (sec) {
+          const float Ox = YV_FADD(Px, YV_FMUL(nx, voxel_size)), Oy = YV_FADD(Py, YV_FMUL(ny, voxel_size)), Oz = YV_FADD(Pz, YV_FMUL(nz, voxel_size));
+          RayState s2; Rec r2;
+          if (shadow) {
+            const float vx = YV_FSUB(light[0], Ox), vy = YV_FSUB(light[1], Oy), vz = YV_FSUB(light[2], Oz);
+            const float len = YV_FSQRT(YV_FADD(YV_FADD(YV_FMUL(vx, vx), YV_FMUL(vy, vy)), YV_FMUL(vz, vz)));
+            if (len > 0 && trace(fetch, root_valid != 0, stk, Ox, Oy, Oz, YV_FDIV(vx, len), YV_FDIV(vy, len), YV_FDIV(vz, len), true, s2, r2, steps)) {
+              const float ts = max3f(s2.t1x, s2.t1y, s2.t1z);
+              if (ts > 0 && ts < len) vis = 0.0f;
+            }
+          }
+          if (ao_samples > 0) {
+            int occ = 0;
+            for (int k = 0; k < ao_samples; ++k) {
+              float ax, ay, az;
+              ao_direction(nx, ny, nz, pixel, (uint32_t)k, seed, ax, ay, az);
+              if (trace(fetch, root_valid != 0, stk, Ox, Oy, Oz, ax, ay, az, true, s2, r2, steps)) {
+                const float ts = max3f(s2.t1x, s2.t1y, s2.t1z);
+                if (ts > 0 && ts < ao_max_t) ++occ;
+              }
+            }
+            ao = YV_FSUB(1.0f, YV_FDIV((float)occ, (float)ao_samples));
+          }
+        }
+        const float k = sec ? YV_FMUL(YV_FADD(YV_SHADE_AMBIENT, YV_FMUL(YV_SHADE_DIFFUSE, YV_FMUL(dl, vis))), ao)
+                            : YV_FADD(YV_SHADE_AMBIENT, YV_FMUL(YV_SHADE_DIFFUSE, YV_FMUL(dl, 1.0f)));
+        out = shade_rgba(data, k);
+      }
+      if (hit_node) hit_node[pixel] = hn;
+      if (hit_child) hit_child[pixel] = hc;
+      if (hit_t) hit_t[pixel] = ht;
+      if (rgba) rgba[pixel] = out;
+    }
+  if (out_fetches) *out_fetches = fetch.fetches;
+  if (out_max_sp) *out_max_sp = stk.max_sp;
+  return 0;
+}

@@ -1,0 +1,373 @@
+"""Host-side mirror of the reference renderer interface over the C ABI (include/yv_b200.h).
+
+Class and method names follow the reference: ``SVOData`` (cell/svodata.h:22-55),
+``ISVORenderer`` setters and ``RenderFrame`` (cell/svorenderer.h:5-24), the CUDA renderer's
+``Render(d_dstBuf)`` / ``SetViewSize`` (demo/SVORenderer.h:8-64) and ``DynamicSVO.TraceRay`` /
+``Save`` / ``nodecount`` (ore/src/main.cpp:119-129). Everything that computes goes through
+``libyv_b200.so``; there is no Python or CPU implementation behind these classes, and loading
+fails loudly when the library has not been built.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+__all__ = [
+    "YVError", "lib", "lib_path", "SVOData", "SVORenderer", "CreateB200Renderer",
+    "pack_voxdata", "device_count", "init_ray_dir", "NODE_DTYPE", "EMPTY_NODE", "FULL_NODE",
+]
+
+EMPTY_NODE = 0x80000000
+FULL_NODE = 0x80000001
+
+# VoxNode (reaction/report/main.tex:46-51): 40 bytes
+NODE_DTYPE = np.dtype([("flags", "<u4"), ("data", "<u4"), ("child", "<u4", (8,))])
+assert NODE_DTYPE.itemsize == 40
+
+
+class YVError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("yv_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libyv_b200.so")
+
+
+_lib = None
+
+
+def lib():
+    """Load libyv_b200.so (built in-tree by __graft_entry__.build() / csrc/Makefile)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise YVError(-100, "libyv_b200.so not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "or `make -C yoxel-voxel_b200/csrc` (there is no fallback implementation)")
+    L = C.CDLL(path)
+    vp, i32, u32, f32 = C.c_void_p, C.c_int, C.c_uint32, C.c_float
+    P = C.POINTER
+    sig = {
+        "yv_last_error": (C.c_char_p, []),
+        "yv_abi_version": (i32, []),
+        "yv_svo_load": (i32, [C.c_char_p, P(vp)]),
+        "yv_svo_from_memory": (i32, [u32, vp, u32, P(vp)]),
+        "yv_svo_save": (i32, [vp, C.c_char_p]),
+        "yv_svo_free": (None, [vp]),
+        "yv_svo_root": (u32, [vp]),
+        "yv_svo_node_count": (u32, [vp]),
+        "yv_svo_depth": (u32, [vp]),
+        "yv_svo_nodes": (vp, [vp]),
+        "yv_svo_build_sphere_fractal": (i32, [i32, i32, P(vp)]),
+        "yv_svo_build_iso_volume": (i32, [i32, u32, i32, i32, P(vp)]),
+        "yv_svo_build_single_sphere": (i32, [i32, i32, i32, i32, i32, C.c_uint8, C.c_uint8, C.c_uint8, P(vp)]),
+        "yv_svo_build_from_dense": (i32, [i32, vp, P(vp)]),
+        "yv_pack_voxdata": (u32, [C.c_uint8, C.c_uint8, C.c_uint8, f32, f32, f32]),
+        "yv_svo_upload": (i32, [vp, i32]),
+        "yv_svo_device_bytes": (C.c_uint64, [vp, i32]),
+        "yv_svo_packed_counts": (i32, [vp, P(u32), P(u32)]),
+        "yv_svo_packed_copy": (i32, [vp, vp, vp]),
+        "yv_renderer_create": (i32, [i32, P(vp)]),
+        "yv_renderer_destroy": (None, [vp]),
+        "yv_set_scene": (i32, [vp, vp]),
+        "yv_set_view_pos": (i32, [vp, P(f32)]),
+        "yv_set_view_dir": (i32, [vp, P(f32)]),
+        "yv_set_view_up": (i32, [vp, P(f32)]),
+        "yv_set_resolution": (i32, [vp, i32, i32]),
+        "yv_get_resolution": (i32, [vp, P(i32), P(i32)]),
+        "yv_set_fov": (i32, [vp, f32]),
+        "yv_get_fov": (i32, [vp, P(f32)]),
+        "yv_render_frame": (i32, [vp, P(vp)]),
+        "yv_render_frame_device": (i32, [vp, vp]),
+        "yv_render_frame_device_async": (i32, [vp, vp]),
+        "yv_sync": (i32, [vp]),
+        "yv_device_framebuffer": (i32, [vp, P(vp)]),
+        "yv_set_rows": (i32, [vp, i32, i32]),
+        "yv_set_secondary": (i32, [vp, i32, i32, u32, P(f32), f32, f32]),
+        "yv_enable_hits": (i32, [vp, i32]),
+        "yv_get_hits": (i32, [vp, vp, vp, vp]),
+        "yv_enable_counters": (i32, [vp, i32]),
+        "yv_get_counters": (i32, [vp, vp]),
+        "yv_last_frame_ms": (f32, [vp]),
+        "yv_last_frame_launches": (i32, [vp]),
+        "yv_set_stream": (i32, [vp, vp]),
+        "yv_set_option": (i32, [vp, C.c_char_p, i32]),
+        "yv_get_option": (i32, [vp, C.c_char_p, P(i32)]),
+        "yv_trace_rays": (i32, [vp, vp, vp, u32, vp, vp, vp]),
+        "yv_ipc_export": (i32, [vp, vp]),
+        "yv_ipc_open": (i32, [i32, vp, P(vp)]),
+        "yv_ipc_close": (i32, [vp]),
+        "yv_init_ray_dir": (i32, [P(f32), P(f32), f32, i32, i32, P(f32), P(f32), P(f32)]),
+        "yv_device_count": (i32, []),
+        "yv_device_name": (i32, [i32, C.c_char_p, C.c_size_t]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    L._yv_signatures = sig
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise YVError(rc, lib().yv_last_error().decode("utf-8", "replace"))
+
+
+def _vec3(v):
+    a = (C.c_float * 3)(*[float(x) for x in v])
+    return a
+
+
+def pack_voxdata(r, g, b, nx, ny, nz):
+    return int(lib().yv_pack_voxdata(int(r), int(g), int(b), float(nx), float(ny), float(nz)))
+
+
+def init_ray_dir(view_dir, up, fov, width, height):
+    """RendererBase::InitRayDir (cell/renderer_base.h:50-61) -> (dir0, du, dv) float32 arrays."""
+    d0, du, dv = (C.c_float * 3)(), (C.c_float * 3)(), (C.c_float * 3)()
+    _check(lib().yv_init_ray_dir(_vec3(view_dir), _vec3(up), float(fov), int(width), int(height), d0, du, dv))
+    return (np.array(d0[:], np.float32), np.array(du[:], np.float32), np.array(dv[:], np.float32))
+
+
+def device_count():
+    return int(lib().yv_device_count())
+
+
+class SVOData:
+    """SVOData (cell/svodata.h:22-55) plus the DynamicSVO surface the scene scripts use."""
+
+    def __init__(self, handle=None):
+        self._h = C.c_void_p(handle) if handle else C.c_void_p()
+
+    # -- construction ------------------------------------------------------------------------
+    def Load(self, fn):                                   # svodata.h:31
+        self._release()
+        _check(lib().yv_svo_load(os.fsencode(fn), C.byref(self._h)))
+        return self
+
+    def Save(self, fn):                                   # ore/src/main.cpp:123
+        _check(lib().yv_svo_save(self._h, os.fsencode(fn)))
+
+    @classmethod
+    def FromNodes(cls, root, nodes):
+        nodes = np.ascontiguousarray(nodes, dtype=NODE_DTYPE)
+        s = cls()
+        _check(lib().yv_svo_from_memory(int(root), nodes.ctypes.data_as(C.c_void_p), len(nodes), C.byref(s._h)))
+        return s
+
+    @classmethod
+    def SphereFractal(cls, depth, threads=0):             # gen_spheres.py
+        s = cls()
+        _check(lib().yv_svo_build_sphere_fractal(int(depth), int(threads or os.cpu_count() or 1), C.byref(s._h)))
+        return s
+
+    @classmethod
+    def IsoVolume(cls, depth, seed=219, iso_level=200, threads=0):   # gen_largevol.py
+        s = cls()
+        _check(lib().yv_svo_build_iso_volume(int(depth), int(seed), int(iso_level),
+                                             int(threads or os.cpu_count() or 1), C.byref(s._h)))
+        return s
+
+    @classmethod
+    def SingleSphere(cls, depth, center, radius, color=(128, 128, 255)):
+        s = cls()
+        _check(lib().yv_svo_build_single_sphere(int(depth), int(center[0]), int(center[1]), int(center[2]),
+                                                int(radius), int(color[0]), int(color[1]), int(color[2]),
+                                                C.byref(s._h)))
+        return s
+
+    @classmethod
+    def FromDense(cls, vox):
+        vox = np.ascontiguousarray(vox, dtype=np.uint32)
+        n = vox.shape[0]
+        assert vox.shape == (n, n, n) and n & (n - 1) == 0, "dense grid must be a power-of-two cube [z][y][x]"
+        s = cls()
+        _check(lib().yv_svo_build_from_dense(int(n).bit_length() - 1, vox.ctypes.data_as(C.c_void_p), C.byref(s._h)))
+        return s
+
+    # -- accessors ---------------------------------------------------------------------------
+    def GetRoot(self):                                    # svodata.h:52
+        return int(lib().yv_svo_root(self._h))
+
+    @property
+    def nodecount(self):                                  # ore/src/main.cpp:126
+        return int(lib().yv_svo_node_count(self._h))
+
+    @property
+    def depth(self):
+        return int(lib().yv_svo_depth(self._h))
+
+    def nodes(self):
+        """Copy of the host node pool as a structured array (reference layout)."""
+        n = self.nodecount
+        out = np.zeros(n, dtype=NODE_DTYPE)
+        if n:
+            C.memmove(out.ctypes.data, lib().yv_svo_nodes(self._h), n * 40)
+        return out
+
+    def packed(self):
+        nr, nl = C.c_uint32(), C.c_uint32()
+        _check(lib().yv_svo_packed_counts(self._h, C.byref(nr), C.byref(nl)))
+        recs = np.zeros((nr.value, 4), dtype=np.uint32)
+        leaves = np.zeros(nl.value, dtype=np.uint32)
+        _check(lib().yv_svo_packed_copy(self._h, recs.ctypes.data_as(C.c_void_p), leaves.ctypes.data_as(C.c_void_p)))
+        return recs, leaves
+
+    def Upload(self, device=0):                           # CudaSVO::Update
+        _check(lib().yv_svo_upload(self._h, int(device)))
+        return int(lib().yv_svo_device_bytes(self._h, int(device)))
+
+    def _release(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().yv_svo_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+
+class SVORenderer:
+    """ISVORenderer (cell/svorenderer.h:5-24) + the CUDA SVORenderer extras (demo/SVORenderer.h)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        self._scene = None
+        self.device = int(device)
+        _check(lib().yv_renderer_create(self.device, C.byref(self._h)))
+
+    def SetScene(self, svo):                              # svorenderer.h:12
+        self._scene = svo
+        _check(lib().yv_set_scene(self._h, svo._h if svo is not None else None))
+
+    def SetViewPos(self, pos):                            # :14
+        _check(lib().yv_set_view_pos(self._h, _vec3(pos)))
+
+    def SetViewDir(self, d):                              # :15
+        _check(lib().yv_set_view_dir(self._h, _vec3(d)))
+
+    def SetViewUp(self, up):                              # :16
+        _check(lib().yv_set_view_up(self._h, _vec3(up)))
+
+    def SetResolution(self, width, height):               # :18
+        _check(lib().yv_set_resolution(self._h, int(width), int(height)))
+
+    SetViewSize = SetResolution                           # demo/SVORenderer.h:20
+
+    def GetResolution(self):                              # :19
+        w, h = C.c_int(), C.c_int()
+        _check(lib().yv_get_resolution(self._h, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def SetFOV(self, fov):                                # :21
+        _check(lib().yv_set_fov(self._h, float(fov)))
+
+    def GetFOV(self):                                     # demo/SVORenderer.h:23
+        f = C.c_float()
+        _check(lib().yv_get_fov(self._h, C.byref(f)))
+        return f.value
+
+    def RenderFrame(self):
+        """const Color32* RenderFrame() (:23): returns an (H, W, 4) uint8 view of the renderer-owned
+        pinned host buffer, or None when no scene is set (the reference returns NULL)."""
+        p = C.c_void_p()
+        rc = lib().yv_render_frame(self._h, C.byref(p))
+        if rc == -5:
+            return None
+        _check(rc)
+        w, h = self.GetResolution()
+        buf = (C.c_uint8 * (w * h * 4)).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.uint8).reshape(h, w, 4)
+
+    def Render(self, d_dst_ptr, sync=True):               # demo/SVORenderer.h:36
+        fn = lib().yv_render_frame_device if sync else lib().yv_render_frame_device_async
+        _check(fn(self._h, C.c_void_p(int(d_dst_ptr))))
+
+    def Sync(self):
+        _check(lib().yv_sync(self._h))
+
+    def DeviceFramebuffer(self):
+        p = C.c_void_p()
+        _check(lib().yv_device_framebuffer(self._h, C.byref(p)))
+        return p.value
+
+    def SetRows(self, y0, y1):
+        _check(lib().yv_set_rows(self._h, int(y0), int(y1)))
+
+    def SetSecondary(self, shadow=0, ao_samples=0, seed=1, light_pos=(0.5, 0.5, 1.0), voxel_size=0.0, ao_max_t=0.05):
+        _check(lib().yv_set_secondary(self._h, int(shadow), int(ao_samples), int(seed), _vec3(light_pos),
+                                      float(voxel_size), float(ao_max_t)))
+
+    def EnableHits(self, on=True):
+        _check(lib().yv_enable_hits(self._h, 1 if on else 0))
+
+    def GetHits(self):
+        w, h = self.GetResolution()
+        node = np.zeros(w * h, dtype=np.uint32)
+        child = np.zeros(w * h, dtype=np.int32)
+        t = np.zeros(w * h, dtype=np.float32)
+        _check(lib().yv_get_hits(self._h, node.ctypes.data_as(C.c_void_p), child.ctypes.data_as(C.c_void_p),
+                                 t.ctypes.data_as(C.c_void_p)))
+        return node.reshape(h, w), child.reshape(h, w), t.reshape(h, w)
+
+    def EnableCounters(self, on=True):
+        _check(lib().yv_enable_counters(self._h, 1 if on else 0))
+
+    def GetCounters(self):
+        w, h = self.GetResolution()
+        c = np.zeros(w * h, dtype=np.uint32)
+        _check(lib().yv_get_counters(self._h, c.ctypes.data_as(C.c_void_p)))
+        c = c.reshape(h, w)
+        return c & 0xFFFF, c >> 16
+
+    def LastFrameMs(self):
+        return float(lib().yv_last_frame_ms(self._h))
+
+    def LastFrameLaunches(self):
+        return int(lib().yv_last_frame_launches(self._h))
+
+    def SetStream(self, cuda_stream_ptr):
+        _check(lib().yv_set_stream(self._h, C.c_void_p(int(cuda_stream_ptr)) if cuda_stream_ptr else None))
+
+    def SetOption(self, name, value):
+        _check(lib().yv_set_option(self._h, name.encode(), int(value)))
+
+    def GetOption(self, name):
+        v = C.c_int()
+        _check(lib().yv_get_option(self._h, name.encode(), C.byref(v)))
+        return v.value
+
+    def TraceRays(self, pos, dirs):                       # DynamicSVO::TraceRay, batched
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+        dirs = np.ascontiguousarray(dirs, dtype=np.float32).reshape(-1, 3)
+        n = len(pos)
+        node = np.zeros(n, dtype=np.uint32)
+        child = np.zeros(n, dtype=np.int32)
+        t = np.zeros(n, dtype=np.float32)
+        _check(lib().yv_trace_rays(self._h, pos.ctypes.data_as(C.c_void_p), dirs.ctypes.data_as(C.c_void_p), n,
+                                   node.ctypes.data_as(C.c_void_p), child.ctypes.data_as(C.c_void_p),
+                                   t.ctypes.data_as(C.c_void_p)))
+        return node, child, t
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().yv_renderer_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def CreateB200Renderer(device=0):
+    """Factory in the style of CreateSimpleRenderer / CreateThreadedRenderer (cell/svorenderer.h:26-30)."""
+    return SVORenderer(device)

@@ -1,0 +1,248 @@
+// trace_core.cuh — per-ray arithmetic of the SVO ray caster: ray generation, slab set-up,
+// iterative (explicit-stack) octree descent over the packed records, VoxData decode and shading.
+//
+// Every float operation that can influence a traversal decision or a pixel value goes through
+// YV_F* wrappers: on the device they are the round-to-nearest intrinsics (__fadd_rn, ... — never
+// contracted into FMA), on the host (tests/emu build only, to check the state machine without a
+// GPU) they are plain operators compiled with -ffp-contract=off. Divide and square root are the
+// IEEE correctly-rounded forms on both sides, so hit ids are bit-exact against the CPU oracle.
+//
+// Reference behaviour restated here (paths relative to the znah/yoxel-voxel tree):
+//   ray generation ...... cell/ppu_renderer.cpp:56-57
+//   AdjustDir ........... reaction/report/voxel.tex:316-318
+//   SetupTrace .......... reaction/report/voxel.tex:319-326, cell/spu/trace_spu.c_:84-93
+//   FindFirstChild ...... cell/spu/trace_spu.cpp:48-68
+//   GoNext .............. cell/spu/trace_spu.cpp:70-93
+//   RecTrace ............ cell/ppu_renderer.cpp:18-41  (recursion -> explicit stack, see trace_step)
+//   Shade ............... include/yv_format.h (body absent from the snapshot)
+#pragma once
+
+#include <cstdint>
+#include <cmath>
+
+#include "../../include/yv_format.h"
+
+#if defined(__CUDACC__)
+#define YV_HD __host__ __device__ __forceinline__
+#else
+#define YV_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define YV_FADD(a, b) __fadd_rn((a), (b))
+#define YV_FSUB(a, b) __fsub_rn((a), (b))
+#define YV_FMUL(a, b) __fmul_rn((a), (b))
+#define YV_FDIV(a, b) __fdiv_rn((a), (b))
+#define YV_FSQRT(a)   __fsqrt_rn((a))
+#define YV_POPC(a)    __popc((a))
+#else
+#define YV_FADD(a, b) ((a) + (b))
+#define YV_FSUB(a, b) ((a) - (b))
+#define YV_FMUL(a, b) ((a) * (b))
+#define YV_FDIV(a, b) ((a) / (b))
+#define YV_FSQRT(a)   sqrtf((a))
+#define YV_POPC(a)    __builtin_popcount((a))
+#endif
+
+namespace yv {
+
+constexpr int kMaxStack = 23;          // supports trees up to 24 levels below the root
+
+struct Rec { uint32_t child_base, leaf_base, masks, orig_id; };   // == PackedRecord == uint4
+
+struct RayState {
+  float t1x, t1y, t1z;   // slab entry parameters of the current child cube
+  float t2x, t2y, t2z;   // slab exit parameters
+  uint32_t idx;          // packed index of the current node
+  uint32_t ch;           // logical (mirrored-space) child index 0..7
+  uint32_t flags;        // dirFlags: axes along which the ray was mirrored
+  int sp;                // stack entries in use
+};
+
+enum : int { kStepContinue = 0, kStepHit = 1, kStepMiss = 2 };
+
+YV_HD float max3f(float a, float b, float c) { float m = a > b ? a : b; return m > c ? m : c; }
+YV_HD float min3f(float a, float b, float c) { float m = a < b ? a : b; return m < c ? m : c; }
+
+// dir = normalized(dir0 + du*x + dv*y); AdjustDir(dir)      (ppu_renderer.cpp:56-57)
+YV_HD void primary_dir(const float dir0[3], const float du[3], const float dv[3], int x, int y,
+                       float &dx, float &dy, float &dz) {
+  const float fx = (float)x, fy = (float)y;
+  float ax = YV_FADD(YV_FADD(dir0[0], YV_FMUL(du[0], fx)), YV_FMUL(dv[0], fy));
+  float ay = YV_FADD(YV_FADD(dir0[1], YV_FMUL(du[1], fx)), YV_FMUL(dv[1], fy));
+  float az = YV_FADD(YV_FADD(dir0[2], YV_FMUL(du[2], fx)), YV_FMUL(dv[2], fy));
+  float n = YV_FSQRT(YV_FADD(YV_FADD(YV_FMUL(ax, ax), YV_FMUL(ay, ay)), YV_FMUL(az, az)));
+  dx = YV_FDIV(ax, n); dy = YV_FDIV(ay, n); dz = YV_FDIV(az, n);
+}
+
+YV_HD float adjust_dir1(float d) { return fabsf(d) < YV_DIR_EPS ? copysignf(YV_DIR_EPS, d) : d; }
+
+// SetupTrace: mirror negative axes, slab parameters of the unit cube. Returns max(t1) < min(t2).
+YV_HD bool setup_trace(float px, float py, float pz, float dx, float dy, float dz, RayState &s) {
+  uint32_t f = 0;
+  if (dx < 0) { px = YV_FSUB(1.0f, px); dx = -dx; f |= 1u; }
+  if (dy < 0) { py = YV_FSUB(1.0f, py); dy = -dy; f |= 2u; }
+  if (dz < 0) { pz = YV_FSUB(1.0f, pz); dz = -dz; f |= 4u; }
+  s.t1x = YV_FDIV(YV_FSUB(0.0f, px), dx); s.t2x = YV_FDIV(YV_FSUB(1.0f, px), dx);
+  s.t1y = YV_FDIV(YV_FSUB(0.0f, py), dy); s.t2y = YV_FDIV(YV_FSUB(1.0f, py), dy);
+  s.t1z = YV_FDIV(YV_FSUB(0.0f, pz), dz); s.t2z = YV_FDIV(YV_FSUB(1.0f, pz), dz);
+  s.flags = f;
+  s.sp = 0;
+  return max3f(s.t1x, s.t1y, s.t1z) < min3f(s.t2x, s.t2y, s.t2z);
+}
+
+// FindFirstChild: narrow (t1,t2) to the first child's interval and return its logical index.
+YV_HD void find_first_child(RayState &s) {
+  const float tmx = YV_FMUL(0.5f, YV_FADD(s.t1x, s.t2x));
+  const float tmy = YV_FMUL(0.5f, YV_FADD(s.t1y, s.t2y));
+  const float tmz = YV_FMUL(0.5f, YV_FADD(s.t1z, s.t2z));
+  const float te = max3f(s.t1x, s.t1y, s.t1z);
+  uint32_t ch = 0;
+  if (te > tmx) { ch |= 1u; s.t1x = tmx; } else s.t2x = tmx;
+  if (te > tmy) { ch |= 2u; s.t1y = tmy; } else s.t2y = tmy;
+  if (te > tmz) { ch |= 4u; s.t1z = tmz; } else s.t2z = tmz;
+  s.ch = ch;
+}
+
+// Explicit stack entry: the parent's state *after* its GoNext, i.e. what the recursion would
+// resume with when RecTrace(child) returns false (ppu_renderer.cpp:35-38). An entry is pushed
+// only if the parent still has a sibling to visit, so a pop never lands on an exhausted node.
+struct StackEntry { float t1x, t1y, t1z; uint32_t idx; float t2x, t2y, t2z; uint32_t ch; };
+
+// One iteration of RecTrace's child loop, with the recursion unrolled onto `stk`.
+//   front_only = false : reference behaviour (leaf test precedes the child's t2 > 0 test,
+//                        so a leaf behind the origin can be reported with t < 0 — SURVEY §8a10)
+//   front_only = true  : secondary rays: a leaf counts only if its own min(t2) > 0
+// (a run-time flag, so primary and secondary rays of one warp share a single instruction stream)
+// fetch(idx) returns the packed record; each call is one node fetch.
+template <class Fetch, class Stack>
+YV_HD int trace_step(RayState &s, Rec &rec, const Fetch &fetch, Stack &stk, const bool front_only) {
+  const uint32_t c = s.ch ^ s.flags;
+  const uint32_t bit = 1u << c;
+  const float t2min = min3f(s.t2x, s.t2y, s.t2z);
+  if ((rec.masks & bit) && (!front_only || t2min > 0.0f)) return kStepHit;        // :27-33
+
+  // would RecTrace(child) pass its entry test (:20) and fetch a node?
+  const bool descend = (((rec.masks >> 8) & bit) != 0u) && (t2min > 0.0f);
+
+  // GoNext on the current state (:38), needed by both the push and the plain advance
+  const uint32_t e = (s.t2x > s.t2y) ? ((s.t2y < s.t2z) ? 1u : 2u) : ((s.t2x < s.t2z) ? 0u : 2u);
+  const bool can_adv = (s.ch & (1u << e)) == 0u;
+  const float a = e == 0u ? s.t1x : (e == 1u ? s.t1y : s.t1z);
+  const float b = e == 0u ? s.t2x : (e == 1u ? s.t2y : s.t2z);
+  const float nb = YV_FADD(b, YV_FSUB(b, a));          // t2[e] += (t2[e] - t1[e])
+  const float n1x = e == 0u ? b : s.t1x, n1y = e == 1u ? b : s.t1y, n1z = e == 2u ? b : s.t1z;
+  const float n2x = e == 0u ? nb : s.t2x, n2y = e == 1u ? nb : s.t2y, n2z = e == 2u ? nb : s.t2z;
+  const uint32_t nch = s.ch ^ (1u << e);
+
+  if (descend) {
+    if (can_adv) {
+      StackEntry en = { n1x, n1y, n1z, s.idx, n2x, n2y, n2z, nch };
+      stk.push(s.sp, en);
+      ++s.sp;
+    }
+    s.idx = rec.child_base + (uint32_t)YV_POPC((rec.masks >> 8) & (bit - 1u));
+    rec = fetch(s.idx);                                                             // :23
+    find_first_child(s);                                                            // :24
+    return kStepContinue;
+  }
+  if (can_adv) {
+    s.t1x = n1x; s.t1y = n1y; s.t1z = n1z; s.t2x = n2x; s.t2y = n2y; s.t2z = n2z; s.ch = nch;
+    return kStepContinue;
+  }
+  if (s.sp == 0) return kStepMiss;
+  --s.sp;
+  const StackEntry en = stk.pop(s.sp);
+  s.t1x = en.t1x; s.t1y = en.t1y; s.t1z = en.t1z; s.t2x = en.t2x; s.t2y = en.t2y; s.t2z = en.t2z;
+  s.idx = en.idx; s.ch = en.ch;
+  rec = fetch(s.idx);              // re-fetch of the parent (not an algorithmic node visit)
+  return kStepContinue;
+}
+
+// Entry test of RecTrace(root): the caller has run setup_trace. Returns false on an immediate miss.
+template <class Fetch>
+YV_HD bool trace_enter_root(RayState &s, Rec &rec, const Fetch &fetch, bool root_valid) {
+  if (!root_valid || min3f(s.t2x, s.t2y, s.t2z) <= 0.0f) return false;               // :20
+  s.idx = 0u;
+  rec = fetch(0u);
+  find_first_child(s);
+  return true;
+}
+
+// ---- VoxData decode + shading (spec: include/yv_format.h) -----------------------------------
+
+YV_HD void unpack_normal(uint32_t data, float &nx, float &ny, float &nz) {
+  float fx = YV_FSUB(YV_FDIV((float)((data >> 16) & 255u), 127.5f), 1.0f);
+  float fy = YV_FSUB(YV_FDIV((float)((data >> 24) & 255u), 127.5f), 1.0f);
+  float fz = YV_FSUB(YV_FSUB(1.0f, fabsf(fx)), fabsf(fy));
+  if (fz < 0) {
+    float ox = YV_FMUL(YV_FSUB(1.0f, fabsf(fy)), fx >= 0 ? 1.0f : -1.0f);
+    float oy = YV_FMUL(YV_FSUB(1.0f, fabsf(fx)), fy >= 0 ? 1.0f : -1.0f);
+    fx = ox; fy = oy;
+  }
+  float len = YV_FSQRT(YV_FADD(YV_FADD(YV_FMUL(fx, fx), YV_FMUL(fy, fy)), YV_FMUL(fz, fz)));
+  nx = YV_FDIV(fx, len); ny = YV_FDIV(fy, len); nz = YV_FDIV(fz, len);
+}
+
+// Lambert term max(0, n . normalize(light - P))
+YV_HD float lambert(float nx, float ny, float nz, float Px, float Py, float Pz,
+                    float lx, float ly, float lz) {
+  float vx = YV_FSUB(lx, Px), vy = YV_FSUB(ly, Py), vz = YV_FSUB(lz, Pz);
+  float len = YV_FSQRT(YV_FADD(YV_FADD(YV_FMUL(vx, vx), YV_FMUL(vy, vy)), YV_FMUL(vz, vz)));
+  float Lx = 0.0f, Ly = 0.0f, Lz = 0.0f;
+  if (len > 0) { Lx = YV_FDIV(vx, len); Ly = YV_FDIV(vy, len); Lz = YV_FDIV(vz, len); }
+  float ndl = YV_FADD(YV_FADD(YV_FMUL(nx, Lx), YV_FMUL(ny, Ly)), YV_FMUL(nz, Lz));
+  return ndl > 0 ? ndl : 0.0f;
+}
+
+// colour * k -> RGBA8 word in memory order R,G,B,A (little-endian: R in bits 0..7)
+YV_HD uint32_t shade_rgba(uint32_t data, float k) {
+  const uint32_t r5 = (data >> 11) & 31u, g6 = (data >> 5) & 63u, b5 = data & 31u;
+  const uint32_t c0 = (r5 << 3) | (r5 >> 2), c1 = (g6 << 2) | (g6 >> 4), c2 = (b5 << 3) | (b5 >> 2);
+  float v0 = floorf(YV_FADD(YV_FMUL((float)c0, k), 0.5f));
+  float v1 = floorf(YV_FADD(YV_FMUL((float)c1, k), 0.5f));
+  float v2 = floorf(YV_FADD(YV_FMUL((float)c2, k), 0.5f));
+  const uint32_t o0 = (uint32_t)(v0 < 255.0f ? v0 : 255.0f);
+  const uint32_t o1 = (uint32_t)(v1 < 255.0f ? v1 : 255.0f);
+  const uint32_t o2 = (uint32_t)(v2 < 255.0f ? v2 : 255.0f);
+  return o0 | (o1 << 8) | (o2 << 16) | 0xff000000u;
+}
+
+// ---- secondary-ray helpers (BASELINE config 4; definition mirrored by oracle/yv_oracle.c) -----
+
+YV_HD uint32_t hash_u32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+
+// unit vector by rejection sampling in a cube of integer lattice points (no transcendentals)
+YV_HD void hash_unit_vector(uint32_t key, float &ux, float &uy, float &uz) {
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t h = hash_u32(key + 0x9e3779b9U * (uint32_t)k);
+    const float x = YV_FSUB((float)(int)(h & 1023u), 511.5f);
+    const float y = YV_FSUB((float)(int)((h >> 10) & 1023u), 511.5f);
+    const float z = YV_FSUB((float)(int)((h >> 20) & 1023u), 511.5f);
+    const float l2 = YV_FADD(YV_FADD(YV_FMUL(x, x), YV_FMUL(y, y)), YV_FMUL(z, z));
+    if (l2 <= 261632.25f && l2 >= 1.0f) {
+      const float l = YV_FSQRT(l2);
+      ux = YV_FDIV(x, l); uy = YV_FDIV(y, l); uz = YV_FDIV(z, l);
+      return;
+    }
+  }
+  ux = 0.0f; uy = 0.0f; uz = 1.0f;
+}
+
+// cosine-weighted AO direction: normalize(n + U), falling back to n when the sum degenerates
+YV_HD void ao_direction(float nx, float ny, float nz, uint32_t pixel, uint32_t sample, uint32_t seed,
+                        float &dx, float &dy, float &dz) {
+  const uint32_t key = hash_u32(pixel * 16u + sample) ^ hash_u32(seed);
+  float ux, uy, uz;
+  hash_unit_vector(key, ux, uy, uz);
+  float x = YV_FADD(nx, ux), y = YV_FADD(ny, uy), z = YV_FADD(nz, uz);
+  const float l2 = YV_FADD(YV_FADD(YV_FMUL(x, x), YV_FMUL(y, y)), YV_FMUL(z, z));
+  if (l2 < 1e-6f) { dx = nx; dy = ny; dz = nz; return; }
+  const float l = YV_FSQRT(l2);
+  dx = YV_FDIV(x, l); dy = YV_FDIV(y, l); dz = YV_FDIV(z, l);
+}
+
+}  // namespace yv

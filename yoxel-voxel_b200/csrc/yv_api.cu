@@ -1,0 +1,668 @@
+// yv_api.cu — C ABI (include/yv_b200.h) over the host-side renderer state and kernel launches.
+//
+// Mirrors RendererBase (cell/renderer_base.h:7-61: camera state, setters, InitRayDir, the
+// renderer-owned colour buffer) and the CUDA host sequence of demo/SVORenderer.cpp:95-149, with
+// the Trace -> ShadeSimple launches fused into one kernel (render_kernels.cuh).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/yv_b200.h"
+#include "render_kernels.cuh"
+#include "svo_host.h"
+#include "svo_pack.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define YV_CUDA(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(YV_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
+  } while (0)
+
+struct DeviceSVO {
+  uint4 *recs = nullptr;
+  uint32_t *leaves = nullptr;
+  size_t n_recs = 0, n_leaves = 0;
+};
+
+}  // namespace
+
+struct yv_svo {
+  yv::HostSVO host;
+  yv::PackedSVO packed;
+  bool packed_ok = false;
+  std::map<int, DeviceSVO> dev;
+  std::mutex mu;
+};
+
+struct yv_renderer {
+  int device = 0;
+  int sm_count = 0;
+  yv_svo *svo = nullptr;
+  // RendererBase state (renderer_base.h:10-18,25)
+  float pos[3] = { 0, 0, 0 }, dir[3] = { 1, 0, 0 }, up[3] = { 0, 0, 1 };
+  float fov = 70.0f;
+  int width = 0, height = 0;
+  int y0 = 0, y1 = 0;
+  bool rows_set = false;
+  // secondary rays
+  int shadow = 0, ao_samples = 0;
+  uint32_t seed = 1;
+  float light[3] = { 0, 0, 0 }, voxel_size = 0.0f, ao_max_t = 0.0f;
+  // buffers
+  uint32_t *d_fb = nullptr;
+  uint8_t *h_fb = nullptr;            // pinned
+  size_t fb_pixels = 0;
+  uint32_t *d_hit_node = nullptr; int32_t *d_hit_child = nullptr; float *d_hit_t = nullptr;
+  uint32_t *d_counters = nullptr;
+  unsigned int *d_tile_counter = nullptr;
+  bool hits = false, counters = false;
+  // launch
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  int launches = 0;
+  // options
+  int opt_smem_nodes = 585;           // four levels: 1 + 8 + 64 + 512
+  int opt_persistent = 0;
+  int opt_refill = 1;
+  int opt_threads = 128;
+};
+
+namespace {
+
+int ensure_packed(yv_svo *svo) {
+  if (svo->packed_ok) return YV_OK;
+  std::string err;
+  if (yv::pack_svo(svo->host, svo->packed, err) != 0) return fail(YV_ERR_FORMAT, err);
+  if ((int)svo->packed.level_start.size() - 1 > yv::kMaxStack + 1)
+    return fail(YV_ERR_FORMAT, "tree deeper than the traversal stack supports");
+  svo->packed_ok = true;
+  return YV_OK;
+}
+
+int ensure_uploaded(yv_svo *svo, int device, DeviceSVO **out) {
+  std::lock_guard<std::mutex> lock(svo->mu);
+  int rc = ensure_packed(svo);
+  if (rc) return rc;
+  auto it = svo->dev.find(device);
+  if (it == svo->dev.end()) {
+    YV_CUDA(cudaSetDevice(device));
+    DeviceSVO d;
+    d.n_recs = svo->packed.records.size();
+    d.n_leaves = svo->packed.leaves.size();
+    YV_CUDA(cudaMalloc(&d.recs, std::max<size_t>(1, d.n_recs) * sizeof(uint4)));
+    YV_CUDA(cudaMalloc(&d.leaves, std::max<size_t>(1, d.n_leaves) * sizeof(uint32_t)));
+    if (d.n_recs)
+      YV_CUDA(cudaMemcpy(d.recs, svo->packed.records.data(), d.n_recs * sizeof(uint4), cudaMemcpyHostToDevice));
+    if (d.n_leaves)
+      YV_CUDA(cudaMemcpy(d.leaves, svo->packed.leaves.data(), d.n_leaves * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    it = svo->dev.emplace(device, d).first;
+  }
+  if (out) *out = &it->second;
+  return YV_OK;
+}
+
+void free_frame_buffers(yv_renderer *r) {
+  cudaSetDevice(r->device);
+  cudaFree(r->d_fb); r->d_fb = nullptr;
+  cudaFreeHost(r->h_fb); r->h_fb = nullptr;
+  cudaFree(r->d_hit_node); cudaFree(r->d_hit_child); cudaFree(r->d_hit_t); cudaFree(r->d_counters);
+  r->d_hit_node = nullptr; r->d_hit_child = nullptr; r->d_hit_t = nullptr; r->d_counters = nullptr;
+  r->fb_pixels = 0;
+}
+
+int ensure_frame_buffers(yv_renderer *r) {
+  const size_t n = (size_t)r->width * (size_t)r->height;
+  YV_CUDA(cudaSetDevice(r->device));
+  if (r->fb_pixels != n) {
+    free_frame_buffers(r);
+    YV_CUDA(cudaMalloc(&r->d_fb, std::max<size_t>(1, n) * 4));
+    YV_CUDA(cudaMallocHost(&r->h_fb, std::max<size_t>(1, n) * 4));
+    r->fb_pixels = n;
+  }
+  if (r->hits && !r->d_hit_node) {
+    YV_CUDA(cudaMalloc(&r->d_hit_node, std::max<size_t>(1, n) * 4));
+    YV_CUDA(cudaMalloc(&r->d_hit_child, std::max<size_t>(1, n) * 4));
+    YV_CUDA(cudaMalloc(&r->d_hit_t, std::max<size_t>(1, n) * 4));
+  }
+  if (r->counters && !r->d_counters) YV_CUDA(cudaMalloc(&r->d_counters, std::max<size_t>(1, n) * 4));
+  return YV_OK;
+}
+
+// RendererBase::InitRayDir (cell/renderer_base.h:50-61), float32 with the cg:: operator order
+// (nest/include/geometry/primitives/point.h:416-440,462-499); tan evaluated in double, rounded once.
+void init_ray_dir_raw(const float vdir[3], const float vup[3], float fov, int width, int height,
+                      float dir0[3], float du[3], float dv[3]) {
+  auto norm3 = [](const float v[3], float o[3]) {
+    float d = 0.0f;
+    d += v[0] * v[0]; d += v[1] * v[1]; d += v[2] * v[2];
+    float n = sqrtf(d);
+    o[0] = v[0] / n; o[1] = v[1] / n; o[2] = v[2] / n;
+  };
+  auto cross3 = [](const float a[3], const float b[3], float o[3]) {
+    o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+  };
+  float fwd[3], rightu[3], right[3], upv[3];
+  norm3(vdir, fwd);
+  cross3(fwd, vup, rightu);
+  norm3(rightu, right);
+  cross3(right, fwd, upv);
+  const float half_deg = fov / 2;
+  const float half_rad = half_deg * (float)(3.14159265358979323846 / 180.0);
+  const float da = (float)(std::tan((double)half_rad) / (double)width);
+  const float w = (float)width, h = (float)height;
+  for (int i = 0; i < 3; ++i) {
+    du[i] = (2.0f * right[i]) * da;
+    dv[i] = (-2.0f * upv[i]) * da;
+    const float a = (du[i] * w) / 2.0f;
+    const float b = (dv[i] * h) / 2.0f;
+    dir0[i] = (fwd[i] - a) - b;
+  }
+}
+
+void init_ray_dir(const yv_renderer *r, float dir0[3], float du[3], float dv[3]) {
+  init_ray_dir_raw(r->dir, r->up, r->fov, r->width, r->height, dir0, du, dv);
+}
+
+template <bool HITS, bool SEC, bool COUNT>
+int launch_variant(yv_renderer *r, const yv::RenderParams &p, size_t smem) {
+  if (r->opt_persistent) {
+    constexpr int kThreads = 128;
+    auto kern = yv::render_persistent<HITS, SEC, COUNT, kThreads>;
+    int per_sm = 0;
+    YV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    YV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    const long warps_needed = ((long)p.num_tiles * 64 + 31) / 32;
+    long grid = (long)r->sm_count * per_sm;
+    const long max_useful = (warps_needed + kThreads / 32 - 1) / (kThreads / 32);
+    if (grid > max_useful) grid = std::max(1l, max_useful);
+    YV_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(unsigned int), r->stream));
+    kern<<<(unsigned)grid, kThreads, smem, r->stream>>>(p);
+  } else {
+    auto kern = yv::render_tiles<HITS, SEC, COUNT>;
+    YV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles_x16 = (p.width + 15) / 16;
+    const int tiles_y8 = (p.y1 - p.y0 + 7) / 8;
+    const long grid = (long)tiles_x16 * tiles_y8;
+    if (grid > 0) kern<<<(unsigned)grid, 128, smem, r->stream>>>(p);
+  }
+  YV_CUDA(cudaGetLastError());
+  return YV_OK;
+}
+
+int launch_frame(yv_renderer *r, void *d_rgba) {
+  if (!r->svo) return fail(YV_ERR_NOSCENE, "no scene set");
+  if (r->width <= 0 || r->height <= 0) return fail(YV_ERR_ARG, "resolution not set");
+  DeviceSVO *ds = nullptr;
+  int rc = ensure_uploaded(r->svo, r->device, &ds);
+  if (rc) return rc;
+  rc = ensure_frame_buffers(r);
+  if (rc) return rc;
+  YV_CUDA(cudaSetDevice(r->device));
+
+  yv::RenderParams p;
+  std::memset(&p, 0, sizeof p);
+  p.recs = ds->recs; p.leaves = ds->leaves;
+  p.root_valid = r->svo->packed.root_null ? 0u : 1u;
+  p.smem_nodes = (uint32_t)std::min<size_t>((size_t)std::max(0, r->opt_smem_nodes), ds->n_recs);
+  for (int i = 0; i < 3; ++i) p.pos[i] = r->pos[i];
+  init_ray_dir(r, p.dir0, p.du, p.dv);
+  const bool sec = r->shadow || r->ao_samples > 0;
+  for (int i = 0; i < 3; ++i) p.light[i] = (sec && r->shadow) ? r->light[i] : r->pos[i];
+  p.width = r->width; p.height = r->height;
+  p.y0 = r->rows_set ? std::max(0, r->y0) : 0;
+  p.y1 = r->rows_set ? std::min(r->height, r->y1) : r->height;
+  if (p.y1 < p.y0) p.y1 = p.y0;
+  p.out_rgba = (uint32_t *)d_rgba;
+  p.hit_node = r->d_hit_node; p.hit_child = r->d_hit_child; p.hit_t = r->d_hit_t;
+  p.counters = r->d_counters;
+  p.tile_counter = r->d_tile_counter;
+  p.tiles_x = (p.width + 7) / 8;
+  p.num_tiles = p.tiles_x * ((p.y1 - p.y0 + 7) / 8);
+  p.shadow = r->shadow; p.ao_samples = r->ao_samples; p.seed = r->seed;
+  p.voxel_size = r->voxel_size; p.ao_max_t = r->ao_max_t;
+  const size_t smem = (size_t)p.smem_nodes * sizeof(uint4);
+
+  YV_CUDA(cudaEventRecord(r->ev0, r->stream));
+  const int key = (r->hits ? 4 : 0) | (sec ? 2 : 0) | (r->counters ? 1 : 0);
+  switch (key) {
+    case 0: rc = launch_variant<false, false, false>(r, p, smem); break;
+    case 1: rc = launch_variant<false, false, true>(r, p, smem); break;
+    case 2: rc = launch_variant<false, true, false>(r, p, smem); break;
+    case 3: rc = launch_variant<false, true, true>(r, p, smem); break;
+    case 4: rc = launch_variant<true, false, false>(r, p, smem); break;
+    case 5: rc = launch_variant<true, false, true>(r, p, smem); break;
+    case 6: rc = launch_variant<true, true, false>(r, p, smem); break;
+    default: rc = launch_variant<true, true, true>(r, p, smem); break;
+  }
+  if (rc) return rc;
+  YV_CUDA(cudaEventRecord(r->ev1, r->stream));
+  r->timed = true;
+  r->launches = 1;
+  return YV_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *yv_last_error(void) { return g_err.c_str(); }
+int yv_abi_version(void) { return 1; }
+
+int yv_svo_load(const char *path, yv_svo **out) {
+  if (!path || !out) return fail(YV_ERR_ARG, "null argument");
+  yv_svo *s = new yv_svo;
+  std::string err;
+  int rc = yv::load_vox(path, s->host, err);
+  if (rc) { delete s; return fail(rc <= -10 ? YV_ERR_FORMAT : YV_ERR_IO, err); }
+  *out = s;
+  return YV_OK;
+}
+
+int yv_svo_from_memory(yv_node_id root, const yv_vox_node *nodes, uint32_t count, yv_svo **out) {
+  if (!out || (!nodes && count)) return fail(YV_ERR_ARG, "null argument");
+  yv_svo *s = new yv_svo;
+  s->host.root = root;
+  s->host.nodes.assign(nodes, nodes + count);
+  std::string err;
+  if (yv::validate(s->host, err)) { delete s; return fail(YV_ERR_FORMAT, err); }
+  *out = s;
+  return YV_OK;
+}
+
+int yv_svo_save(const yv_svo *svo, const char *path) {
+  if (!svo || !path) return fail(YV_ERR_ARG, "null argument");
+  std::string err;
+  if (yv::save_vox(path, svo->host, err)) return fail(YV_ERR_IO, err);
+  return YV_OK;
+}
+
+void yv_svo_free(yv_svo *svo) {
+  if (!svo) return;
+  for (auto &kv : svo->dev) {
+    cudaSetDevice(kv.first);
+    cudaFree(kv.second.recs);
+    cudaFree(kv.second.leaves);
+  }
+  delete svo;
+}
+
+yv_node_id yv_svo_root(const yv_svo *svo) { return svo ? svo->host.root : YV_EMPTY_NODE; }
+uint32_t yv_svo_node_count(const yv_svo *svo) { return svo ? (uint32_t)svo->host.nodes.size() : 0u; }
+uint32_t yv_svo_depth(const yv_svo *svo) { return svo ? svo->host.depth : 0u; }
+const yv_vox_node *yv_svo_nodes(const yv_svo *svo) { return svo && !svo->host.nodes.empty() ? svo->host.nodes.data() : nullptr; }
+
+static int finish_build(yv_svo *s, int rc, const std::string &err, yv_svo **out) {
+  if (rc) { delete s; return fail(YV_ERR_ARG, err); }
+  *out = s;
+  return YV_OK;
+}
+
+int yv_svo_build_sphere_fractal(int depth, int threads, yv_svo **out) {
+  if (!out) return fail(YV_ERR_ARG, "null argument");
+  yv_svo *s = new yv_svo; std::string err;
+  return finish_build(s, yv::build_sphere_fractal(depth, threads, s->host, err), err, out);
+}
+int yv_svo_build_iso_volume(int depth, uint32_t seed, int iso_level, int threads, yv_svo **out) {
+  if (!out) return fail(YV_ERR_ARG, "null argument");
+  yv_svo *s = new yv_svo; std::string err;
+  return finish_build(s, yv::build_iso_volume(depth, seed, iso_level, threads, s->host, err), err, out);
+}
+int yv_svo_build_single_sphere(int depth, int cx, int cy, int cz, int radius, uint8_t r, uint8_t g, uint8_t b, yv_svo **out) {
+  if (!out) return fail(YV_ERR_ARG, "null argument");
+  yv_svo *s = new yv_svo; std::string err;
+  return finish_build(s, yv::build_single_sphere(depth, cx, cy, cz, radius, r, g, b, s->host, err), err, out);
+}
+int yv_svo_build_from_dense(int depth, const uint32_t *voxdata, yv_svo **out) {
+  if (!out || !voxdata) return fail(YV_ERR_ARG, "null argument");
+  yv_svo *s = new yv_svo; std::string err;
+  return finish_build(s, yv::build_from_dense(depth, voxdata, s->host, err), err, out);
+}
+uint32_t yv_pack_voxdata(uint8_t r, uint8_t g, uint8_t b, float nx, float ny, float nz) {
+  return yv::pack_voxdata(r, g, b, nx, ny, nz);
+}
+
+int yv_svo_upload(yv_svo *svo, int device) {
+  if (!svo) return fail(YV_ERR_ARG, "null scene");
+  return ensure_uploaded(svo, device, nullptr);
+}
+
+uint64_t yv_svo_device_bytes(const yv_svo *svo, int device) {
+  if (!svo) return 0;
+  auto it = svo->dev.find(device);
+  if (it == svo->dev.end()) return 0;
+  return (uint64_t)it->second.n_recs * 16u + (uint64_t)it->second.n_leaves * 4u;
+}
+
+int yv_svo_packed_counts(yv_svo *svo, uint32_t *records, uint32_t *leaves) {
+  if (!svo) return fail(YV_ERR_ARG, "null scene");
+  std::lock_guard<std::mutex> lock(svo->mu);
+  int rc = ensure_packed(svo);
+  if (rc) return rc;
+  if (records) *records = (uint32_t)svo->packed.records.size();
+  if (leaves) *leaves = (uint32_t)svo->packed.leaves.size();
+  return YV_OK;
+}
+
+int yv_svo_packed_copy(yv_svo *svo, uint32_t *records_out, uint32_t *leaves_out) {
+  if (!svo) return fail(YV_ERR_ARG, "null scene");
+  std::lock_guard<std::mutex> lock(svo->mu);
+  int rc = ensure_packed(svo);
+  if (rc) return rc;
+  if (records_out && !svo->packed.records.empty())
+    std::memcpy(records_out, svo->packed.records.data(), svo->packed.records.size() * 16u);
+  if (leaves_out && !svo->packed.leaves.empty())
+    std::memcpy(leaves_out, svo->packed.leaves.data(), svo->packed.leaves.size() * 4u);
+  return YV_OK;
+}
+
+int yv_init_ray_dir(const float dir[3], const float up[3], float fov_deg, int width, int height,
+                    float dir0[3], float du[3], float dv[3]) {
+  if (!dir || !up || !dir0 || !du || !dv || width <= 0 || height <= 0) return fail(YV_ERR_ARG, "bad argument");
+  init_ray_dir_raw(dir, up, fov_deg, width, height, dir0, du, dv);
+  return YV_OK;
+}
+
+int yv_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int yv_device_name(int device, char *buf, size_t len) {
+  cudaDeviceProp prop;
+  YV_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (buf && len) std::snprintf(buf, len, "%s", prop.name);
+  return YV_OK;
+}
+
+int yv_renderer_create(int device, yv_renderer **out) {
+  if (!out) return fail(YV_ERR_ARG, "null argument");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return fail(YV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  }
+  if (device < 0 || device >= n) return fail(YV_ERR_ARG, "device index out of range");
+  YV_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  YV_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(YV_ERR_CUDA, std::string("device is not sm_100-class: ") + prop.name);
+  yv_renderer *r = new yv_renderer;
+  r->device = device;
+  r->sm_count = prop.multiProcessorCount;
+  cudaError_t e = cudaStreamCreateWithFlags(&r->own_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&r->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&r->ev1);
+  if (e == cudaSuccess) e = cudaMalloc(&r->d_tile_counter, sizeof(unsigned int));
+  if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); yv_renderer_destroy(r); return fail(YV_ERR_CUDA, m); }
+  r->stream = r->own_stream;
+  r->width = 640; r->height = 480;            // renderer_base.h:25
+  *out = r;
+  return YV_OK;
+}
+
+void yv_renderer_destroy(yv_renderer *r) {
+  if (!r) return;
+  cudaSetDevice(r->device);
+  if (r->own_stream) cudaStreamSynchronize(r->own_stream);
+  free_frame_buffers(r);
+  cudaFree(r->d_tile_counter);
+  if (r->ev0) cudaEventDestroy(r->ev0);
+  if (r->ev1) cudaEventDestroy(r->ev1);
+  if (r->own_stream) cudaStreamDestroy(r->own_stream);
+  delete r;
+}
+
+int yv_set_scene(yv_renderer *r, yv_svo *svo) {
+  if (!r) return fail(YV_ERR_ARG, "null renderer");
+  r->svo = svo;
+  return YV_OK;
+}
+
+int yv_set_view_pos(yv_renderer *r, const float pos[3]) {
+  if (!r || !pos) return fail(YV_ERR_ARG, "null argument");
+  for (int i = 0; i < 3; ++i) r->pos[i] = pos[i];
+  return YV_OK;
+}
+int yv_set_view_dir(yv_renderer *r, const float dir[3]) {
+  if (!r || !dir) return fail(YV_ERR_ARG, "null argument");
+  for (int i = 0; i < 3; ++i) r->dir[i] = dir[i];
+  return YV_OK;
+}
+int yv_set_view_up(yv_renderer *r, const float up[3]) {
+  if (!r || !up) return fail(YV_ERR_ARG, "null argument");
+  for (int i = 0; i < 3; ++i) r->up[i] = up[i];
+  return YV_OK;
+}
+
+int yv_set_resolution(yv_renderer *r, int width, int height) {
+  if (!r) return fail(YV_ERR_ARG, "null renderer");
+  if (width <= 0 || height <= 0 || (uint64_t)width * (uint64_t)height > 0x10000000ull)
+    return fail(YV_ERR_ARG, "bad resolution");
+  r->width = width; r->height = height;
+  r->rows_set = false;
+  return YV_OK;
+}
+int yv_get_resolution(const yv_renderer *r, int *width, int *height) {
+  if (!r) return fail(YV_ERR_ARG, "null renderer");
+  if (width) *width = r->width;
+  if (height) *height = r->height;
+  return YV_OK;
+}
+int yv_set_fov(yv_renderer *r, float fov_deg) {
+  if (!r) return fail(YV_ERR_ARG, "null renderer");
+  r->fov = fov_deg;
+  return YV_OK;
+}
+int yv_get_fov(const yv_renderer *r, float *fov_deg) {
+  if (!r || !fov_deg) return fail(YV_ERR_ARG, "null argument");
+  *fov_deg = r->fov;
+  return YV_OK;
+}
+
+int yv_set_rows(yv_renderer *r, int y0, int y1) {
+  if (!r) return fail(YV_ERR_ARG, "null renderer");
+  if (y0 < 0 || y1 < y0) return fail(YV_ERR_ARG, "bad row band");
+  r->y0 = y0; r->y1 = y1; r->rows_set = true;
+  return YV_OK;
+}
+
+int yv_set_secondary(yv_renderer *r, int shadow, int ao_samples, uint32_t seed,
+                     const float light_pos[3], float voxel_size, float ao_max_t) {
+  if (!r) return fail(YV_ERR_ARG, "null renderer");
+  if (ao_samples < 0 || ao_samples > 16) return fail(YV_ERR_ARG, "ao_samples must be 0..16");
+  r->shadow = shadow ? 1 : 0; r->ao_samples = ao_samples; r->seed = seed;
+  if (light_pos) for (int i = 0; i < 3; ++i) r->light[i] = light_pos[i];
+  r->voxel_size = voxel_size; r->ao_max_t = ao_max_t;
+  return YV_OK;
+}
+
+int yv_enable_hits(yv_renderer *r, int enable) {
+  if (!r) return fail(YV_ERR_ARG, "null renderer");
+  r->hits = enable != 0;
+  return YV_OK;
+}
+int yv_enable_counters(yv_renderer *r, int enable) {
+  if (!r) return fail(YV_ERR_ARG, "null renderer");
+  r->counters = enable != 0;
+  return YV_OK;
+}
+
+int yv_render_frame_device_async(yv_renderer *r, void *d_rgba) {
+  if (!r || !d_rgba) return fail(YV_ERR_ARG, "null argument");
+  return launch_frame(r, d_rgba);
+}
+
+int yv_sync(yv_renderer *r) {
+  if (!r) return fail(YV_ERR_ARG, "null renderer");
+  YV_CUDA(cudaSetDevice(r->device));
+  YV_CUDA(cudaStreamSynchronize(r->stream));
+  return YV_OK;
+}
+
+int yv_render_frame_device(yv_renderer *r, void *d_rgba) {
+  int rc = yv_render_frame_device_async(r, d_rgba);
+  if (rc) return rc;
+  return yv_sync(r);
+}
+
+int yv_device_framebuffer(yv_renderer *r, void **d_rgba) {
+  if (!r || !d_rgba) return fail(YV_ERR_ARG, "null argument");
+  int rc = ensure_frame_buffers(r);
+  if (rc) return rc;
+  *d_rgba = r->d_fb;
+  return YV_OK;
+}
+
+int yv_render_frame(yv_renderer *r, const uint8_t **rgba) {
+  if (!r || !rgba) return fail(YV_ERR_ARG, "null argument");
+  *rgba = nullptr;                                     // reference returns NULL on failure
+  if (!r->svo) return fail(YV_ERR_NOSCENE, "no scene set");
+  int rc = ensure_frame_buffers(r);
+  if (rc) return rc;
+  rc = launch_frame(r, r->d_fb);
+  if (rc) return rc;
+  const int y0 = r->rows_set ? std::max(0, r->y0) : 0;
+  const int y1 = r->rows_set ? std::min(r->height, r->y1) : r->height;
+  if (y1 > y0) {
+    const size_t off = (size_t)y0 * r->width * 4, bytes = (size_t)(y1 - y0) * r->width * 4;
+    YV_CUDA(cudaMemcpyAsync(r->h_fb + off, (const uint8_t *)r->d_fb + off, bytes, cudaMemcpyDeviceToHost, r->stream));
+  }
+  YV_CUDA(cudaStreamSynchronize(r->stream));
+  *rgba = r->h_fb;
+  return YV_OK;
+}
+
+int yv_get_hits(yv_renderer *r, uint32_t *node, int32_t *child, float *t) {
+  if (!r) return fail(YV_ERR_ARG, "null renderer");
+  if (!r->hits || !r->d_hit_node) return fail(YV_ERR_ARG, "hit buffers not enabled before the last frame");
+  YV_CUDA(cudaSetDevice(r->device));
+  YV_CUDA(cudaStreamSynchronize(r->stream));
+  const size_t bytes = r->fb_pixels * 4;
+  if (node) YV_CUDA(cudaMemcpy(node, r->d_hit_node, bytes, cudaMemcpyDeviceToHost));
+  if (child) YV_CUDA(cudaMemcpy(child, r->d_hit_child, bytes, cudaMemcpyDeviceToHost));
+  if (t) YV_CUDA(cudaMemcpy(t, r->d_hit_t, bytes, cudaMemcpyDeviceToHost));
+  return YV_OK;
+}
+
+int yv_get_counters(yv_renderer *r, uint32_t *fetches_per_ray) {
+  if (!r || !fetches_per_ray) return fail(YV_ERR_ARG, "null argument");
+  if (!r->counters || !r->d_counters) return fail(YV_ERR_ARG, "counters not enabled before the last frame");
+  YV_CUDA(cudaSetDevice(r->device));
+  YV_CUDA(cudaStreamSynchronize(r->stream));
+  YV_CUDA(cudaMemcpy(fetches_per_ray, r->d_counters, r->fb_pixels * 4, cudaMemcpyDeviceToHost));
+  return YV_OK;
+}
+
+float yv_last_frame_ms(const yv_renderer *r) {
+  if (!r || !r->timed) return -1.0f;
+  cudaSetDevice(r->device);
+  if (cudaEventSynchronize(r->ev1) != cudaSuccess) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventElapsedTime(&ms, r->ev0, r->ev1) != cudaSuccess) return -1.0f;
+  return ms;
+}
+
+int yv_last_frame_launches(const yv_renderer *r) { return r ? r->launches : 0; }
+
+int yv_set_stream(yv_renderer *r, void *cuda_stream) {
+  if (!r) return fail(YV_ERR_ARG, "null renderer");
+  r->stream = cuda_stream ? (cudaStream_t)cuda_stream : r->own_stream;
+  return YV_OK;
+}
+
+int yv_set_option(yv_renderer *r, const char *name, int value) {
+  if (!r || !name) return fail(YV_ERR_ARG, "null argument");
+  std::string n(name);
+  if (n == "smem_nodes") { if (value < 0 || value > 12288) return fail(YV_ERR_ARG, "smem_nodes must be 0..12288"); r->opt_smem_nodes = value; }
+  else if (n == "persistent") r->opt_persistent = value ? 1 : 0;
+  else if (n == "refill") r->opt_refill = value ? 1 : 0;
+  else return fail(YV_ERR_ARG, "unknown option " + n);
+  return YV_OK;
+}
+
+int yv_get_option(const yv_renderer *r, const char *name, int *value) {
+  if (!r || !name || !value) return fail(YV_ERR_ARG, "null argument");
+  std::string n(name);
+  if (n == "smem_nodes") *value = r->opt_smem_nodes;
+  else if (n == "persistent") *value = r->opt_persistent;
+  else if (n == "refill") *value = r->opt_refill;
+  else return fail(YV_ERR_ARG, "unknown option " + n);
+  return YV_OK;
+}
+
+int yv_trace_rays(yv_renderer *r, const float *pos, const float *dir, uint32_t count,
+                  uint32_t *node, int32_t *child, float *t) {
+  if (!r || (!pos && count) || (!dir && count)) return fail(YV_ERR_ARG, "null argument");
+  if (!r->svo) return fail(YV_ERR_NOSCENE, "no scene set");
+  if (count == 0) return YV_OK;
+  DeviceSVO *ds = nullptr;
+  int rc = ensure_uploaded(r->svo, r->device, &ds);
+  if (rc) return rc;
+  YV_CUDA(cudaSetDevice(r->device));
+  float *d_pos = nullptr, *d_dir = nullptr, *d_t = nullptr; uint32_t *d_node = nullptr; int32_t *d_child = nullptr;
+  const size_t n = count;
+  cudaError_t e = cudaMalloc(&d_pos, n * 12);
+  if (e == cudaSuccess) e = cudaMalloc(&d_dir, n * 12);
+  if (e == cudaSuccess) e = cudaMalloc(&d_node, n * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&d_child, n * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&d_t, n * 4);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_pos, pos, n * 12, cudaMemcpyHostToDevice, r->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_dir, dir, n * 12, cudaMemcpyHostToDevice, r->stream);
+  if (e == cudaSuccess) {
+    yv::trace_rays_kernel<<<(unsigned)((n + 127) / 128), 128, 0, r->stream>>>(
+        ds->recs, r->svo->packed.root_null ? 0u : 1u, d_pos, d_dir, count, d_node, d_child, d_t);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess && node) e = cudaMemcpyAsync(node, d_node, n * 4, cudaMemcpyDeviceToHost, r->stream);
+  if (e == cudaSuccess && child) e = cudaMemcpyAsync(child, d_child, n * 4, cudaMemcpyDeviceToHost, r->stream);
+  if (e == cudaSuccess && t) e = cudaMemcpyAsync(t, d_t, n * 4, cudaMemcpyDeviceToHost, r->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(r->stream);
+  cudaFree(d_pos); cudaFree(d_dir); cudaFree(d_node); cudaFree(d_child); cudaFree(d_t);
+  if (e != cudaSuccess) return fail(YV_ERR_CUDA, cudaGetErrorString(e));
+  return YV_OK;
+}
+
+int yv_ipc_export(void *d_ptr, uint8_t handle[64]) {
+  if (!d_ptr || !handle) return fail(YV_ERR_ARG, "null argument");
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  YV_CUDA(cudaIpcGetMemHandle(&h, d_ptr));
+  std::memcpy(handle, &h, 64);
+  return YV_OK;
+}
+
+int yv_ipc_open(int device, const uint8_t handle[64], void **d_ptr) {
+  if (!handle || !d_ptr) return fail(YV_ERR_ARG, "null argument");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, 64);
+  YV_CUDA(cudaSetDevice(device));
+  YV_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return YV_OK;
+}
+
+int yv_ipc_close(void *d_ptr) {
+  if (!d_ptr) return YV_OK;
+  YV_CUDA(cudaIpcCloseMemHandle(d_ptr));
+  return YV_OK;
+}
+
+}  // extern "C"
