@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s and frame ms of the SVO ray caster on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A step is one rendered frame. N=1: BASELINE config 2 (depth-12 sphere fractal, 1920x1080, primary rays
++ Lambert shading, one B200). N>1 (one process per GPU under torchrun): every rank renders one frame
+of a flythrough batch of the same scene (frame f -> GPU f mod N, north_star "by frames for flythrough
+batches") and writes its pixels straight into GPU 0's batch buffer over NVLink: weak scaling.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+NODE_BYTES = 40          # reference node (reaction/report/main.tex:46-51) — roofline unit, SURVEY §8d
+PIXEL_BYTES = 4          # one RGBA8 store
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--depth", type=int, default=12)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--schedule", default="auto", choices=["auto", "tiles", "persistent"])
+    ap.add_argument("--smem-nodes", type=int, default=-1)
+    ap.add_argument("--secondary", action="store_true", help="BASELINE config 4: shadow + 4 AO rays")
+    ap.add_argument("--partition", default="frames", choices=["frames", "tiles"],
+                    help="N>1: one frame per rank (weak) or one frame split into row bands (strong)")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-l2-flush", action="store_true")
+    return ap.parse_args()
+
+
+# camera: eye of cell/main.cpp:25; that file's view direction (-1,-1,-1.5) was written for scene.vox and
+# sees none of the sphere fractal (0 hits), so the z component is flipped to look at the fractal.
+BASE_POS = (0.5, 0.5, 0.3)
+BASE_DIR = (-1.0, -1.0, 1.5)
+UP = (0.0, 0.0, 1.0)
+FOV = 70.0
+
+
+def camera_for(frame):
+    """Deterministic flythrough: frame 0 is the base camera; later frames orbit the eye a little."""
+    if frame == 0:
+        return BASE_POS, BASE_DIR
+    a = 0.35 * frame
+    pos = (BASE_POS[0] + 0.05 * np.sin(a), BASE_POS[1] + 0.05 * (1 - np.cos(a)), BASE_POS[2] + 0.01 * frame)
+    d = (BASE_DIR[0] + 0.2 * np.sin(0.5 * a), BASE_DIR[1] - 0.2 * np.sin(0.3 * a), BASE_DIR[2])
+    return tuple(float(v) for v in pos), tuple(float(v) for v in d)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        rows = [r for (ts, r) in self.rows if t0 - 0.05 <= ts <= t1 + 0.1 and len(r) >= 8] or \
+               [r for (_, r) in self.rows if len(r) >= 8]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = []
+        for i, name in ((4, "hw_slowdown"), (5, "hw_thermal_slowdown"), (6, "sw_thermal_slowdown"), (7, "sw_power_cap")):
+            if any(r[i].lower().startswith("active") for r in rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+def workload_name(a):
+    return ("gen_spheres sphere-fractal SVO depth %d, %dx%d primary rays + Lambert%s" %
+            (a.depth, a.width, a.height, " + shadow + 4 AO" if a.secondary else ""))
+
+
+def oracle_frame(svo_nodes, root, a, frame, threads, want_visits=False):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import yvo
+    pos, d = camera_for(frame)
+    cam = yvo.camera(pos, d, UP, FOV, a.width, a.height)
+    sec = None
+    if a.secondary:
+        sec = yvo.secondary(shadow=1, ao_samples=4, seed=1, light_pos=(0.6, 0.4, 1.2),
+                            voxel_size=1.0 / (1 << a.depth), ao_max_t=0.05)
+    t0 = time.perf_counter()
+    r = yvo.render(svo_nodes, root, cam, sec=sec, threads=threads, want_visits=want_visits)
+    return r, time.perf_counter() - t0
+
+
+def run_reference(a, rank):
+    """--impl reference: the reference's CPU tracer restated (oracle/), all host threads, same config.
+    The reference's own sources do not compile here (missing cpp/ headers), so kind = "port"."""
+    if rank != 0:
+        return
+    import yoxel_voxel_b200 as yv
+    cores = os.cpu_count() or 1
+    svo = yv.SVOData.SphereFractal(a.depth, threads=cores)
+    nodes, root = svo.nodes(), svo.GetRoot()
+    for _ in range(a.warmup):
+        oracle_frame(nodes, root, a, 0, cores)
+    times, rays = [], 0
+    for _ in range(a.steps):
+        r, dt = oracle_frame(nodes, root, a, 0, cores)
+        times.append(dt)
+        rays += r["stats"]["rays"]
+    total = sum(times)
+    val = rays / total / 1e6
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": val, "unit": "Mrays/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "camera": {"pos": BASE_POS, "dir": BASE_DIR, "fov": FOV}},
+        "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                         "sample": "whole %dx%d frame per step, %d row strips (TreadedRenderer split)" % (a.width, a.height, cores)},
+        "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        return run_reference(a, rank)
+
+    import torch
+    import torch.distributed as dist
+    import yoxel_voxel_b200 as yv
+    from yoxel_voxel_b200 import multigpu
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    cores = os.cpu_count() or 1
+
+    # ---- scene: replicated on every GPU ----------------------------------------------------------
+    t0 = time.time()
+    svo = yv.SVOData.SphereFractal(a.depth, threads=max(1, cores // world))
+    build_s = time.time() - t0
+    dev_bytes = svo.Upload(local)
+    n_rec, n_leaf = (x.shape[0] for x in svo.packed())
+
+    r = yv.SVORenderer(local)
+    schedule = a.schedule if a.schedule != "auto" else "tiles"
+    r.SetOption("persistent", 1 if schedule == "persistent" else 0)
+    if a.smem_nodes >= 0:
+        r.SetOption("smem_nodes", a.smem_nodes)
+    r.SetScene(svo)
+    r.SetResolution(a.width, a.height)
+    r.SetViewUp(UP); r.SetFOV(FOV)
+    if a.secondary:
+        r.SetSecondary(shadow=1, ao_samples=4, seed=1, light_pos=(0.6, 0.4, 1.2),
+                       voxel_size=1.0 / (1 << a.depth), ao_max_t=0.05)
+    stream = torch.cuda.current_stream()
+    r.SetStream(stream.cuda_stream)
+
+    # ---- partition ----------------------------------------------------------------------------
+    frame_bytes = a.width * a.height * 4
+    tiles_mode = world > 1 and a.partition == "tiles"
+    if tiles_mode:
+        y0, y1 = multigpu.row_band(rank, world, a.height)
+        r.SetRows(y0, y1)
+        my_frame, my_rays_px = 0, (y1 - y0) * a.width
+        target_bytes = frame_bytes
+    else:
+        y0, y1 = 0, a.height
+        my_frame, my_rays_px = rank, a.width * a.height
+        target_bytes = frame_bytes * world
+    pos, d = camera_for(my_frame)
+    r.SetViewPos(pos); r.SetViewDir(d)
+
+    gather = a.gather if world > 1 else "none"
+    target_ptr, target_obj, local_fb, gather_list = None, None, None, None
+    if world > 1 and gather == "p2p":
+        try:
+            target_ptr, target_obj = multigpu.open_gather_target(dist, rank, world, local, target_bytes)
+        except yv.YVError as e:                       # no IPC on this box: fall back to the NCCL baseline
+            gather = "nccl"
+            if rank == 0:
+                print("p2p gather unavailable (%s); using nccl" % e, file=sys.stderr)
+        flag = torch.tensor([1 if gather == "p2p" else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            gather = "nccl"
+    if world > 1 and gather == "nccl":
+        local_fb = torch.zeros(a.height, a.width, 4, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            gather_list = [torch.zeros_like(local_fb) for _ in range(world)]
+    if world == 1:
+        local_fb = torch.zeros(a.height, a.width, 4, dtype=torch.uint8, device=dev)
+
+    def dst_ptr():
+        if gather == "p2p":
+            return target_ptr + (0 if tiles_mode else rank * frame_bytes)
+        return local_fb.data_ptr()
+
+    def render_step():
+        r.Render(dst_ptr(), sync=False)
+        if gather == "nccl":
+            dist.gather(local_fb, gather_list, dst=0)
+
+    # ---- V-bar for the roofline: the kernel's own node-visit counters on this workload -----------
+    # (tests/test_gpu_parity.py::test_counters_equal_oracle_visits pins them to the oracle's count of
+    # the node fetch at cell/ppu_renderer.cpp:23)
+    r.EnableCounters(True)
+    probe = torch.zeros(a.height, a.width, 4, dtype=torch.uint8, device=dev)
+    r.Render(probe.data_ptr(), sync=True)
+    visits, pops = r.GetCounters()
+    r.EnableCounters(False)
+    vis_sum = int(visits[y0:y1].sum())
+    pop_sum = int(pops[y0:y1].sum())
+    hit_px = int((probe[y0:y1, :, 3] == 255).sum().item())
+    my_px = (y1 - y0) * a.width
+    my_rays = my_px + (5 * hit_px if a.secondary else 0)      # shadow + 4 AO per hit pixel
+    del probe
+
+    flush = None if a.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    warm = max(a.warmup, 3)
+    for _ in range(warm):
+        if flush is not None:
+            flush.zero_()
+        render_step()
+    sync_all()
+
+    # ---- timed region: K frames, CUDA events on the launching stream ------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    sync_all()
+    wall0 = time.time()
+    for i in range(a.steps):
+        if flush is not None:
+            flush.zero_()                           # evict the node pool from L2 between frames (not timed)
+        evs[i][0].record(stream)
+        render_step()
+        evs[i][1].record(stream)
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()                          # the batch on GPU 0 is complete once every rank has stored
+    sync_all()
+    wall1 = time.time()
+    clocks = sampler.stop(wall0, wall1) if sampler else None
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    sums = torch.tensor([float(my_rays), float(my_px), float(vis_sum), float(pop_sum)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)          # max over ranks
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)              # units all ranks processed
+    total_s = float(total_ms.item()) / 1e3
+    rays_step, px_step, vis_step, pop_step = (float(v) for v in sums.tolist())
+    value = rays_step * a.steps / total_s / 1e6
+
+    # ---- e2e: the public host API with host buffers (camera in, RGBA8 frame out) -------------------
+    if world == 1:
+        r.SetStream(0)
+        e2e_t = []
+        for i in range(warm + a.steps):
+            if flush is not None:
+                flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r.SetViewPos(pos); r.SetViewDir(d); r.SetViewUp(UP); r.SetFOV(FOV)      # host camera -> kernel params
+            img = r.RenderFrame()                                                   # launch + D2H (pinned) + sync
+            e2e_t.append(time.perf_counter() - t0)
+        e2e_s = sum(e2e_t[warm:])
+        e2e = {"value": rays_step * a.steps / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 40,
+               "d2h_bytes_per_step": frame_bytes, "ms_per_step": 1e3 * e2e_s / a.steps,
+               "api": "yv_set_view_* + yv_render_frame: host camera in, pinned host RGBA8 frame out",
+               "checksum": int(img[::16, ::16].astype(np.uint64).sum())}
+        r.SetStream(stream.cuda_stream)
+    else:
+        # the timed region already ends with every pixel resident on GPU 0; add rank 0's D2H of the batch
+        d2h_s = 0.0
+        if rank == 0 and gather == "p2p":
+            t0 = time.perf_counter()
+            target_obj.to_host()
+            d2h_s = time.perf_counter() - t0
+        elif rank == 0:
+            t0 = time.perf_counter()
+            torch.stack(gather_list).cpu()
+            d2h_s = time.perf_counter() - t0
+        e2e = {"value": rays_step * a.steps / (total_s + d2h_s * a.steps) / 1e6, "unit": "Mrays/s",
+               "h2d_bytes_per_step": 40 * world, "d2h_bytes_per_step": target_bytes,
+               "api": "yv_render_frame_device into GPU 0's buffer (%s) + D2H of the gathered pixels on rank 0" % gather}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return
+
+    # ---- CPU baseline + parity check (rank 0, N=1): the oracle on the host cores --------------------
+    cpu_baseline, parity = None, None
+    if world == 1 and not a.no_cpu_baseline:
+        nodes, root = svo.nodes(), svo.GetRoot()
+        o, _ = oracle_frame(nodes, root, a, 0, cores, want_visits=True)        # warm run, parity, V-bar cross-check
+        o2, dt = oracle_frame(nodes, root, a, 0, cores)
+        cpu_baseline = {"value": o2["stats"]["rays"] / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                        "sample": "one whole %dx%d frame, %d row strips (%.2f s)" % (a.width, a.height, cores, dt),
+                        "ms_per_frame": 1e3 * dt}
+        gpu_img = r.RenderFrame()
+        parity = {"rgba_identical_to_oracle": bool((gpu_img == o["rgba"]).all()),
+                  "rays_identical": bool(o["stats"]["rays"] == int(rays_step)),
+                  "node_visits_identical": bool(o["stats"]["node_visits"] == int(vis_step))}
+
+    # ---- roofline: algorithmic bytes / measured kernel time vs the measured HBM peak ----------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg_bytes_step = vis_step * NODE_BYTES + px_step * PIXEL_BYTES        # all GPUs
+    kernel_s = total_s / a.steps
+    achieved = alg_bytes_step / world / kernel_s / 1e9                    # per GPU (per launch)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "yv::render_%s" % schedule,
+                "algorithmic_bytes_per_launch": alg_bytes_step / world,
+                "node_visits_per_ray": vis_step / rays_step, "pop_refetches_per_ray": pop_step / rays_step,
+                "kernel_ms": 1e3 * kernel_s}
+
+    line = {
+        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": a.steps, "warmup": warm,
+        "ms_per_step": 1e3 * total_s / a.steps, "higher_is_better": True,
+        "scaling": "strong" if tiles_mode else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "camera": {"pos": BASE_POS, "dir": BASE_DIR, "fov": FOV},
+                   "schedule": schedule, "smem_nodes": r.GetOption("smem_nodes"),
+                   "l2": "flushed between frames (256 MiB write, untimed)" if flush is not None
+                         else "not flushed; node pool %d MB > L2" % (dev_bytes >> 20),
+                   "nodes": svo.nodecount, "packed_bytes": dev_bytes, "scene_build_s": round(build_s, 2),
+                   "partition": ("row bands of one frame" if tiles_mode else "one frame per GPU") if world > 1 else "single GPU",
+                   "gather": gather},
+        "frame_ms": 1e3 * total_s / a.steps, "rays_per_step": rays_step,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
+        "gpu_launches": a.steps * world, "parity": parity,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+
+
+if __name__ == "__main__":
+    main()

@@ -141,6 +141,9 @@ int yv_trace_rays(yv_renderer *r, const float *pos, const float *dir, uint32_t c
 /* Export a device allocation made by this library (yv_device_framebuffer) as a 64-byte CUDA
  * IPC handle; open it in another process; the mapping is a valid target for
  * yv_render_frame_device there (direct peer stores into GPU 0's frame). */
+int yv_device_alloc(int device, size_t bytes, void **d_ptr);      /* plain cudaMalloc (IPC-exportable) */
+int yv_device_free(int device, void *d_ptr);
+int yv_copy_to_host(int device, void *dst_host, const void *src_device, size_t bytes);
 int yv_ipc_export(void *d_ptr, uint8_t handle[64]);
 int yv_ipc_open(int device, const uint8_t handle[64], void **d_ptr);
 int yv_ipc_close(void *d_ptr);

@@ -1,0 +1,63 @@
+"""The kernel's per-ray code (trace_core.cuh: explicit-stack descent over the packed records, VoxData
+decode, shading, secondary-ray helpers) compiled for the host and compared with the oracle.
+This checks the state machine and the repack on CPU; the GPU parity proper is tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import scenes
+import yve
+import yvo
+import yoxel_voxel_b200 as yv
+
+
+def _compare(svo, cam_spec, W, H, sec_kw=None):
+    name, pos, d, up, fov = cam_spec
+    nodes = svo.nodes()
+    recs, leaves = svo.packed()
+    cam = yvo.camera(pos, d, up, fov, W, H)
+    d0, du, dv = yv.init_ray_dir(d, up, fov, W, H)
+    if sec_kw:
+        o = yvo.render(nodes, svo.GetRoot(), cam, sec=yvo.secondary(**sec_kw), threads=4)
+        light = sec_kw["light_pos"] if sec_kw.get("shadow") else pos
+        e = yve.render(recs, leaves, len(recs) > 0, pos, d0, du, dv, light, W, H,
+                       shadow=sec_kw.get("shadow", 0), ao_samples=sec_kw.get("ao_samples", 0), seed=sec_kw.get("seed", 1),
+                       voxel_size=sec_kw.get("voxel_size", 0.0), ao_max_t=sec_kw.get("ao_max_t", 0.05))
+    else:
+        o = yvo.render(nodes, svo.GetRoot(), cam, threads=4)
+        e = yve.render(recs, leaves, len(recs) > 0, pos, d0, du, dv, pos, W, H)
+    assert (o["node"] == e["node"]).all(), name
+    assert (o["child"] == e["child"]).all(), name
+    assert o["t"].tobytes() == e["t"].tobytes(), name
+    assert (o["rgba"] == e["rgba"]).all(), name
+    return o, e
+
+
+@pytest.mark.parametrize("cam", scenes.CAMERAS, ids=[c[0] for c in scenes.CAMERAS])
+def test_fractal_primary(cam):
+    o, e = _compare(scenes.fractal(9), cam, 160, 120)
+    assert e["max_sp"] <= 8                      # stack depth < tree depth (tail pushes are elided)
+    assert e["fetches"] >= o["stats"]["node_visits"]
+
+
+@pytest.mark.parametrize("cam", [scenes.CAMERAS[2], scenes.CAMERAS[4], scenes.CAMERAS[5]], ids=lambda c: c[0])
+def test_single_sphere_and_dense(cam):
+    _compare(scenes.single_sphere(6), cam, 96, 96)
+    _compare(scenes.dense_random(5, 0.03)[0], cam, 96, 96)
+
+
+@pytest.mark.parametrize("sec", [
+    dict(shadow=1, ao_samples=0, seed=1, light_pos=(0.6, 0.4, 1.2), voxel_size=1.0 / 512, ao_max_t=0.05),
+    dict(shadow=0, ao_samples=4, seed=1, light_pos=(0.6, 0.4, 1.2), voxel_size=1.0 / 512, ao_max_t=0.05),
+    dict(shadow=1, ao_samples=4, seed=7, light_pos=(0.6, 0.4, 1.2), voxel_size=1.0 / 512, ao_max_t=0.1),
+], ids=["shadow", "ao4", "shadow+ao4"])
+def test_fractal_secondary(sec):
+    o, e = _compare(scenes.fractal(9), scenes.CAMERAS[1], 128, 96, sec)
+    base = yvo.render(scenes.fractal(9).nodes(), scenes.fractal(9).GetRoot(),
+                      yvo.camera(*scenes.CAMERAS[1][1:4], scenes.CAMERAS[1][4], 128, 96))
+    assert (o["rgba"] != base["rgba"]).any()     # the secondary rays do change the picture
+
+
+def test_empty_scene():
+    s = yv.SVOData.FromNodes(yv.EMPTY_NODE, np.zeros(0, yv.NODE_DTYPE))
+    o, e = _compare(s, scenes.CAMERAS[2], 32, 32)
+    assert (o["rgba"] == 0).all()

@@ -1,0 +1,230 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): hit node/child ids bit-exact; hit distance t within 1e-4 relative;
+per-pixel RGB within 1 LSB. The kernel uses the same float32 operations in the same order as the
+oracle, so the tests additionally report (and require) exact equality of t and RGBA."""
+import numpy as np
+import pytest
+
+import scenes
+import yvo
+import yoxel_voxel_b200 as yv
+
+pytestmark = pytest.mark.gpu
+
+T_RTOL = 1e-4      # north_star tolerance for the hit distance
+RGB_LSB = 1        # north_star tolerance for colour
+
+
+def _check(o, img, node, child, t, tag):
+    assert (node == o["node"]).all(), "%s: hit node ids differ in %d pixels" % (tag, (node != o["node"]).sum())
+    assert (child == o["child"]).all(), "%s: hit child ids differ" % tag
+    assert np.allclose(t, o["t"], rtol=T_RTOL, atol=0), tag
+    assert np.abs(img.astype(int) - o["rgba"].astype(int)).max() <= RGB_LSB, tag
+    # stronger than required: same arithmetic => identical bits
+    assert t.tobytes() == o["t"].tobytes(), "%s: t not bit-identical" % tag
+    assert (img == o["rgba"]).all(), "%s: rgba not identical" % tag
+
+
+def _render_gpu(r, cam_spec, W, H, sec=None):
+    name, pos, d, up, fov = cam_spec
+    r.SetResolution(W, H)
+    r.SetViewPos(pos); r.SetViewDir(d); r.SetViewUp(up); r.SetFOV(fov)
+    if sec:
+        r.SetSecondary(**sec)
+    else:
+        r.SetSecondary(0, 0)
+    img = r.RenderFrame().copy()
+    node, child, t = r.GetHits()
+    return img, node, child, t
+
+
+def _render_cpu(svo, cam_spec, W, H, sec=None, visits=False):
+    name, pos, d, up, fov = cam_spec
+    return yvo.render(svo.nodes(), svo.GetRoot(), yvo.camera(pos, d, up, fov, W, H),
+                      sec=yvo.secondary(**sec) if sec else None, threads=8, want_visits=visits)
+
+
+@pytest.fixture(scope="module")
+def renderer():
+    r = yv.SVORenderer(0)
+    r.EnableHits(True)
+    yield r
+    r.close()
+
+
+@pytest.mark.parametrize("persistent", [0, 1], ids=["tiles", "persistent"])
+@pytest.mark.parametrize("cam", scenes.CAMERAS, ids=[c[0] for c in scenes.CAMERAS])
+def test_fractal10_primary(renderer, cam, persistent):
+    """BASELINE config 1: depth-10 sphere fractal, 512x512 primary rays (+ the other cameras)."""
+    svo = scenes.fractal(10)
+    renderer.SetOption("persistent", persistent)
+    renderer.SetScene(svo)
+    img, node, child, t = _render_gpu(renderer, cam, 512, 512)
+    _check(_render_cpu(svo, cam, 512, 512), img, node, child, t, cam[0])
+
+
+@pytest.mark.parametrize("smem_nodes", [0, 1, 73, 585, 4681])
+@pytest.mark.parametrize("persistent", [0, 1], ids=["tiles", "persistent"])
+def test_shared_memory_staging_sizes(renderer, smem_nodes, persistent):
+    svo = scenes.fractal(9)
+    renderer.SetOption("persistent", persistent)
+    renderer.SetOption("smem_nodes", smem_nodes)
+    renderer.SetScene(svo)
+    cam = scenes.CAMERAS[1]
+    img, node, child, t = _render_gpu(renderer, cam, 320, 200)
+    _check(_render_cpu(svo, cam, 320, 200), img, node, child, t, "smem%d" % smem_nodes)
+    renderer.SetOption("smem_nodes", 585)
+
+
+@pytest.mark.parametrize("size", [(1, 1), (7, 5), (37, 23), (130, 67), (1024, 768)])
+@pytest.mark.parametrize("persistent", [0, 1], ids=["tiles", "persistent"])
+def test_ragged_resolutions(renderer, size, persistent):
+    """Partial tiles at the right / bottom edges; cell/main.cpp's 1024x768."""
+    svo = scenes.fractal(9)
+    renderer.SetOption("persistent", persistent)
+    renderer.SetScene(svo)
+    cam = scenes.CAMERAS[1]
+    img, node, child, t = _render_gpu(renderer, cam, *size)
+    assert img.shape == (size[1], size[0], 4)
+    _check(_render_cpu(svo, cam, *size), img, node, child, t, "res%dx%d" % size)
+
+
+@pytest.mark.parametrize("persistent", [0, 1], ids=["tiles", "persistent"])
+@pytest.mark.parametrize("sec", [
+    dict(shadow=1, ao_samples=0, seed=1, light_pos=(0.6, 0.4, 1.2), voxel_size=1.0 / 1024, ao_max_t=0.05),
+    dict(shadow=0, ao_samples=4, seed=1, light_pos=(0.6, 0.4, 1.2), voxel_size=1.0 / 1024, ao_max_t=0.05),
+    dict(shadow=1, ao_samples=4, seed=1, light_pos=(0.6, 0.4, 1.2), voxel_size=1.0 / 1024, ao_max_t=0.05),
+    dict(shadow=1, ao_samples=16, seed=99, light_pos=(0.1, 0.9, 0.2), voxel_size=2.0 / 1024, ao_max_t=0.2),
+], ids=["shadow", "ao4", "shadow+ao4", "shadow+ao16"])
+def test_secondary_rays(renderer, sec, persistent):
+    """BASELINE config 4 (at depth 10): primary + shadow + AO rays."""
+    svo = scenes.fractal(10)
+    renderer.SetOption("persistent", persistent)
+    renderer.SetScene(svo)
+    for cam in (scenes.CAMERAS[1], scenes.CAMERAS[4]):
+        img, node, child, t = _render_gpu(renderer, cam, 400, 300, sec)
+        o = _render_cpu(svo, cam, 400, 300, sec)
+        _check(o, img, node, child, t, "sec")
+    renderer.SetSecondary(0, 0)
+
+
+@pytest.mark.parametrize("persistent", [0, 1], ids=["tiles", "persistent"])
+def test_other_scenes(renderer, persistent):
+    renderer.SetOption("persistent", persistent)
+    for svo in (scenes.single_sphere(6), scenes.dense_random(5, 0.03)[0], scenes.dense_random(4, 0.08)[0],
+                yv.SVOData.IsoVolume(8, threads=8)):
+        renderer.SetScene(svo)
+        for cam in scenes.CAMERAS:
+            img, node, child, t = _render_gpu(renderer, cam, 200, 160)
+            _check(_render_cpu(svo, cam, 200, 160), img, node, child, t, cam[0])
+
+
+def test_empty_scene_and_no_scene():
+    r = yv.SVORenderer(0)
+    assert r.RenderFrame() is None                                  # reference: NULL (ppu_renderer.cpp:78-79)
+    assert r.GetResolution() == (640, 480) and r.GetFOV() == 70.0   # renderer_base.h:25
+    empty = yv.SVOData.FromNodes(yv.EMPTY_NODE, np.zeros(0, yv.NODE_DTYPE))
+    r.SetScene(empty)
+    r.SetResolution(64, 64)
+    r.SetViewPos((0.5, 0.5, -1)); r.SetViewDir((0, 0, 1))
+    img = r.RenderFrame()
+    assert img.shape == (64, 64, 4) and (img == 0).all()
+    r.close()
+
+
+def test_row_bands_compose_to_the_full_frame(renderer):
+    """Multi-GPU partition: bands rendered separately are byte-identical to the full frame."""
+    svo = scenes.fractal(10)
+    renderer.SetOption("persistent", 0)
+    renderer.SetScene(svo)
+    cam = scenes.CAMERAS[1]
+    full, *_ = _render_gpu(renderer, cam, 640, 363)
+    out = np.zeros_like(full)
+    for (y0, y1) in [(0, 91), (91, 182), (182, 300), (300, 363)]:
+        for persistent in (0, 1):
+            renderer.SetOption("persistent", persistent)
+            renderer.SetRows(y0, y1)
+            band = renderer.RenderFrame()
+            assert (band[y0:y1] == full[y0:y1]).all()
+        out[y0:y1] = band[y0:y1]
+    assert (out == full).all()
+    renderer.SetResolution(640, 363)      # resets the band
+
+
+def test_trace_rays_matches_oracle(renderer):
+    """DynamicSVO::TraceRay (ore/src/main.cpp:125) batched on the device."""
+    svo = scenes.fractal(9)
+    renderer.SetScene(svo)
+    nodes = svo.nodes()
+    rng = np.random.RandomState(5)
+    pos = rng.rand(4000, 3).astype(np.float32) * 1.6 - 0.3
+    dirs = rng.randn(4000, 3).astype(np.float32)
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    dirs[::7, 0] = 0.0                      # exercise AdjustDir
+    node, child, t = renderer.TraceRays(pos, dirs)
+    nh = 0
+    for i in range(len(pos)):
+        hit, n, c, tt = yvo.trace_ray(nodes, svo.GetRoot(), pos[i], dirs[i])
+        assert (node[i], child[i]) == (n, c), i
+        assert np.float32(tt).tobytes() == t[i].tobytes()
+        nh += hit
+    assert nh > 100
+
+
+def test_counters_equal_oracle_visits(renderer):
+    """The kernel dereferences exactly the nodes the oracle does (basis of the roofline's V-bar)."""
+    svo = scenes.fractal(10)
+    renderer.SetScene(svo)
+    renderer.EnableCounters(True)
+    cam = scenes.CAMERAS[1]
+    for persistent in (0, 1):
+        renderer.SetOption("persistent", persistent)
+        _render_gpu(renderer, cam, 256, 256)
+        visits, pops = renderer.GetCounters()
+        o = _render_cpu(svo, cam, 256, 256, visits=True)
+        assert (visits == o["visits"]).all()
+        assert pops.sum() > 0
+    renderer.EnableCounters(False)
+
+
+def test_device_pointer_render_and_timing(renderer):
+    """SVORenderer::Render(void* d_dstBuf) (demo/SVORenderer.h:36) into a caller-owned device buffer."""
+    import torch
+    svo = scenes.fractal(10)
+    renderer.SetOption("persistent", 0)
+    renderer.SetScene(svo)
+    cam = scenes.CAMERAS[1]
+    img, *_ = _render_gpu(renderer, cam, 512, 384)
+    buf = torch.zeros(384, 512, 4, dtype=torch.uint8, device="cuda:0")
+    torch.cuda.synchronize()
+    renderer.Render(buf.data_ptr())
+    assert (buf.cpu().numpy() == img).all()
+    assert 0 < renderer.LastFrameMs() < 1000 and renderer.LastFrameLaunches() == 1
+    # on torch's current stream
+    renderer.SetStream(torch.cuda.current_stream().cuda_stream)
+    buf.zero_()
+    renderer.Render(buf.data_ptr(), sync=False)
+    torch.cuda.synchronize()
+    assert (buf.cpu().numpy() == img).all()
+    renderer.SetStream(0)
+
+
+def test_full_size_config2_depth12_1080p():
+    """BASELINE config 2 at full size: depth-12 sphere fractal, 1920x1080, primary + Lambert.
+    The threaded oracle renders the whole frame in seconds, so the comparison is exhaustive."""
+    svo = scenes.fractal(12)
+    r = yv.SVORenderer(0)
+    r.EnableHits(True)
+    r.SetScene(svo)
+    cam = scenes.CAMERAS[1]
+    o = _render_cpu(svo, cam, 1920, 1080)
+    assert (o["node"] != yvo.MISS_NODE).mean() > 0.3
+    for persistent in (0, 1):
+        r.SetOption("persistent", persistent)
+        img, node, child, t = _render_gpu(r, cam, 1920, 1080)
+        _check(o, img, node, child, t, "config2/%d" % persistent)
+    # idempotence: a second frame is byte-identical
+    img2, *_ = _render_gpu(r, cam, 1920, 1080)
+    assert (img2 == img).all()
+    r.close()

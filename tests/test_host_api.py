@@ -1,0 +1,162 @@
+"""CPU-side checks of the product's host code: the C-ABI library loads and exports every symbol the
+header declares, scene builders / .vox I/O / repack behave, and the renderer refuses to run without
+a GPU (no CPU fallback). No kernel is launched here."""
+import ctypes as C
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+import conftest
+import scenes
+import yvo
+import yoxel_voxel_b200 as yv
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "yv_b200.h")).read()
+    declared = set(re.findall(r"\b(yv_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 45
+    L = C.CDLL(yv.lib_path())
+    missing = [n for n in sorted(declared) if not hasattr(L, n)]
+    assert not missing, missing
+    # and the Python mirror binds all of them
+    assert declared <= set(yv.lib()._yv_signatures), declared - set(yv.lib()._yv_signatures)
+    assert yv.lib().yv_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu():
+    if conftest.has_gpu():
+        pytest.skip("GPU present")
+    with pytest.raises(yv.YVError) as e:
+        yv.SVORenderer(0)
+    assert e.value.code == -4 and "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_reference_the_oracle():
+    pkg = os.path.join(ROOT, "yoxel-voxel_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle/" not in text and "yv_oracle" not in text and "yvo_" not in text, f
+
+
+def test_builder_is_deterministic_and_valid():
+    a = yv.SVOData.SphereFractal(8, threads=1).nodes()
+    b = yv.SVOData.SphereFractal(8, threads=8).nodes()
+    assert a.tobytes() == b.tobytes()
+    assert len(a) == 35645
+    # flags are consistent with the child words (main.tex:40-42)
+    leaf = (a["flags"][:, None] >> np.arange(8)) & 1
+    null = (a["flags"][:, None] >> (8 + np.arange(8))) & 1
+    topbit = (a["child"] >> 31) & 1
+    assert ((null == 1) == ((leaf == 0) & (topbit == 1))).all()
+    inner = (leaf == 0) & (null == 0)
+    assert (a["child"][inner] < len(a)).all()
+    # every internal node has at least one non-null child (uniform octets collapse)
+    assert ((leaf | inner).sum(axis=1) > 0).all()
+
+
+def test_sphere_fractal_follows_gen_spheres():
+    """gen_spheres.py:8-32 at depth 8: only lev-5 spheres survive (radius 32/2^5 = 1), 5^5 of them,
+    colour (128,128,5*255/8=159) -> RGB565."""
+    s = yv.SVOData.SphereFractal(8)
+    nodes = s.nodes()
+    leaf = ((nodes["flags"][:, None] >> np.arange(8)) & 1).astype(bool)
+    data = nodes["child"][leaf]
+    assert len(np.unique(data & 0xFFFF)) == 1
+    assert (data[0] & 0xFFFF) == ((128 >> 3) << 11 | (128 >> 2) << 5 | (159 >> 3))
+    assert s.depth == 8
+
+
+def test_vox_roundtrip_matches_svodata_layout(tmp_path):
+    s = scenes.single_sphere(6)
+    fn = str(tmp_path / "sphere.vox")
+    s.Save(fn)
+    raw = open(fn, "rb").read()
+    root, w1, w2, count = np.frombuffer(raw[:16], "<u4")
+    assert root == s.GetRoot() and count == s.nodecount and len(raw) == 16 + 40 * count     # svodata.h:36-42
+    # the oracle's SVOData::Load restatement reads the same pool
+    oroot, onodes = yvo.load_vox(fn)
+    assert oroot == s.GetRoot() and onodes.tobytes() == s.nodes().tobytes()
+    t = yv.SVOData().Load(fn)
+    assert t.GetRoot() == s.GetRoot() and t.nodes().tobytes() == s.nodes().tobytes() and t.depth == 6
+
+
+def test_load_errors_are_reported(tmp_path):
+    with pytest.raises(yv.YVError) as e:
+        yv.SVOData().Load(str(tmp_path / "missing.vox"))
+    assert e.value.code == -2
+    fn = tmp_path / "short.vox"
+    fn.write_bytes(np.array([0, 0, 0, 5], "<u4").tobytes() + b"\0" * 40)
+    with pytest.raises(yv.YVError):
+        yv.SVOData().Load(str(fn))
+    bad = np.zeros(1, yv.NODE_DTYPE)
+    bad[0]["child"][:] = yv.EMPTY_NODE
+    bad[0]["child"][3] = 77                                  # dangling child id
+    with pytest.raises(yv.YVError) as e:
+        yv.SVOData.FromNodes(0, bad)
+    assert e.value.code == -3
+
+
+def test_packed_pool_invariants():
+    s = scenes.fractal(8)
+    nodes = s.nodes()
+    recs, leaves = s.packed()
+    assert recs.dtype == np.uint32 and recs.shape[1] == 4              # 16-byte records
+    assert len(recs) == len(nodes)                                     # a tree: no duplication
+    assert sorted(recs[:, 3]) == list(range(len(nodes)))               # orig ids are a permutation
+    assert recs[0, 3] == s.GetRoot()
+    leaf_mask, child_mask = recs[:, 2] & 0xFF, (recs[:, 2] >> 8) & 0xFF
+    assert (leaf_mask & child_mask == 0).all()
+    pc = np.array([bin(i).count("1") for i in range(256)])
+    # children of consecutive records are laid out back to back, breadth first
+    assert recs[0, 0] == 1
+    assert (np.diff(recs[:, 0].astype(np.int64)) == pc[child_mask][:-1]).all()
+    assert (np.diff(recs[:, 1].astype(np.int64)) == pc[leaf_mask][:-1]).all()
+    assert recs[-1, 1] + pc[leaf_mask][-1] == len(leaves)
+    # spot-check content: leaf words and child links agree with the reference pool
+    rng = np.random.RandomState(1)
+    for i in rng.randint(0, len(recs), 300):
+        nd = nodes[recs[i, 3]]
+        k_leaf = k_child = 0
+        for c in range(8):
+            if (nd["flags"] >> c) & 1:
+                assert leaves[recs[i, 1] + k_leaf] == nd["child"][c]; k_leaf += 1
+                assert (leaf_mask[i] >> c) & 1
+            elif not nd["child"][c] & 0x80000000:
+                assert recs[recs[i, 0] + k_child, 3] == nd["child"][c]; k_child += 1
+                assert (child_mask[i] >> c) & 1
+
+
+def test_packed_pool_of_null_root_is_empty():
+    s = yv.SVOData.FromNodes(yv.EMPTY_NODE, np.zeros(0, yv.NODE_DTYPE))
+    recs, leaves = s.packed()
+    assert len(recs) == 0 and len(leaves) == 0
+
+
+def test_init_ray_dir_matches_oracle_bitwise():
+    for name, pos, d, up, fov in scenes.CAMERAS:
+        for (w, h) in [(512, 512), (1920, 1080), (37, 23), (1, 1)]:
+            cam = yvo.camera(pos, d, up, fov, w, h)
+            o = yvo.init_ray_dir(cam)
+            p = yv.init_ray_dir(d, up, fov, w, h)
+            for a, b in zip(o, p):
+                assert a.tobytes() == b.tobytes(), (name, w, h)
+
+
+def test_iso_volume_builder_small():
+    s = yv.SVOData.IsoVolume(7, seed=219, iso_level=200, threads=4)
+    nodes = s.nodes()
+    assert 1000 < len(nodes) < 200000
+    assert hashlib.sha256(nodes.tobytes()).hexdigest() == \
+        hashlib.sha256(yv.SVOData.IsoVolume(7, seed=219, iso_level=200, threads=1).nodes().tobytes()).hexdigest()
+    # a camera above the slab sees terrain
+    cam = yvo.camera((0.5, 0.5, 0.6), (0.3, 0.4, -1), (0, 0, 1), 70, 64, 64)
+    r = yvo.render(nodes, s.GetRoot(), cam)
+    assert (r["node"] != yvo.MISS_NODE).mean() > 0.5

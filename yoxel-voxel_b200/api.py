@@ -97,6 +97,9 @@ def lib():
         "yv_set_option": (i32, [vp, C.c_char_p, i32]),
         "yv_get_option": (i32, [vp, C.c_char_p, P(i32)]),
         "yv_trace_rays": (i32, [vp, vp, vp, u32, vp, vp, vp]),
+        "yv_device_alloc": (i32, [i32, C.c_size_t, P(vp)]),
+        "yv_device_free": (i32, [i32, vp]),
+        "yv_copy_to_host": (i32, [i32, vp, vp, C.c_size_t]),
         "yv_ipc_export": (i32, [vp, vp]),
         "yv_ipc_open": (i32, [i32, vp, P(vp)]),
         "yv_ipc_close": (i32, [vp]),

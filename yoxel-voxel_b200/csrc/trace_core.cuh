@@ -208,7 +208,7 @@ YV_HD uint32_t shade_rgba(uint32_t data, float k) {
   return o0 | (o1 << 8) | (o2 << 16) | 0xff000000u;
 }
 
-// ---- secondary-ray helpers (BASELINE config 4; definition mirrored by oracle/yv_oracle.c) -----
+// ---- secondary-ray helpers (BASELINE config 4; spec: include/yv_b200.h YV secondary rays) -----
 
 YV_HD uint32_t hash_u32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;

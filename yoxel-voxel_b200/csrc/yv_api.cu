@@ -641,6 +641,28 @@ int yv_trace_rays(yv_renderer *r, const float *pos, const float *dir, uint32_t c
   return YV_OK;
 }
 
+int yv_device_alloc(int device, size_t bytes, void **d_ptr) {
+  if (!d_ptr || bytes == 0) return fail(YV_ERR_ARG, "bad argument");
+  YV_CUDA(cudaSetDevice(device));
+  YV_CUDA(cudaMalloc(d_ptr, bytes));
+  YV_CUDA(cudaMemset(*d_ptr, 0, bytes));
+  return YV_OK;
+}
+
+int yv_device_free(int device, void *d_ptr) {
+  if (!d_ptr) return YV_OK;
+  YV_CUDA(cudaSetDevice(device));
+  YV_CUDA(cudaFree(d_ptr));
+  return YV_OK;
+}
+
+int yv_copy_to_host(int device, void *dst_host, const void *src_device, size_t bytes) {
+  if (!dst_host || !src_device) return fail(YV_ERR_ARG, "null argument");
+  YV_CUDA(cudaSetDevice(device));
+  YV_CUDA(cudaMemcpy(dst_host, src_device, bytes, cudaMemcpyDeviceToHost));
+  return YV_OK;
+}
+
 int yv_ipc_export(void *d_ptr, uint8_t handle[64]) {
   if (!d_ptr || !handle) return fail(YV_ERR_ARG, "null argument");
   cudaIpcMemHandle_t h;
