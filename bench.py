@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--schedule", default="auto", choices=["auto", "tiles", "persistent"])
     ap.add_argument("--smem-nodes", type=int, default=-1)
+    ap.add_argument("--stack", type=int, default=-1, choices=[-1, 0, 1, 2, 4])
     ap.add_argument("--secondary", action="store_true", help="BASELINE config 4: shadow + 4 AO rays")
     ap.add_argument("--partition", default="frames", choices=["frames", "tiles"],
                     help="N>1: one frame per rank (weak) or one frame split into row bands (strong)")
@@ -185,13 +186,16 @@ def main():
     r.SetOption("persistent", 1 if schedule == "persistent" else 0)
     if a.smem_nodes >= 0:
         r.SetOption("smem_nodes", a.smem_nodes)
+    if a.stack >= 0:
+        r.SetOption("stack", a.stack)
     r.SetScene(svo)
     r.SetResolution(a.width, a.height)
     r.SetViewUp(UP); r.SetFOV(FOV)
     if a.secondary:
         r.SetSecondary(shadow=1, ao_samples=4, seed=1, light_pos=(0.6, 0.4, 1.2),
                        voxel_size=1.0 / (1 << a.depth), ao_max_t=0.05)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)       # a real (non-NULL) stream: the renderer, the L2 flush and the
+    torch.cuda.set_stream(stream)                # timing events all run on it
     r.SetStream(stream.cuda_stream)
 
     # ---- partition ----------------------------------------------------------------------------
@@ -365,7 +369,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "yv::render_%s" % schedule,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "yv::render_frame<%s>" % schedule,
                 "algorithmic_bytes_per_launch": alg_bytes_step / world,
                 "node_visits_per_ray": vis_step / rays_step, "pop_refetches_per_ray": pop_step / rays_step,
                 "kernel_ms": 1e3 * kernel_s}
@@ -375,7 +379,7 @@ def main():
         "ms_per_step": 1e3 * total_s / a.steps, "higher_is_better": True,
         "scaling": "strong" if tiles_mode else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "camera": {"pos": BASE_POS, "dir": BASE_DIR, "fov": FOV},
-                   "schedule": schedule, "smem_nodes": r.GetOption("smem_nodes"),
+                   "schedule": schedule, "smem_nodes": r.GetOption("smem_nodes"), "stack": r.GetOption("stack"),
                    "l2": "flushed between frames (256 MiB write, untimed)" if flush is not None
                          else "not flushed; node pool %d MB > L2" % (dev_bytes >> 20),
                    "nodes": svo.nodecount, "packed_bytes": dev_bytes, "scene_build_s": round(build_s, 2),

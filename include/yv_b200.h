@@ -128,7 +128,9 @@ int yv_set_stream(yv_renderer *r, void *cuda_stream);
 /* Kernel variant knobs (for ablation runs; defaults are the tuned ones):
  *   "smem_nodes"  number of top-of-tree records staged in shared memory per CTA
  *   "persistent"  1 = persistent CTAs pulling tiles from an atomic counter, 0 = one CTA per tile
- *   "refill"      1 = warp-level ray refill (ballot/shuffle compaction) in the persistent kernel */
+ *                 (with warp-level lane refill: ballot + popc compaction of finished rays)
+ *   "stack"       where the traversal stack lives: 0 local memory, 4 = four-entry
+ *                 shared-memory ring spilling to local memory */
 int yv_set_option(yv_renderer *r, const char *name, int value);
 int yv_get_option(const yv_renderer *r, const char *name, int *value);
 

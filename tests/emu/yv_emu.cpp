@@ -11,23 +11,56 @@
 using namespace yv;
 
 namespace {
+int g_mode = 2;   // 0 = trace_step, 1 = seek_child/enter_node, 2 = lean_step (what render_frame runs)
 struct HostStack {
   StackEntry e[kMaxStack];
   int max_sp = 0;
   void push(int sp, const StackEntry &en) { e[sp] = en; if (sp + 1 > max_sp) max_sp = sp + 1; }
   StackEntry pop(int sp) const { return e[sp]; }
 };
+struct LeanHostStack {
+  U4 a[kMaxStack], b[kMaxStack];
+  int max_sp = 0;
+  void push(int sp, const U4 &x, const U4 &y) { a[sp] = x; b[sp] = y; if (sp + 1 > max_sp) max_sp = sp + 1; }
+  void pop(int sp, U4 &x, U4 &y) const { x = a[sp]; y = b[sp]; }
+};
+LeanHostStack g_lean_stack;
 struct HostFetch {
   const Rec *recs;
-  mutable uint64_t fetches = 0;
-  Rec operator()(uint32_t idx) const { ++fetches; return recs[idx]; }
+  mutable uint64_t fetches = 0, visits = 0;
+  Rec operator()(uint32_t idx) const { ++fetches; ++visits; return recs[idx]; }
+  Rec get(uint32_t idx, bool visit) const { ++fetches; if (visit) ++visits; return recs[idx]; }
 };
 
 bool trace(const HostFetch &fetch, bool root_valid, HostStack &stk, float ox, float oy, float oz,
            float dx, float dy, float dz, bool front_only, RayState &s, Rec &rec, uint64_t &steps) {
   dx = adjust_dir1(dx); dy = adjust_dir1(dy); dz = adjust_dir1(dz);
+  if (g_mode == 2) {
+    LeanState ls;
+    if (!lean_begin(ls, fetch, root_valid, ox, oy, oz, dx, dy, dz)) return false;
+    for (;;) {
+      ++steps;
+      const int r = lean_step(ls, fetch, g_lean_stack, front_only);
+      if (r == kStepContinue) continue;
+      if (g_lean_stack.max_sp > stk.max_sp) stk.max_sp = g_lean_stack.max_sp;
+      if (r == kStepMiss) return false;
+      // present the result through the classic state the caller reads
+      s.t1x = ls.t1x; s.t1y = ls.t1y; s.t1z = ls.t1z; s.ch = ls.ch; s.flags = ls.flags;
+      rec = fetch.recs[ls.idx];
+      return true;
+    }
+  }
   if (!setup_trace(ox, oy, oz, dx, dy, dz, s)) return false;
   if (!trace_enter_root(s, rec, fetch, root_valid)) return false;
+  if (g_mode == 1) {
+    SeekResult sk;
+    for (;;) {
+      ++steps;
+      const int need = seek_child(s, rec, front_only, sk);
+      if (need == kSeekHit) return true;
+      if (enter_node(s, rec, fetch, stk, need, sk) == kStepMiss) return false;
+    }
+  }
   for (;;) {
     ++steps;
     int r = trace_step(s, rec, fetch, stk, front_only);
@@ -37,12 +70,14 @@ bool trace(const HostFetch &fetch, bool root_valid, HostStack &stk, float ox, fl
 }
 }  // namespace
 
+extern "C" void yve_set_mode(int mode) { g_mode = mode; }
+
 extern "C" int yve_render(const uint32_t *records, const uint32_t *leaves, int root_valid,
                           const float pos[3], const float dir0[3], const float du[3], const float dv[3],
                           const float light[3], int width, int height,
                           int shadow, int ao_samples, uint32_t seed, float voxel_size, float ao_max_t,
                           uint32_t *hit_node, int32_t *hit_child, float *hit_t, uint32_t *rgba,
-                          uint64_t *out_fetches, int *out_max_sp) {
+                          uint64_t *out_fetches, int *out_max_sp, uint64_t *out_visits) {
   const Rec *recs = reinterpret_cast<const Rec *>(records);
   HostFetch fetch{ recs };
   HostStack stk;
@@ -99,6 +134,7 @@ extern "C" int yve_render(const uint32_t *records, const uint32_t *leaves, int r
       if (rgba) rgba[pixel] = out;
     }
   if (out_fetches) *out_fetches = fetch.fetches;
+  if (out_visits) *out_visits = fetch.visits;
   if (out_max_sp) *out_max_sp = stk.max_sp;
   return 0;
 }

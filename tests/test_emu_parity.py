@@ -10,7 +10,7 @@ import yvo
 import yoxel_voxel_b200 as yv
 
 
-def _compare(svo, cam_spec, W, H, sec_kw=None):
+def _compare(svo, cam_spec, W, H, sec_kw=None, mode=2):
     name, pos, d, up, fov = cam_spec
     nodes = svo.nodes()
     recs, leaves = svo.packed()
@@ -21,10 +21,11 @@ def _compare(svo, cam_spec, W, H, sec_kw=None):
         light = sec_kw["light_pos"] if sec_kw.get("shadow") else pos
         e = yve.render(recs, leaves, len(recs) > 0, pos, d0, du, dv, light, W, H,
                        shadow=sec_kw.get("shadow", 0), ao_samples=sec_kw.get("ao_samples", 0), seed=sec_kw.get("seed", 1),
-                       voxel_size=sec_kw.get("voxel_size", 0.0), ao_max_t=sec_kw.get("ao_max_t", 0.05))
+                       voxel_size=sec_kw.get("voxel_size", 0.0), ao_max_t=sec_kw.get("ao_max_t", 0.05), mode=mode)
     else:
         o = yvo.render(nodes, svo.GetRoot(), cam, threads=4)
-        e = yve.render(recs, leaves, len(recs) > 0, pos, d0, du, dv, pos, W, H)
+        e = yve.render(recs, leaves, len(recs) > 0, pos, d0, du, dv, pos, W, H, mode=mode)
+        assert e["visits"] == o["stats"]["node_visits"]
     assert (o["node"] == e["node"]).all(), name
     assert (o["child"] == e["child"]).all(), name
     assert o["t"].tobytes() == e["t"].tobytes(), name
@@ -32,9 +33,10 @@ def _compare(svo, cam_spec, W, H, sec_kw=None):
     return o, e
 
 
+@pytest.mark.parametrize("mode", [2, 1, 0], ids=["lean_step", "seek+enter", "trace_step"])
 @pytest.mark.parametrize("cam", scenes.CAMERAS, ids=[c[0] for c in scenes.CAMERAS])
-def test_fractal_primary(cam):
-    o, e = _compare(scenes.fractal(9), cam, 160, 120)
+def test_fractal_primary(cam, mode):
+    o, e = _compare(scenes.fractal(9), cam, 160, 120, mode=mode)
     assert e["max_sp"] <= 8                      # stack depth < tree depth (tail pushes are elided)
     assert e["fetches"] >= o["stats"]["node_visits"]
 

@@ -74,7 +74,25 @@ def test_shared_memory_staging_sizes(renderer, smem_nodes, persistent):
     cam = scenes.CAMERAS[1]
     img, node, child, t = _render_gpu(renderer, cam, 320, 200)
     _check(_render_cpu(svo, cam, 320, 200), img, node, child, t, "smem%d" % smem_nodes)
-    renderer.SetOption("smem_nodes", 585)
+    renderer.SetOption("smem_nodes", 0)
+
+
+@pytest.mark.parametrize("stack", [0, 4], ids=["local", "ring4"])
+@pytest.mark.parametrize("persistent", [0, 1], ids=["tiles", "persistent"])
+def test_stack_variants(renderer, stack, persistent):
+    """The traversal stack in local memory, shared memory, or a shared ring spilling to local memory."""
+    svo = scenes.fractal(10)
+    renderer.SetOption("persistent", persistent)
+    renderer.SetOption("stack", stack)
+    renderer.SetScene(svo)
+    sec = dict(shadow=1, ao_samples=4, seed=1, light_pos=(0.6, 0.4, 1.2), voxel_size=1.0 / 1024, ao_max_t=0.05)
+    for cam in (scenes.CAMERAS[1], scenes.CAMERAS[4]):
+        img, node, child, t = _render_gpu(renderer, cam, 333, 250)
+        _check(_render_cpu(svo, cam, 333, 250), img, node, child, t, "stack%d" % stack)
+        img, node, child, t = _render_gpu(renderer, cam, 333, 250, sec)
+        _check(_render_cpu(svo, cam, 333, 250, sec), img, node, child, t, "stack%d/sec" % stack)
+    renderer.SetOption("stack", 0)
+    renderer.SetSecondary(0, 0)
 
 
 @pytest.mark.parametrize("size", [(1, 1), (7, 5), (37, 23), (130, 67), (1024, 768)])

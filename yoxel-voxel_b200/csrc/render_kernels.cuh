@@ -5,15 +5,21 @@
 // RGBA8 store (:54,:67) — the reference CUDA path's InitEyeRays / Trace / ShadeSimple sequence
 // (demo/SVORenderer.cpp:95-149, trace_cuda.py:20-23) collapsed into one launch.
 //
-// Two schedules share the per-ray code in trace_core.cuh:
-//   render_tiles       one CTA per 16x8 pixel tile, one thread per pixel (8x4 pixels per warp)
-//   render_persistent  resident CTAs; every warp pulls 8x8 pixel tiles from an atomic counter and
-//                      re-fills idle lanes with new rays (ballot + popc prefix) once fewer than
-//                      kRefillThreshold lanes are still traversing; secondary rays (shadow, AO)
-//                      re-enter the same traversal loop as further stages of the pixel's state
-//                      machine instead of running as divergent tails.
-// The top `smem_nodes` records of the breadth-first pool are staged in shared memory per CTA
-// (precedent: the SPU's software node cache, cell/spu/trace_spu.cpp:15-35).
+// render_frame<SEC, COUNT, STACK, PERSISTENT, STAGED> is one warp-synchronous state machine:
+//   * every lane owns one pixel at a time; a pixel's rays (primary, then shadow and AO samples when
+//     SEC) are stages of the lane's state, so secondary rays re-enter the same traversal loop
+//     instead of running as divergent tails, and ray set-up / shading run batched over many lanes;
+//   * the traversal loop is flat: each iteration every live lane performs one lean_step
+//     (trace_core.cuh) — test the current child, then one sibling step or one (descend | pop);
+//   * PERSISTENT = false: one CTA per 16x8 pixel tile, one pixel per lane (8x4 pixels per warp);
+//     PERSISTENT = true : resident CTAs; each warp pulls 8x8-pixel tiles from an atomic counter and
+//     re-fills idle lanes (ballot + popc prefix) once <= kRefillThreshold lanes are still traversing;
+//   * STAGED: the top `smem_nodes` records of the breadth-first pool are read from shared memory
+//     (precedent: the SPU's software node cache, cell/spu/trace_spu.cpp:15-35). Measured on B200 the
+//     126 MB L2 + L1 already serve these records (L1 hit rate 94 % without staging) and the extra
+//     branch costs issue slots, so the default is smem_nodes = 0; the knob stays for ablation;
+//   * STACK selects where the explicit traversal stack lives: local memory, or a 4-entry
+//     shared-memory ring for the hot top of the stack that spills to local memory.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -33,10 +39,10 @@ struct RenderParams {
   int width, height;           // m_viewSize
   int y0, y1;                  // row band rendered by this launch
   uint32_t *out_rgba;          // full-frame addressed: out_rgba[y*width + x]
-  uint32_t *hit_node;          // optional TraceResult planes (ppu_renderer.cpp:7-12)
+  uint32_t *hit_node;          // optional TraceResult planes (ppu_renderer.cpp:7-12); NULL = off
   int32_t *hit_child;
   float *hit_t;
-  uint32_t *counters;          // optional: low 16 bits node visits, high 16 bits pop re-fetches
+  uint32_t *counters;          // COUNT: low 16 bits node visits, high 16 bits pop re-fetches
   unsigned int *tile_counter;  // persistent schedule: next tile to hand out
   int tiles_x, num_tiles;      // 8x8 tiles covering [0,width) x [y0,y1)
   int shadow, ao_samples;      // secondary rays
@@ -46,15 +52,27 @@ struct RenderParams {
 
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kRefillThreshold = 20;   // refill once <= this many lanes are still traversing
+constexpr int kCtaThreads = 128;
 
-// per-thread traversal stack in local memory: two 16-byte words per entry (LDL.128 / STL.128)
+enum : int { kStackLocal = 0, kStackRing4 = 4 };
+
+// ---- traversal stacks: two 16-byte words per entry ------------------------------------------------
+__device__ __forceinline__ uint4 to_uint4(const U4 &v) { return make_uint4(v.x, v.y, v.z, v.w); }
+__device__ __forceinline__ U4 to_u4(const uint4 &v) { U4 r = { v.x, v.y, v.z, v.w }; return r; }
+
+// per-thread stack in local memory (LDL.128 / STL.128)
 struct LocalStack {
   uint4 w[2 * kMaxStack];
+  __device__ __forceinline__ LocalStack(uint4 *) {}
+  __device__ __forceinline__ void reset() {}
+  __device__ __forceinline__ void push(int sp, const U4 &a, const U4 &b) { w[2 * sp] = to_uint4(a); w[2 * sp + 1] = to_uint4(b); }
+  __device__ __forceinline__ void pop(int sp, U4 &a, U4 &b) { a = to_u4(w[2 * sp]); b = to_u4(w[2 * sp + 1]); }
+  // classic StackEntry interface (trace_step, used by trace_rays_kernel)
   __device__ __forceinline__ void push(int sp, const StackEntry &e) {
     w[2 * sp]     = make_uint4(__float_as_uint(e.t1x), __float_as_uint(e.t1y), __float_as_uint(e.t1z), e.idx);
     w[2 * sp + 1] = make_uint4(__float_as_uint(e.t2x), __float_as_uint(e.t2y), __float_as_uint(e.t2z), e.ch);
   }
-  __device__ __forceinline__ StackEntry pop(int sp) const {
+  __device__ __forceinline__ StackEntry pop(int sp) {
     const uint4 a = w[2 * sp], b = w[2 * sp + 1];
     StackEntry e = { __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), a.w,
                      __uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), b.w };
@@ -62,8 +80,42 @@ struct LocalStack {
   }
 };
 
-// node fetch: shared memory for the staged top of the tree, read-only global path otherwise
-template <bool COUNT>
+// the K most recent entries in shared memory ([slot][half][thread]: a warp's 128-bit accesses never
+// bank-conflict), older ones spilled to local memory
+template <int K>
+struct RingStack {
+  uint4 *base;
+  uint4 spill[2 * kMaxStack];
+  int lo;        // entries [lo, sp) live in the ring
+  __device__ __forceinline__ RingStack(uint4 *area) : base(area + threadIdx.x), lo(0) {}
+  __device__ __forceinline__ void reset() { lo = 0; }
+  __device__ __forceinline__ void push(int sp, const U4 &a, const U4 &b) {
+    if (sp - lo == K) {
+      const int slot = lo & (K - 1);
+      spill[2 * lo] = base[(2 * slot) * kCtaThreads];
+      spill[2 * lo + 1] = base[(2 * slot + 1) * kCtaThreads];
+      ++lo;
+    }
+    const int slot = sp & (K - 1);
+    base[(2 * slot) * kCtaThreads] = to_uint4(a); base[(2 * slot + 1) * kCtaThreads] = to_uint4(b);
+  }
+  __device__ __forceinline__ void pop(int sp, U4 &a, U4 &b) {
+    if (sp < lo) { lo = sp; a = to_u4(spill[2 * sp]); b = to_u4(spill[2 * sp + 1]); return; }
+    const int slot = sp & (K - 1);
+    a = to_u4(base[(2 * slot) * kCtaThreads]); b = to_u4(base[(2 * slot + 1) * kCtaThreads]);
+  }
+};
+
+template <int STACK> struct StackOf { using type = LocalStack; };
+template <> struct StackOf<kStackRing4> { using type = RingStack<4>; };
+
+// shared-memory bytes the stack variant needs per CTA
+__host__ __device__ inline size_t stack_smem_bytes(int stack) {
+  return stack == kStackRing4 ? 4 * 2 * sizeof(uint4) * kCtaThreads : 0;
+}
+
+// node fetch: shared memory for the staged top of the tree (STAGED), read-only global path otherwise
+template <bool COUNT, bool STAGED>
 struct NodeFetch {
   const uint4 *recs;
   const uint4 *staged;
@@ -71,222 +123,134 @@ struct NodeFetch {
   mutable uint32_t visits, revisits;
   __device__ __forceinline__ Rec load(uint32_t idx) const {
     uint4 v;
-    if (idx < staged_n) v = staged[idx];
+    if (STAGED && idx < staged_n) v = staged[idx];
     else v = __ldg(recs + idx);
     Rec r = { v.x, v.y, v.z, v.w };
     return r;
   }
   __device__ __forceinline__ Rec operator()(uint32_t idx) const { if (COUNT) ++visits; return load(idx); }
-};
-
-// trace_step's pop path calls fetch(idx) as well; to separate algorithmic visits from re-fetches
-// the counter variant tracks stack depth changes outside (see trace_to_end).
-
-__device__ __forceinline__ void stage_top_records(const RenderParams &p, uint4 *staged) {
-  for (uint32_t i = threadIdx.x; i < p.smem_nodes; i += blockDim.x) staged[i] = __ldg(p.recs + i);
-  __syncthreads();
-}
-
-// Run one ray to completion (used by the tile schedule and by yv_trace_rays).
-template <bool FRONT_ONLY, bool COUNT>
-__device__ __forceinline__ bool trace_to_end(const NodeFetch<COUNT> &fetch, bool root_valid, LocalStack &stk,
-                                             float ox, float oy, float oz, float dx, float dy, float dz,
-                                             RayState &s, Rec &rec, uint32_t &pops) {
-  dx = adjust_dir1(dx); dy = adjust_dir1(dy); dz = adjust_dir1(dz);
-  if (!setup_trace(ox, oy, oz, dx, dy, dz, s)) return false;
-  if (!trace_enter_root(s, rec, fetch, root_valid)) return false;
-  for (;;) {
-    const int sp0 = s.sp;
-    const int r = trace_step(s, rec, fetch, stk, FRONT_ONLY);
-    if (COUNT && s.sp < sp0) ++pops;
-    if (r == kStepHit) return true;
-    if (r == kStepMiss) return false;
+  // one load instruction for both the descend (counted visit) and the pop (re-fetch) case
+  __device__ __forceinline__ Rec get(uint32_t idx, bool visit) const {
+    if (COUNT) { if (visit) ++visits; else ++revisits; }
+    return load(idx);
   }
-}
+};
 
 __device__ __forceinline__ uint32_t leaf_data(const RenderParams &p, const Rec &rec, uint32_t c) {
   return __ldg(p.leaves + rec.leaf_base + (uint32_t)__popc(rec.masks & 0xffu & ((1u << c) - 1u)));
 }
 
-// Shade one pixel from its primary hit, tracing the secondary rays in-thread (tile schedule).
-template <bool SEC, bool COUNT>
-__device__ __forceinline__ uint32_t shade_hit(const RenderParams &p, const NodeFetch<COUNT> &fetch, LocalStack &stk,
-                                              uint32_t pixel, uint32_t data, float dx, float dy, float dz, float t,
-                                              uint32_t &pops) {
-  float nx, ny, nz;
-  unpack_normal(data, nx, ny, nz);
-  const float Px = YV_FADD(p.pos[0], YV_FMUL(dx, t));
-  const float Py = YV_FADD(p.pos[1], YV_FMUL(dy, t));
-  const float Pz = YV_FADD(p.pos[2], YV_FMUL(dz, t));
-  const float dl = lambert(nx, ny, nz, Px, Py, Pz, p.light[0], p.light[1], p.light[2]);
-  if (!SEC) {
-    const float k = YV_FADD(YV_SHADE_AMBIENT, YV_FMUL(YV_SHADE_DIFFUSE, YV_FMUL(dl, 1.0f)));
-    return shade_rgba(data, k);
-  }
-  const float Ox = YV_FADD(Px, YV_FMUL(nx, p.voxel_size));
-  const float Oy = YV_FADD(Py, YV_FMUL(ny, p.voxel_size));
-  const float Oz = YV_FADD(Pz, YV_FMUL(nz, p.voxel_size));
-  float vis = 1.0f;
-  RayState s; Rec rec;
-  if (p.shadow) {
-    const float vx = YV_FSUB(p.light[0], Ox), vy = YV_FSUB(p.light[1], Oy), vz = YV_FSUB(p.light[2], Oz);
-    const float len = YV_FSQRT(YV_FADD(YV_FADD(YV_FMUL(vx, vx), YV_FMUL(vy, vy)), YV_FMUL(vz, vz)));
-    if (len > 0) {
-      const bool h = trace_to_end<true, COUNT>(fetch, p.root_valid != 0u, stk, Ox, Oy, Oz,
-                                               YV_FDIV(vx, len), YV_FDIV(vy, len), YV_FDIV(vz, len), s, rec, pops);
-      if (h) { const float ts = max3f(s.t1x, s.t1y, s.t1z); if (ts > 0 && ts < len) vis = 0.0f; }
-    }
-  }
-  float ao = 1.0f;
-  if (p.ao_samples > 0) {
-    int occ = 0;
-    for (int smp = 0; smp < p.ao_samples; ++smp) {
-      float ax, ay, az;
-      ao_direction(nx, ny, nz, pixel, (uint32_t)smp, p.seed, ax, ay, az);
-      const bool h = trace_to_end<true, COUNT>(fetch, p.root_valid != 0u, stk, Ox, Oy, Oz, ax, ay, az, s, rec, pops);
-      if (h) { const float ts = max3f(s.t1x, s.t1y, s.t1z); if (ts > 0 && ts < p.ao_max_t) ++occ; }
-    }
-    ao = YV_FSUB(1.0f, YV_FDIV((float)occ, (float)p.ao_samples));
-  }
-  const float k = YV_FMUL(YV_FADD(YV_SHADE_AMBIENT, YV_FMUL(YV_SHADE_DIFFUSE, YV_FMUL(dl, vis))), ao);
-  return shade_rgba(data, k);
-}
-
-// ---------------------------------------------------------------------------------------------
-// schedule 1: one CTA per 16x8 tile, one thread per pixel
-// ---------------------------------------------------------------------------------------------
-template <bool HITS, bool SEC, bool COUNT>
-__global__ void __launch_bounds__(128) render_tiles(const __grid_constant__ RenderParams p) {
-  extern __shared__ uint4 staged[];
-  stage_top_records(p, staged);
-
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int tiles_x16 = (p.width + 15) >> 4;
-  const int tx = blockIdx.x % tiles_x16, ty = blockIdx.x / tiles_x16;
-  const int x = tx * 16 + (warp & 1) * 8 + (lane & 7);
-  const int y = p.y0 + ty * 8 + (warp >> 1) * 4 + (lane >> 3);
-  if (x >= p.width || y >= p.y1) return;
-  const uint32_t pixel = (uint32_t)y * (uint32_t)p.width + (uint32_t)x;
-
-  NodeFetch<COUNT> fetch = { p.recs, staged, p.smem_nodes, 0u, 0u };
-  LocalStack stk;
-  RayState s; Rec rec;
-  uint32_t pops = 0;
-
-  float dx, dy, dz;
-  primary_dir(p.dir0, p.du, p.dv, x, y, dx, dy, dz);
-  dx = adjust_dir1(dx); dy = adjust_dir1(dy); dz = adjust_dir1(dz);
-  const bool hit = trace_to_end<false, COUNT>(fetch, p.root_valid != 0u, stk, p.pos[0], p.pos[1], p.pos[2],
-                                              dx, dy, dz, s, rec, pops);
-  uint32_t rgba = 0u;
-  uint32_t hn = YV_MISS_NODE; int32_t hc = YV_MISS_CHILD; float ht = 0.0f;
-  if (hit) {
-    const uint32_t c = s.ch ^ s.flags;
-    hn = rec.orig_id; hc = (int32_t)c; ht = max3f(s.t1x, s.t1y, s.t1z);
-    const uint32_t data = leaf_data(p, rec, c);
-    rgba = shade_hit<SEC, COUNT>(p, fetch, stk, pixel, data, dx, dy, dz, ht, pops);
-  }
-  p.out_rgba[pixel] = rgba;
-  if (HITS) { p.hit_node[pixel] = hn; p.hit_child[pixel] = hc; p.hit_t[pixel] = ht; }
-  if (COUNT) p.counters[pixel] = ((fetch.visits - pops) & 0xffffu) | (pops << 16);
-}
-
-// ---------------------------------------------------------------------------------------------
-// schedule 2: persistent warps, atomic tile queue, lane refill, secondary rays as stages
-// ---------------------------------------------------------------------------------------------
 enum : int { kLaneIdle = 0, kLaneActive = 1, kLaneHit = 2, kLaneMiss = 3, kLaneNew = 4 };
 
-template <bool HITS, bool SEC, bool COUNT, int THREADS>
-__global__ void __launch_bounds__(THREADS) render_persistent(const __grid_constant__ RenderParams p) {
-  extern __shared__ uint4 staged[];
-  stage_top_records(p, staged);
+template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED>
+__global__ void __launch_bounds__(kCtaThreads) render_frame(const __grid_constant__ RenderParams p) {
+  extern __shared__ uint4 smem[];
+  uint4 *staged = smem;
+  uint4 *stack_area = smem + (STAGED ? p.smem_nodes : 0u);
+  if (STAGED) {
+    for (uint32_t i = threadIdx.x; i < p.smem_nodes; i += kCtaThreads) staged[i] = __ldg(p.recs + i);
+    __syncthreads();
+  }
 
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  NodeFetch<COUNT> fetch = { p.recs, staged, p.smem_nodes, 0u, 0u };
-  LocalStack stk;
-  RayState s; Rec rec;
-  uint32_t pops = 0;
+  NodeFetch<COUNT, STAGED> fetch = { p.recs, staged, p.smem_nodes, 0u, 0u };
+  typename StackOf<STACK>::type stk(stack_area);
+  LeanState s;
 
-  // warp-uniform tile pool
+  // warp-uniform tile pool (PERSISTENT)
   constexpr int kTilePix = 64;            // 8x8 pixels, handed out in Morton order
   int pool_next = kTilePix, tile_x0 = 0, tile_y0 = 0;
-  bool pool_empty = false;
+  bool pool_empty = !PERSISTENT;
 
   // per-lane pixel state
   int state = kLaneIdle;
   int x = 0, y = 0;
-  uint32_t pixel = 0;
-  float dx = 0.f, dy = 0.f, dz = 0.f;     // direction of the ray being traversed
   // secondary-ray stage machine (SEC only): stage 0 = primary, 1 = shadow, 2.. = AO samples
   int stage = 0;
-  uint32_t sdata = 0; float nx = 0.f, ny = 0.f, nz = 0.f, Ox = 0.f, Oy = 0.f, Oz = 0.f;
+  uint32_t sdata = 0; float Ox = 0.f, Oy = 0.f, Oz = 0.f;
   float dl = 0.f, vis = 1.f, slen = 0.f; int occ = 0;
 
+  if (!PERSISTENT) {
+    // one CTA per 16x8 tile: warp w covers an 8x4 block
+    const int warp = threadIdx.x >> 5;
+    const int tiles_x16 = (p.width + 15) >> 4;
+    const int tx = blockIdx.x % tiles_x16, ty = blockIdx.x / tiles_x16;
+    x = tx * 16 + (warp & 1) * 8 + (lane & 7);
+    y = p.y0 + ty * 8 + (warp >> 1) * 4 + (lane >> 3);
+    if (x < p.width && y < p.y1) state = kLaneNew;
+  }
+
   for (;;) {
-    // ---- 1. hand new pixels to idle lanes --------------------------------------------------
-    unsigned idle = __ballot_sync(kFullMask, state == kLaneIdle);
-    while (idle != 0u && !pool_empty) {
-      if (pool_next >= kTilePix) {
-        unsigned t = 0;
-        if (lane == 0) t = atomicAdd(p.tile_counter, 1u);
-        t = __shfl_sync(kFullMask, t, 0);
-        if (t >= (unsigned)p.num_tiles) { pool_empty = true; break; }
-        tile_x0 = (int)(t % (unsigned)p.tiles_x) * 8;
-        tile_y0 = p.y0 + (int)(t / (unsigned)p.tiles_x) * 8;
-        pool_next = 0;
+    // ---- 1. hand new pixels to idle lanes (persistent schedule) -----------------------------
+    if (PERSISTENT) {
+      unsigned idle = __ballot_sync(kFullMask, state == kLaneIdle);
+      while (idle != 0u && !pool_empty) {
+        if (pool_next >= kTilePix) {
+          unsigned t = 0;
+          if (lane == 0) t = atomicAdd(p.tile_counter, 1u);
+          t = __shfl_sync(kFullMask, t, 0);
+          if (t >= (unsigned)p.num_tiles) { pool_empty = true; break; }
+          tile_x0 = (int)(t % (unsigned)p.tiles_x) * 8;
+          tile_y0 = p.y0 + (int)(t / (unsigned)p.tiles_x) * 8;
+          pool_next = 0;
+        }
+        const int take = min(__popc(idle), kTilePix - pool_next);
+        const int rank = __popc(idle & lt_mask);
+        if (state == kLaneIdle && rank < take) {
+          const int m = pool_next + rank;   // Morton index inside the tile
+          x = tile_x0 + ((m & 1) | ((m >> 1) & 2) | ((m >> 2) & 4));
+          y = tile_y0 + (((m >> 1) & 1) | ((m >> 2) & 2) | ((m >> 3) & 4));
+          if (x < p.width && y < p.y1) state = kLaneNew;
+        }
+        pool_next += take;
+        idle = __ballot_sync(kFullMask, state == kLaneIdle);
       }
-      const int take = min(__popc(idle), kTilePix - pool_next);
-      const int rank = __popc(idle & lt_mask);
-      if (state == kLaneIdle && rank < take) {
-        const int m = pool_next + rank;   // Morton index inside the tile
-        x = tile_x0 + ((m & 1) | ((m >> 1) & 2) | ((m >> 2) & 4));
-        y = tile_y0 + (((m >> 1) & 1) | ((m >> 2) & 2) | ((m >> 3) & 4));
-        if (x < p.width && y < p.y1) state = kLaneNew;
-      }
-      pool_next += take;
-      idle = __ballot_sync(kFullMask, state == kLaneIdle);
     }
 
-    // ---- 2. primary ray set-up for the new lanes --------------------------------------------
+    // ---- 2. primary ray set-up for the new lanes ----------------------------------------------
     if (state == kLaneNew) {
-      pixel = (uint32_t)y * (uint32_t)p.width + (uint32_t)x;
-      if (COUNT) { fetch.visits = 0; pops = 0; }
+      if (COUNT) { fetch.visits = 0; fetch.revisits = 0; }
+      float dx, dy, dz;
       primary_dir(p.dir0, p.du, p.dv, x, y, dx, dy, dz);
       dx = adjust_dir1(dx); dy = adjust_dir1(dy); dz = adjust_dir1(dz);
       stage = 0;
-      state = kLaneMiss;
-      if (setup_trace(p.pos[0], p.pos[1], p.pos[2], dx, dy, dz, s) &&
-          trace_enter_root(s, rec, fetch, p.root_valid != 0u))
-        state = kLaneActive;
+      stk.reset();
+      state = lean_begin(s, fetch, p.root_valid != 0u, p.pos[0], p.pos[1], p.pos[2], dx, dy, dz) ? kLaneActive : kLaneMiss;
     }
 
-    // ---- 3. traversal: all lanes step in lock-step until too few are left --------------------
-    for (;;) {
-      const unsigned am = __ballot_sync(kFullMask, state == kLaneActive);
-      if (am == 0u) break;
-      if (!pool_empty && __popc(am) <= kRefillThreshold) break;
+    // ---- 3. traversal: one lean_step per live lane per iteration --------------------------------
+    for (int it = 0;; ++it) {
+      if ((it & 1) == 0) {
+        const unsigned am = __ballot_sync(kFullMask, state == kLaneActive);
+        if (am == 0u) break;
+        if (PERSISTENT && !pool_empty && __popc(am) <= kRefillThreshold) break;
+      }
       if (state == kLaneActive) {
-        const int sp0 = s.sp;
-        const int r = trace_step(s, rec, fetch, stk, SEC && stage > 0);
-        if (COUNT && s.sp < sp0) ++pops;
+        const int r = lean_step(s, fetch, stk, SEC && stage > 0);
         if (r == kStepHit) state = kLaneHit;
         else if (r == kStepMiss) state = kLaneMiss;
       }
     }
 
-    // ---- 4. finished rays: shade / spawn the next secondary ray / store ----------------------
+    // ---- 4. finished rays: shade / spawn the next secondary ray / store -------------------------
     if (state == kLaneHit || state == kLaneMiss) {
       const bool hit = state == kLaneHit;
+      const uint32_t pixel = (uint32_t)y * (uint32_t)p.width + (uint32_t)x;
       bool done = true;
       uint32_t rgba = 0u;
+      float nx = 0.f, ny = 0.f, nz = 0.f;
       if (!SEC || stage == 0) {
         uint32_t hn = YV_MISS_NODE; int32_t hc = YV_MISS_CHILD; float ht = 0.0f;
         if (hit) {
+          const Rec rec = fetch.load(s.idx);                      // re-read the hit node's record
           const uint32_t c = s.ch ^ s.flags;
           hn = rec.orig_id; hc = (int32_t)c; ht = max3f(s.t1x, s.t1y, s.t1z);
           sdata = leaf_data(p, rec, c);
           unpack_normal(sdata, nx, ny, nz);
+          float dx, dy, dz;                                       // the primary direction, recomputed
+          primary_dir(p.dir0, p.du, p.dv, x, y, dx, dy, dz);
+          dx = adjust_dir1(dx); dy = adjust_dir1(dy); dz = adjust_dir1(dz);
           const float Px = YV_FADD(p.pos[0], YV_FMUL(dx, ht));
           const float Py = YV_FADD(p.pos[1], YV_FMUL(dy, ht));
           const float Pz = YV_FADD(p.pos[2], YV_FMUL(dz, ht));
@@ -301,7 +265,7 @@ __global__ void __launch_bounds__(THREADS) render_persistent(const __grid_consta
             done = false;           // secondary stages follow
           }
         }
-        if (HITS) { p.hit_node[pixel] = hn; p.hit_child[pixel] = hc; p.hit_t[pixel] = ht; }
+        if (p.hit_node) { p.hit_node[pixel] = hn; p.hit_child[pixel] = hc; p.hit_t[pixel] = ht; }
       } else {
         // a secondary ray came back
         const float ts = max3f(s.t1x, s.t1y, s.t1z);
@@ -323,10 +287,12 @@ __global__ void __launch_bounds__(THREADS) render_persistent(const __grid_consta
             if (!(slen > 0)) continue;
             rx = YV_FDIV(vx, slen); ry = YV_FDIV(vy, slen); rz = YV_FDIV(vz, slen);
           } else {
+            if (stage > 1 && nx == 0.f && ny == 0.f && nz == 0.f) unpack_normal(sdata, nx, ny, nz);
             ao_direction(nx, ny, nz, pixel, (uint32_t)(stage - 2), p.seed, rx, ry, rz);
           }
           rx = adjust_dir1(rx); ry = adjust_dir1(ry); rz = adjust_dir1(rz);
-          if (setup_trace(Ox, Oy, Oz, rx, ry, rz, s) && trace_enter_root(s, rec, fetch, p.root_valid != 0u))
+          stk.reset();
+          if (lean_begin(s, fetch, p.root_valid != 0u, Ox, Oy, Oz, rx, ry, rz))
             launched = true;          // otherwise this secondary ray misses outright: unoccluded
         }
         if (launched) state = kLaneActive;
@@ -340,12 +306,12 @@ __global__ void __launch_bounds__(THREADS) render_persistent(const __grid_consta
       }
       if (done) {
         p.out_rgba[pixel] = rgba;
-        if (COUNT) p.counters[pixel] = ((fetch.visits - pops) & 0xffffu) | (pops << 16);
+        if (COUNT) p.counters[pixel] = (fetch.visits & 0xffffu) | (fetch.revisits << 16);
         state = kLaneIdle;
       }
     }
 
-    // ---- 5. the warp retires when the queue is dry and every lane is idle --------------------
+    // ---- 5. the warp retires when no pixel is pending and the queue is dry -----------------------
     if (pool_empty && __ballot_sync(kFullMask, state != kLaneIdle) == 0u) break;
   }
 }
@@ -358,12 +324,19 @@ __global__ void __launch_bounds__(128) trace_rays_kernel(const uint4 *recs, uint
                                                          uint32_t *node, int32_t *child, float *t) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  NodeFetch<false> fetch = { recs, nullptr, 0u, 0u, 0u };
-  LocalStack stk;
+  NodeFetch<false, false> fetch = { recs, nullptr, 0u, 0u, 0u };
+  LocalStack stk(nullptr);
   RayState s; Rec rec;
-  uint32_t pops = 0;
-  const bool hit = trace_to_end<false, false>(fetch, root_valid != 0u, stk, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2],
-                                              dir[3 * i], dir[3 * i + 1], dir[3 * i + 2], s, rec, pops);
+  float dx = adjust_dir1(dir[3 * i]), dy = adjust_dir1(dir[3 * i + 1]), dz = adjust_dir1(dir[3 * i + 2]);
+  bool hit = false;
+  if (setup_trace(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], dx, dy, dz, s) &&
+      trace_enter_root(s, rec, fetch, root_valid != 0u)) {
+    for (;;) {
+      const int r = trace_step(s, rec, fetch, stk, false);
+      if (r == kStepHit) { hit = true; break; }
+      if (r == kStepMiss) break;
+    }
+  }
   node[i] = hit ? rec.orig_id : YV_MISS_NODE;
   child[i] = hit ? (int32_t)(s.ch ^ s.flags) : YV_MISS_CHILD;
   t[i] = hit ? max3f(s.t1x, s.t1y, s.t1z) : 0.0f;

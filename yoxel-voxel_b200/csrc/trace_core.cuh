@@ -18,6 +18,7 @@
 #pragma once
 
 #include <cstdint>
+#include <cstring>
 #include <cmath>
 
 #include "../../include/yv_format.h"
@@ -114,7 +115,7 @@ struct StackEntry { float t1x, t1y, t1z; uint32_t idx; float t2x, t2y, t2z; uint
 //                        so a leaf behind the origin can be reported with t < 0 — SURVEY §8a10)
 //   front_only = true  : secondary rays: a leaf counts only if its own min(t2) > 0
 // (a run-time flag, so primary and secondary rays of one warp share a single instruction stream)
-// fetch(idx) returns the packed record; each call is one node fetch.
+// fetch.get(idx, visit) returns the packed record (visit = false for the re-fetch after a pop).
 template <class Fetch, class Stack>
 YV_HD int trace_step(RayState &s, Rec &rec, const Fetch &fetch, Stack &stk, const bool front_only) {
   const uint32_t c = s.ch ^ s.flags;
@@ -142,7 +143,7 @@ YV_HD int trace_step(RayState &s, Rec &rec, const Fetch &fetch, Stack &stk, cons
       ++s.sp;
     }
     s.idx = rec.child_base + (uint32_t)YV_POPC((rec.masks >> 8) & (bit - 1u));
-    rec = fetch(s.idx);                                                             // :23
+    rec = fetch.get(s.idx, true);                                                   // :23
     find_first_child(s);                                                            // :24
     return kStepContinue;
   }
@@ -155,7 +156,188 @@ YV_HD int trace_step(RayState &s, Rec &rec, const Fetch &fetch, Stack &stk, cons
   const StackEntry en = stk.pop(s.sp);
   s.t1x = en.t1x; s.t1y = en.t1y; s.t1z = en.t1z; s.t2x = en.t2x; s.t2y = en.t2y; s.t2z = en.t2z;
   s.idx = en.idx; s.ch = en.ch;
-  rec = fetch(s.idx);              // re-fetch of the parent (not an algorithmic node visit)
+  rec = fetch.get(s.idx, false);   // re-fetch of the parent (not an algorithmic node visit)
+  return kStepContinue;
+}
+
+// ---- phase-split form of the same loop (what the kernels run) ------------------------------------
+// A warp executes the union of its lanes' paths, so the kernels split a node visit into two phases
+// and re-converge between them:
+//   seek_child : cheap, register-only. Walk the current node's children in ray order (leaf test,
+//                entry test, GoNext) until the ray hits a leaf, finds a child node to enter, or
+//                runs out of siblings. At most 4 iterations.
+//   enter_node : the expensive part every live lane needs next — push+descend or pop, ONE node fetch,
+//                FindFirstChild.
+// seek_child followed by enter_node is exactly trace_step iterated until it fetches (or ends).
+enum : int { kSeekHit = 1, kSeekDescend = 2, kSeekPop = 3 };
+
+struct SeekResult {
+  StackEntry resume;   // parent's state after GoNext (valid when can_adv)
+  bool can_adv;
+};
+
+YV_HD int seek_child(RayState &s, const Rec &rec, const bool front_only, SeekResult &out) {
+  for (;;) {
+    const uint32_t c = s.ch ^ s.flags;
+    const uint32_t bit = 1u << c;
+    const float t2min = min3f(s.t2x, s.t2y, s.t2z);
+    const bool leaf = ((rec.masks & bit) != 0u) && (!front_only || t2min > 0.0f);             // :27
+    const bool descend = (((rec.masks >> 8) & bit) != 0u) && (t2min > 0.0f);                   // :20,:35
+    const uint32_t e = (s.t2x > s.t2y) ? ((s.t2y < s.t2z) ? 1u : 2u) : ((s.t2x < s.t2z) ? 0u : 2u);
+    const bool can_adv = (s.ch & (1u << e)) == 0u;                                             // :38
+    const float a = e == 0u ? s.t1x : (e == 1u ? s.t1y : s.t1z);
+    const float b = e == 0u ? s.t2x : (e == 1u ? s.t2y : s.t2z);
+    const float nb = YV_FADD(b, YV_FSUB(b, a));
+    const float n1x = e == 0u ? b : s.t1x, n1y = e == 1u ? b : s.t1y, n1z = e == 2u ? b : s.t1z;
+    const float n2x = e == 0u ? nb : s.t2x, n2y = e == 1u ? nb : s.t2y, n2z = e == 2u ? nb : s.t2z;
+    const uint32_t nch = s.ch ^ (1u << e);
+    if (leaf) return kSeekHit;
+    if (descend || !can_adv) {
+      out.resume.t1x = n1x; out.resume.t1y = n1y; out.resume.t1z = n1z; out.resume.idx = s.idx;
+      out.resume.t2x = n2x; out.resume.t2y = n2y; out.resume.t2z = n2z; out.resume.ch = nch;
+      out.can_adv = can_adv;
+      return descend ? kSeekDescend : kSeekPop;
+    }
+    s.t1x = n1x; s.t1y = n1y; s.t1z = n1z; s.t2x = n2x; s.t2y = n2y; s.t2z = n2z; s.ch = nch;
+  }
+}
+
+// returns kStepContinue, or kStepMiss when a pop finds the stack empty
+template <class Fetch, class Stack>
+YV_HD int enter_node(RayState &s, Rec &rec, const Fetch &fetch, Stack &stk, const int need, const SeekResult &sk) {
+  const bool descend = need == kSeekDescend;
+  if (descend) {
+    if (sk.can_adv) { stk.push(s.sp, sk.resume); ++s.sp; }
+    const uint32_t bit = 1u << (s.ch ^ s.flags);
+    s.idx = rec.child_base + (uint32_t)YV_POPC((rec.masks >> 8) & (bit - 1u));
+  } else {
+    if (s.sp == 0) return kStepMiss;
+    --s.sp;
+    const StackEntry en = stk.pop(s.sp);
+    s.t1x = en.t1x; s.t1y = en.t1y; s.t1z = en.t1z; s.t2x = en.t2x; s.t2y = en.t2y; s.t2z = en.t2z;
+    s.idx = en.idx; s.ch = en.ch;
+  }
+  rec = fetch.get(s.idx, descend);                                                             // :23
+  if (descend) find_first_child(s);                                                            // :24
+  return kStepContinue;
+}
+
+// ---- lean form (what render_frame runs) ----------------------------------------------------------
+// Same decisions and the same float operations as trace_step, arranged for instruction count:
+//   * the exit parameter an axis takes when it is stepped, N = t2 + (t2 - t1) (GoNext,
+//     trace_spu.cpp:84-90), is evaluated for all three axes once per node (after FindFirstChild or a
+//     pop) instead of being selected per sibling step, so a step is six predicated moves;
+//   * argmin(t2) yields the exit axis and min(t2) together;
+//   * push stores the parent's registers as they are plus the exit axis; the GoNext the recursion
+//     would run after the child returns (ppu_renderer.cpp:38) is applied when the entry is popped;
+//   * descend and pop share one node fetch and one evaluation of N.
+// Only child_base and the two masks of a record stay in registers; a hit re-reads its record.
+struct LeanState {
+  float t1x, t1y, t1z;   // entry parameters of the current child cube
+  float Tx, Ty, Tz;      // exit parameters (t2)
+  float Nx, Ny, Nz;      // t2 + (t2 - t1) per axis, valid while that axis' ch bit is clear
+  uint32_t ch, flags, idx;
+  uint32_t masks, child_base;
+  int sp;
+};
+
+struct U4 { uint32_t x, y, z, w; };
+
+#if defined(__CUDA_ARCH__)
+#define YV_F2U(f) __float_as_uint(f)
+#define YV_U2F(u) __uint_as_float(u)
+#else
+YV_HD uint32_t yv_f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+YV_HD float yv_u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+#define YV_F2U(f) yv_f2u(f)
+#define YV_U2F(u) yv_u2f(u)
+#endif
+
+YV_HD void lean_eval_next(LeanState &s) {
+  s.Nx = YV_FADD(s.Tx, YV_FSUB(s.Tx, s.t1x));
+  s.Ny = YV_FADD(s.Ty, YV_FSUB(s.Ty, s.t1y));
+  s.Nz = YV_FADD(s.Tz, YV_FSUB(s.Tz, s.t1z));
+}
+
+// branch-free on purpose: lanes of one warp step different axes, selects keep them converged
+YV_HD void lean_apply_step(LeanState &s, const uint32_t e) {
+  const bool ex = e == 0u, ey = e == 1u, ez = e == 2u;
+  s.t1x = ex ? s.Tx : s.t1x; s.Tx = ex ? s.Nx : s.Tx;
+  s.t1y = ey ? s.Ty : s.t1y; s.Ty = ey ? s.Ny : s.Ty;
+  s.t1z = ez ? s.Tz : s.t1z; s.Tz = ez ? s.Nz : s.Tz;
+  s.ch |= (ex || ey || ez) ? (1u << e) : 0u;
+}
+
+// FindFirstChild on (t1, T); fmaxf is used only where the result is compared, never stored
+YV_HD void lean_first_child(LeanState &s) {
+  const float tmx = YV_FMUL(0.5f, YV_FADD(s.t1x, s.Tx));
+  const float tmy = YV_FMUL(0.5f, YV_FADD(s.t1y, s.Ty));
+  const float tmz = YV_FMUL(0.5f, YV_FADD(s.t1z, s.Tz));
+  const float te = fmaxf(fmaxf(s.t1x, s.t1y), s.t1z);
+  const bool fx = te > tmx, fy = te > tmy, fz = te > tmz;
+  s.t1x = fx ? tmx : s.t1x; s.Tx = fx ? s.Tx : tmx;
+  s.t1y = fy ? tmy : s.t1y; s.Ty = fy ? s.Ty : tmy;
+  s.t1z = fz ? tmz : s.t1z; s.Tz = fz ? s.Tz : tmz;
+  s.ch = (fx ? 1u : 0u) | (fy ? 2u : 0u) | (fz ? 4u : 0u);
+}
+
+template <class Fetch>
+YV_HD void lean_load_node(LeanState &s, const Fetch &fetch, const bool visit) {
+  const Rec r = fetch.get(s.idx, visit);
+  s.masks = r.masks; s.child_base = r.child_base;
+}
+
+// SetupTrace + RecTrace's entry test on the root. Returns false on an immediate miss.
+template <class Fetch>
+YV_HD bool lean_begin(LeanState &s, const Fetch &fetch, const bool root_valid,
+                      float px, float py, float pz, float dx, float dy, float dz) {
+  RayState r;
+  if (!setup_trace(px, py, pz, dx, dy, dz, r)) return false;
+  if (!root_valid || fminf(fminf(r.t2x, r.t2y), r.t2z) <= 0.0f) return false;
+  s.t1x = r.t1x; s.t1y = r.t1y; s.t1z = r.t1z; s.Tx = r.t2x; s.Ty = r.t2y; s.Tz = r.t2z;
+  s.flags = r.flags; s.sp = 0; s.idx = 0u;
+  lean_load_node(s, fetch, true);
+  lean_first_child(s);
+  lean_eval_next(s);
+  return true;
+}
+
+// One micro-step: test the current child; then either take one sibling step, or (descend | pop).
+// Stack: push(sp, U4, U4) / pop(sp, U4&, U4&).
+template <class Fetch, class Stack>
+YV_HD int lean_step(LeanState &s, const Fetch &fetch, Stack &stk, const bool front_only) {
+  const uint32_t bit = 1u << (s.ch ^ s.flags);
+  const bool xy = s.Tx > s.Ty;
+  const bool nz = xy ? (s.Ty < s.Tz) : (s.Tx < s.Tz);
+  const uint32_t e = nz ? (xy ? 1u : 0u) : 2u;                     // argmin with the reference's tie order
+  const float tmin = fminf(fminf(s.Tx, s.Ty), s.Tz);               // compared only
+  if (((s.masks & bit) != 0u) && (!front_only || tmin > 0.0f)) return kStepHit;             // :27
+  const bool descend = (((s.masks >> 8) & bit) != 0u) && (tmin > 0.0f);                      // :20,:35
+  const bool can_adv = ((s.ch >> e) & 1u) == 0u;                                             // :38
+  if (!descend && can_adv) { lean_apply_step(s, e); return kStepContinue; }
+
+  uint32_t pending = 3u;                                           // exit axis to apply after a pop (3 = none)
+  if (descend) {
+    if (can_adv) {
+      const U4 a = { YV_F2U(s.t1x), YV_F2U(s.t1y), YV_F2U(s.t1z), s.idx };
+      const U4 b = { YV_F2U(s.Tx), YV_F2U(s.Ty), YV_F2U(s.Tz), s.ch | (e << 3) };
+      stk.push(s.sp, a, b);
+      ++s.sp;
+    }
+    s.idx = s.child_base + (uint32_t)YV_POPC((s.masks >> 8) & (bit - 1u));
+  } else {
+    if (s.sp == 0) return kStepMiss;
+    --s.sp;
+    U4 a, b;
+    stk.pop(s.sp, a, b);
+    s.t1x = YV_U2F(a.x); s.t1y = YV_U2F(a.y); s.t1z = YV_U2F(a.z); s.idx = a.w;
+    s.Tx = YV_U2F(b.x); s.Ty = YV_U2F(b.y); s.Tz = YV_U2F(b.z);
+    s.ch = b.w & 7u; pending = b.w >> 3;
+  }
+  lean_load_node(s, fetch, descend);                                                         // :23
+  if (descend) lean_first_child(s);                                                          // :24
+  lean_eval_next(s);
+  lean_apply_step(s, pending);                                     // the parent's deferred GoNext (no-op for 3)
   return kStepContinue;
 }
 

@@ -75,10 +75,9 @@ struct yv_renderer {
   bool timed = false;
   int launches = 0;
   // options
-  int opt_smem_nodes = 585;           // four levels: 1 + 8 + 64 + 512
+  int opt_smem_nodes = 0;             // records staged in shared memory (585 = four levels)
   int opt_persistent = 0;
-  int opt_refill = 1;
-  int opt_threads = 128;
+  int opt_stack = 0;                  // yv::kStackLocal / kStackRing4
 };
 
 namespace {
@@ -177,31 +176,44 @@ void init_ray_dir(const yv_renderer *r, float dir0[3], float du[3], float dv[3])
   init_ray_dir_raw(r->dir, r->up, r->fov, r->width, r->height, dir0, du, dv);
 }
 
-template <bool HITS, bool SEC, bool COUNT>
-int launch_variant(yv_renderer *r, const yv::RenderParams &p, size_t smem) {
-  if (r->opt_persistent) {
-    constexpr int kThreads = 128;
-    auto kern = yv::render_persistent<HITS, SEC, COUNT, kThreads>;
+template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED>
+int launch_kernel(yv_renderer *r, const yv::RenderParams &p, size_t smem) {
+  auto kern = yv::render_frame<SEC, COUNT, STACK, PERSISTENT, STAGED>;
+  YV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long grid;
+  if (PERSISTENT) {
     int per_sm = 0;
-    YV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    YV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+    YV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, yv::kCtaThreads, smem));
     if (per_sm < 1) per_sm = 1;
+    grid = (long)r->sm_count * per_sm;
     const long warps_needed = ((long)p.num_tiles * 64 + 31) / 32;
-    long grid = (long)r->sm_count * per_sm;
-    const long max_useful = (warps_needed + kThreads / 32 - 1) / (kThreads / 32);
+    const long max_useful = (warps_needed + yv::kCtaThreads / 32 - 1) / (yv::kCtaThreads / 32);
     if (grid > max_useful) grid = std::max(1l, max_useful);
     YV_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(unsigned int), r->stream));
-    kern<<<(unsigned)grid, kThreads, smem, r->stream>>>(p);
   } else {
-    auto kern = yv::render_tiles<HITS, SEC, COUNT>;
-    YV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int tiles_x16 = (p.width + 15) / 16;
-    const int tiles_y8 = (p.y1 - p.y0 + 7) / 8;
-    const long grid = (long)tiles_x16 * tiles_y8;
-    if (grid > 0) kern<<<(unsigned)grid, 128, smem, r->stream>>>(p);
+    grid = (long)((p.width + 15) / 16) * ((p.y1 - p.y0 + 7) / 8);
   }
+  if (grid > 0) kern<<<(unsigned)grid, yv::kCtaThreads, smem, r->stream>>>(p);
   YV_CUDA(cudaGetLastError());
   return YV_OK;
+}
+
+template <bool SEC, bool COUNT, int STACK, bool PERSISTENT>
+int launch_staged(yv_renderer *r, const yv::RenderParams &p, size_t smem) {
+  return p.smem_nodes > 0 ? launch_kernel<SEC, COUNT, STACK, PERSISTENT, true>(r, p, smem)
+                          : launch_kernel<SEC, COUNT, STACK, PERSISTENT, false>(r, p, smem);
+}
+
+template <bool SEC, bool COUNT, int STACK>
+int launch_schedule(yv_renderer *r, const yv::RenderParams &p, size_t smem) {
+  return r->opt_persistent ? launch_staged<SEC, COUNT, STACK, true>(r, p, smem)
+                           : launch_staged<SEC, COUNT, STACK, false>(r, p, smem);
+}
+
+template <bool SEC, bool COUNT>
+int launch_stack(yv_renderer *r, const yv::RenderParams &p, size_t smem) {
+  return r->opt_stack == yv::kStackRing4 ? launch_schedule<SEC, COUNT, yv::kStackRing4>(r, p, smem)
+                                         : launch_schedule<SEC, COUNT, yv::kStackLocal>(r, p, smem);
 }
 
 int launch_frame(yv_renderer *r, void *d_rgba) {
@@ -228,26 +240,23 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
   p.y1 = r->rows_set ? std::min(r->height, r->y1) : r->height;
   if (p.y1 < p.y0) p.y1 = p.y0;
   p.out_rgba = (uint32_t *)d_rgba;
-  p.hit_node = r->d_hit_node; p.hit_child = r->d_hit_child; p.hit_t = r->d_hit_t;
+  if (r->hits) { p.hit_node = r->d_hit_node; p.hit_child = r->d_hit_child; p.hit_t = r->d_hit_t; }
   p.counters = r->d_counters;
   p.tile_counter = r->d_tile_counter;
   p.tiles_x = (p.width + 7) / 8;
   p.num_tiles = p.tiles_x * ((p.y1 - p.y0 + 7) / 8);
   p.shadow = r->shadow; p.ao_samples = r->ao_samples; p.seed = r->seed;
   p.voxel_size = r->voxel_size; p.ao_max_t = r->ao_max_t;
-  const size_t smem = (size_t)p.smem_nodes * sizeof(uint4);
+  const size_t smem = (size_t)p.smem_nodes * sizeof(uint4) + yv::stack_smem_bytes(r->opt_stack);
+  if (smem > 227 * 1024) return fail(YV_ERR_ARG, "shared-memory request exceeds 227 KB (lower smem_nodes or change stack)");
 
   YV_CUDA(cudaEventRecord(r->ev0, r->stream));
-  const int key = (r->hits ? 4 : 0) | (sec ? 2 : 0) | (r->counters ? 1 : 0);
+  const int key = (sec ? 2 : 0) | (r->counters ? 1 : 0);
   switch (key) {
-    case 0: rc = launch_variant<false, false, false>(r, p, smem); break;
-    case 1: rc = launch_variant<false, false, true>(r, p, smem); break;
-    case 2: rc = launch_variant<false, true, false>(r, p, smem); break;
-    case 3: rc = launch_variant<false, true, true>(r, p, smem); break;
-    case 4: rc = launch_variant<true, false, false>(r, p, smem); break;
-    case 5: rc = launch_variant<true, false, true>(r, p, smem); break;
-    case 6: rc = launch_variant<true, true, false>(r, p, smem); break;
-    default: rc = launch_variant<true, true, true>(r, p, smem); break;
+    case 0: rc = launch_stack<false, false>(r, p, smem); break;
+    case 1: rc = launch_stack<false, true>(r, p, smem); break;
+    case 2: rc = launch_stack<true, false>(r, p, smem); break;
+    default: rc = launch_stack<true, true>(r, p, smem); break;
   }
   if (rc) return rc;
   YV_CUDA(cudaEventRecord(r->ev1, r->stream));
@@ -594,7 +603,11 @@ int yv_set_option(yv_renderer *r, const char *name, int value) {
   std::string n(name);
   if (n == "smem_nodes") { if (value < 0 || value > 12288) return fail(YV_ERR_ARG, "smem_nodes must be 0..12288"); r->opt_smem_nodes = value; }
   else if (n == "persistent") r->opt_persistent = value ? 1 : 0;
-  else if (n == "refill") r->opt_refill = value ? 1 : 0;
+  else if (n == "stack") {
+    if (value != yv::kStackLocal && value != yv::kStackRing4)
+      return fail(YV_ERR_ARG, "stack must be 0 (local memory) or 4 (4-entry shared ring + local spill)");
+    r->opt_stack = value;
+  }
   else return fail(YV_ERR_ARG, "unknown option " + n);
   return YV_OK;
 }
@@ -604,7 +617,7 @@ int yv_get_option(const yv_renderer *r, const char *name, int *value) {
   std::string n(name);
   if (n == "smem_nodes") *value = r->opt_smem_nodes;
   else if (n == "persistent") *value = r->opt_persistent;
-  else if (n == "refill") *value = r->opt_refill;
+  else if (n == "stack") *value = r->opt_stack;
   else return fail(YV_ERR_ARG, "unknown option " + n);
   return YV_OK;
 }
