@@ -53,6 +53,7 @@ struct RenderParams {
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kRefillThreshold = 20;   // refill once <= this many lanes are still traversing
 constexpr int kCtaThreads = 128;
+constexpr int kStepsPerVote = 4;       // lean_steps between two warp votes on "anyone still traversing?"
 
 enum : int { kStackLocal = 0, kStackRing4 = 4 };
 
@@ -220,16 +221,17 @@ __global__ void __launch_bounds__(kCtaThreads) render_frame(const __grid_constan
     }
 
     // ---- 3. traversal: one lean_step per live lane per iteration --------------------------------
-    for (int it = 0;; ++it) {
-      if ((it & 1) == 0) {
-        const unsigned am = __ballot_sync(kFullMask, state == kLaneActive);
-        if (am == 0u) break;
-        if (PERSISTENT && !pool_empty && __popc(am) <= kRefillThreshold) break;
-      }
-      if (state == kLaneActive) {
-        const int r = lean_step(s, fetch, stk, SEC && stage > 0);
-        if (r == kStepHit) state = kLaneHit;
-        else if (r == kStepMiss) state = kLaneMiss;
+    for (;;) {
+      const unsigned am = __ballot_sync(kFullMask, state == kLaneActive);
+      if (am == 0u) break;
+      if (PERSISTENT && !pool_empty && __popc(am) <= kRefillThreshold) break;
+#pragma unroll
+      for (int u = 0; u < kStepsPerVote; ++u) {
+        if (state == kLaneActive) {
+          const int r = lean_step(s, fetch, stk, SEC && stage > 0);
+          if (r == kStepHit) state = kLaneHit;
+          else if (r == kStepMiss) state = kLaneMiss;
+        }
       }
     }
 

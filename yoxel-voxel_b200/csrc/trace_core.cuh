@@ -259,13 +259,15 @@ YV_HD void lean_eval_next(LeanState &s) {
   s.Nz = YV_FADD(s.Tz, YV_FSUB(s.Tz, s.t1z));
 }
 
-// branch-free on purpose: lanes of one warp step different axes, selects keep them converged
-YV_HD void lean_apply_step(LeanState &s, const uint32_t e) {
-  const bool ex = e == 0u, ey = e == 1u, ez = e == 2u;
+// The exit axis is carried one-hot (bit 0 = x, 1 = y, 2 = z; 0 = no step) so that "already in the
+// upper half" is one AND with ch and the step is six selects — branch-free on purpose: lanes of one
+// warp step different axes, selects keep them converged.
+YV_HD void lean_apply_step(LeanState &s, const uint32_t ebits) {
+  const bool ex = (ebits & 1u) != 0u, ey = (ebits & 2u) != 0u, ez = (ebits & 4u) != 0u;
   s.t1x = ex ? s.Tx : s.t1x; s.Tx = ex ? s.Nx : s.Tx;
   s.t1y = ey ? s.Ty : s.t1y; s.Ty = ey ? s.Ny : s.Ty;
   s.t1z = ez ? s.Tz : s.t1z; s.Tz = ez ? s.Nz : s.Tz;
-  s.ch |= (ex || ey || ez) ? (1u << e) : 0u;
+  s.ch |= ebits;
 }
 
 // FindFirstChild on (t1, T); fmaxf is used only where the result is compared, never stored
@@ -309,14 +311,14 @@ YV_HD int lean_step(LeanState &s, const Fetch &fetch, Stack &stk, const bool fro
   const uint32_t bit = 1u << (s.ch ^ s.flags);
   const bool xy = s.Tx > s.Ty;
   const bool nz = xy ? (s.Ty < s.Tz) : (s.Tx < s.Tz);
-  const uint32_t e = nz ? (xy ? 1u : 0u) : 2u;                     // argmin with the reference's tie order
+  const uint32_t e = nz ? (xy ? 2u : 1u) : 4u;                     // argmin(t2), one-hot, the reference's tie order
   const float tmin = fminf(fminf(s.Tx, s.Ty), s.Tz);               // compared only
   if (((s.masks & bit) != 0u) && (!front_only || tmin > 0.0f)) return kStepHit;             // :27
   const bool descend = (((s.masks >> 8) & bit) != 0u) && (tmin > 0.0f);                      // :20,:35
-  const bool can_adv = ((s.ch >> e) & 1u) == 0u;                                             // :38
+  const bool can_adv = (s.ch & e) == 0u;                                                     // :38
   if (!descend && can_adv) { lean_apply_step(s, e); return kStepContinue; }
 
-  uint32_t pending = 3u;                                           // exit axis to apply after a pop (3 = none)
+  uint32_t pending = 0u;                                           // exit axis (one-hot) to apply after a pop
   if (descend) {
     if (can_adv) {
       const U4 a = { YV_F2U(s.t1x), YV_F2U(s.t1y), YV_F2U(s.t1z), s.idx };
@@ -337,7 +339,7 @@ YV_HD int lean_step(LeanState &s, const Fetch &fetch, Stack &stk, const bool fro
   lean_load_node(s, fetch, descend);                                                         // :23
   if (descend) lean_first_child(s);                                                          // :24
   lean_eval_next(s);
-  lean_apply_step(s, pending);                                     // the parent's deferred GoNext (no-op for 3)
+  lean_apply_step(s, pending);                                     // the parent's deferred GoNext (no-op for 0)
   return kStepContinue;
 }
 
