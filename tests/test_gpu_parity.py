@@ -246,3 +246,25 @@ def test_full_size_config2_depth12_1080p():
     img2, *_ = _render_gpu(r, cam, 1920, 1080)
     assert (img2 == img).all()
     r.close()
+
+
+def test_cpp_adapter_renders_like_cell_main(tmp_path):
+    """The C++ ISVORenderer adapter driven like cell/main.cpp:21-40 (1024x768, eye (0.5,0.5,0.3))."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-s", "-C", os.path.join(root, "tools")])
+    svo = scenes.fractal(9)
+    vox = str(tmp_path / "scene.vox")
+    svo.Save(vox)
+    out = str(tmp_path / "frame.ppm")
+    p = subprocess.run([os.path.join(root, "tools", "render_main"), vox, out, "1024", "768", "-1", "-1", "1.5"],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert "time:" in p.stdout
+    raw = open(out, "rb").read()
+    hdr = b"P6\n1024 768\n255\n"
+    assert raw.startswith(hdr)
+    img = np.frombuffer(raw[len(hdr):], np.uint8).reshape(768, 1024, 3)
+    o = _render_cpu(svo, ("m", (0.5, 0.5, 0.3), (-1, -1, 1.5), (0, 0, 1), 70.0), 1024, 768)
+    assert (img == o["rgba"][:, :, :3]).all()

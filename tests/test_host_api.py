@@ -160,3 +160,15 @@ def test_iso_volume_builder_small():
     cam = yvo.camera((0.5, 0.5, 0.6), (0.3, 0.4, -1), (0, 0, 1), 70, 64, 64)
     r = yvo.render(nodes, s.GetRoot(), cam)
     assert (r["node"] != yvo.MISS_NODE).mean() > 0.5
+
+
+def test_cpp_adapter_builds_and_refuses_without_gpu(tmp_path):
+    """include/yv_renderer.hpp (ISVORenderer-shaped adapter) + tools/render_main.cpp (cell/main.cpp:21-56)."""
+    import subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tools")])
+    exe = os.path.join(ROOT, "tools", "render_main")
+    assert os.path.exists(exe)
+    if conftest.has_gpu():
+        pytest.skip("GPU present: covered by the gpu test")
+    p = subprocess.run([exe, "--fractal", "8", str(tmp_path / "o.ppm"), "64", "48"], capture_output=True, text=True)
+    assert p.returncode == 2 and "no CPU fallback" in p.stderr       # RenderFrame() == NULL, like the reference
