@@ -36,7 +36,9 @@ def parse():
     ap.add_argument("--depth", type=int, default=12)
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--schedule", default="auto", choices=["auto", "tiles", "persistent"])
+    ap.add_argument("--scene", default="fractal", choices=["fractal", "iso"],
+                    help="fractal = gen_spheres.py scene (configs 1,2,4); iso = synthetic large volume (configs 3,5)")
+    ap.add_argument("--schedule", default="auto", choices=["auto", "tiles", "persistent", "queue"])
     ap.add_argument("--smem-nodes", type=int, default=-1)
     ap.add_argument("--stack", type=int, default=-1, choices=[-1, 0, 1, 2, 4])
     ap.add_argument("--secondary", action="store_true", help="BASELINE config 4: shadow + 4 AO rays")
@@ -56,8 +58,23 @@ UP = (0.0, 0.0, 1.0)
 FOV = 70.0
 
 
+ISO_POS = (0.2, 0.15, 0.45)       # above the terrain slab of the synthetic large volume, looking across it
+ISO_DIR = (0.6, 0.7, -0.45)
+SCENE = "fractal"
+
+
+def build_scene(yv, a, threads):
+    if a.scene == "iso":
+        return yv.SVOData.IsoVolume(a.depth, seed=219, iso_level=200, threads=threads)      # gen_largevol.py:8-30
+    return yv.SVOData.SphereFractal(a.depth, threads=threads)                               # gen_spheres.py:8-32
+
+
 def camera_for(frame):
     """Deterministic flythrough: frame 0 is the base camera; later frames orbit the eye a little."""
+    if SCENE == "iso":
+        a = 0.15 * frame
+        return ((ISO_POS[0] + 0.02 * frame, ISO_POS[1] + 0.015 * frame, ISO_POS[2]),
+                (ISO_DIR[0] + 0.1 * float(np.sin(a)), ISO_DIR[1], ISO_DIR[2]))
     if frame == 0:
         return BASE_POS, BASE_DIR
     a = 0.35 * frame
@@ -91,23 +108,28 @@ class ClockSampler:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.12)
-        self.proc.terminate()
+        deadline = time.time() + 1.0
+        while not self.rows and time.time() < deadline:      # nvidia-smi needs ~0.2 s to print its first row
+            time.sleep(0.05)
         rows = [r for (ts, r) in self.rows if t0 - 0.05 <= ts <= t1 + 0.1 and len(r) >= 8] or \
                [r for (_, r) in self.rows if len(r) >= 8]
         if not rows:
+            self.proc.terminate()
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm = sorted(float(r[1]) for r in rows)
         reasons = []
         for i, name in ((4, "hw_slowdown"), (5, "hw_thermal_slowdown"), (6, "sw_thermal_slowdown"), (7, "sw_power_cap")):
             if any(r[i].lower().startswith("active") for r in rows):
                 reasons.append(name)
+        self.proc.terminate()
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
                 "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
 
 
 def workload_name(a):
-    return ("gen_spheres sphere-fractal SVO depth %d, %dx%d primary rays + Lambert%s" %
-            (a.depth, a.width, a.height, " + shadow + 4 AO" if a.secondary else ""))
+    scene = "gen_spheres sphere-fractal SVO" if a.scene == "fractal" else "gen_largevol-style synthetic iso-volume SVO (seed 219, iso 200)"
+    return ("%s depth %d, %dx%d primary rays + Lambert%s" %
+            (scene, a.depth, a.width, a.height, " + shadow + 4 AO" if a.secondary else ""))
 
 
 def oracle_frame(svo_nodes, root, a, frame, threads, want_visits=False):
@@ -131,7 +153,7 @@ def run_reference(a, rank):
         return
     import yoxel_voxel_b200 as yv
     cores = os.cpu_count() or 1
-    svo = yv.SVOData.SphereFractal(a.depth, threads=cores)
+    svo = build_scene(yv, a, cores)
     nodes, root = svo.nodes(), svo.GetRoot()
     for _ in range(a.warmup):
         oracle_frame(nodes, root, a, 0, cores)
@@ -146,7 +168,7 @@ def run_reference(a, rank):
         "impl": "reference", "metric": "Mrays/s", "value": val, "unit": "Mrays/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "camera": {"pos": BASE_POS, "dir": BASE_DIR, "fov": FOV}},
+        "config": {"workload": workload_name(a), "camera": {"pos": camera_for(0)[0], "dir": camera_for(0)[1], "fov": FOV}},
         "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port",
                          "sample": "whole %dx%d frame per step, %d row strips (TreadedRenderer split)" % (a.width, a.height, cores)},
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -155,7 +177,9 @@ def run_reference(a, rank):
 
 
 def main():
+    global SCENE
     a = parse()
+    SCENE = a.scene
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -176,14 +200,14 @@ def main():
 
     # ---- scene: replicated on every GPU ----------------------------------------------------------
     t0 = time.time()
-    svo = yv.SVOData.SphereFractal(a.depth, threads=max(1, cores // world))
+    svo = build_scene(yv, a, max(1, cores // world))
     build_s = time.time() - t0
     dev_bytes = svo.Upload(local)
     n_rec, n_leaf = (x.shape[0] for x in svo.packed())
 
     r = yv.SVORenderer(local)
     schedule = a.schedule if a.schedule != "auto" else "tiles"
-    r.SetOption("persistent", 1 if schedule == "persistent" else 0)
+    r.SetOption("schedule", {"tiles": 0, "persistent": 1, "queue": 2}[schedule])
     if a.smem_nodes >= 0:
         r.SetOption("smem_nodes", a.smem_nodes)
     if a.stack >= 0:
@@ -266,6 +290,7 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None
     warm = max(a.warmup, 3)
     for _ in range(warm):
         if flush is not None:
@@ -274,7 +299,6 @@ def main():
     sync_all()
 
     # ---- timed region: K frames, CUDA events on the launching stream ------------------------------
-    sampler = ClockSampler(local) if rank == 0 else None
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     sync_all()
     wall0 = time.time()
@@ -322,8 +346,9 @@ def main():
         # the timed region already ends with every pixel resident on GPU 0; add rank 0's D2H of the batch
         d2h_s = 0.0
         if rank == 0 and gather == "p2p":
+            pinned = torch.empty(target_bytes, dtype=torch.uint8, pin_memory=True)
             t0 = time.perf_counter()
-            target_obj.to_host()
+            yv.lib().yv_copy_to_host(local, ctypes.c_void_p(pinned.data_ptr()), ctypes.c_void_p(target_ptr), target_bytes)
             d2h_s = time.perf_counter() - t0
         elif rank == 0:
             t0 = time.perf_counter()
@@ -336,6 +361,7 @@ def main():
     if rank != 0:
         if world > 1:
             dist.barrier()
+            dist.destroy_process_group()
         return
 
     # ---- CPU baseline + parity check (rank 0, N=1): the oracle on the host cores --------------------
@@ -378,7 +404,7 @@ def main():
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": a.steps, "warmup": warm,
         "ms_per_step": 1e3 * total_s / a.steps, "higher_is_better": True,
         "scaling": "strong" if tiles_mode else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "camera": {"pos": BASE_POS, "dir": BASE_DIR, "fov": FOV},
+        "config": {"workload": workload_name(a), "camera": {"pos": camera_for(0)[0], "dir": camera_for(0)[1], "fov": FOV},
                    "schedule": schedule, "smem_nodes": r.GetOption("smem_nodes"), "stack": r.GetOption("stack"),
                    "l2": "flushed between frames (256 MiB write, untimed)" if flush is not None
                          else "not flushed; node pool %d MB > L2" % (dev_bytes >> 20),
@@ -392,6 +418,7 @@ def main():
     print(json.dumps(line))
     if world > 1:
         dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

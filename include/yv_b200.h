@@ -127,8 +127,11 @@ int yv_set_stream(yv_renderer *r, void *cuda_stream);
 
 /* Kernel variant knobs (for ablation runs; defaults are the tuned ones):
  *   "smem_nodes"  number of top-of-tree records staged in shared memory per CTA
- *   "persistent"  1 = persistent CTAs pulling tiles from an atomic counter, 0 = one CTA per tile
+ *   "schedule"    0 = one CTA per 16x8 tile, one pixel per lane; 1 = persistent CTAs pulling tiles
+ *                 from an atomic counter; 2 = per-warp ray queue (a warp schedules the 128 rays of a
+ *                 16x8 tile over its lanes; primary rays). "persistent" is an alias.
  *                 (with warp-level lane refill: ballot + popc compaction of finished rays)
+ *   "refill"      persistent schedule: refill a warp once <= this many lanes are still traversing
  *   "stack"       where the traversal stack lives: 0 local memory, 4 = four-entry
  *                 shared-memory ring spilling to local memory */
 int yv_set_option(yv_renderer *r, const char *name, int value);

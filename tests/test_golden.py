@@ -41,7 +41,7 @@ def test_golden_has_content(golden):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("persistent", [0, 1])
+@pytest.mark.parametrize("persistent", [0, 1, 2])
 @pytest.mark.parametrize("scene", SCENES)
 def test_cuda_matches_golden(golden, scene, persistent):
     svo = yv.SVOData().Load(os.path.join(HERE, scene + ".vox"))

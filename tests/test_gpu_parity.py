@@ -53,7 +53,7 @@ def renderer():
     r.close()
 
 
-@pytest.mark.parametrize("persistent", [0, 1], ids=["tiles", "persistent"])
+@pytest.mark.parametrize("persistent", [0, 1, 2], ids=["tiles", "persistent", "queue"])
 @pytest.mark.parametrize("cam", scenes.CAMERAS, ids=[c[0] for c in scenes.CAMERAS])
 def test_fractal10_primary(renderer, cam, persistent):
     """BASELINE config 1: depth-10 sphere fractal, 512x512 primary rays (+ the other cameras)."""
@@ -96,7 +96,7 @@ def test_stack_variants(renderer, stack, persistent):
 
 
 @pytest.mark.parametrize("size", [(1, 1), (7, 5), (37, 23), (130, 67), (1024, 768)])
-@pytest.mark.parametrize("persistent", [0, 1], ids=["tiles", "persistent"])
+@pytest.mark.parametrize("persistent", [0, 1, 2], ids=["tiles", "persistent", "queue"])
 def test_ragged_resolutions(renderer, size, persistent):
     """Partial tiles at the right / bottom edges; cell/main.cpp's 1024x768."""
     svo = scenes.fractal(9)
@@ -127,7 +127,7 @@ def test_secondary_rays(renderer, sec, persistent):
     renderer.SetSecondary(0, 0)
 
 
-@pytest.mark.parametrize("persistent", [0, 1], ids=["tiles", "persistent"])
+@pytest.mark.parametrize("persistent", [0, 1, 2], ids=["tiles", "persistent", "queue"])
 def test_other_scenes(renderer, persistent):
     renderer.SetOption("persistent", persistent)
     for svo in (scenes.single_sphere(6), scenes.dense_random(5, 0.03)[0], scenes.dense_random(4, 0.08)[0],
@@ -160,7 +160,7 @@ def test_row_bands_compose_to_the_full_frame(renderer):
     full, *_ = _render_gpu(renderer, cam, 640, 363)
     out = np.zeros_like(full)
     for (y0, y1) in [(0, 91), (91, 182), (182, 300), (300, 363)]:
-        for persistent in (0, 1):
+        for persistent in (0, 1, 2):
             renderer.SetOption("persistent", persistent)
             renderer.SetRows(y0, y1)
             band = renderer.RenderFrame()
@@ -196,7 +196,7 @@ def test_counters_equal_oracle_visits(renderer):
     renderer.SetScene(svo)
     renderer.EnableCounters(True)
     cam = scenes.CAMERAS[1]
-    for persistent in (0, 1):
+    for persistent in (0, 1, 2):
         renderer.SetOption("persistent", persistent)
         _render_gpu(renderer, cam, 256, 256)
         visits, pops = renderer.GetCounters()
@@ -238,7 +238,7 @@ def test_full_size_config2_depth12_1080p():
     cam = scenes.CAMERAS[1]
     o = _render_cpu(svo, cam, 1920, 1080)
     assert (o["node"] != yvo.MISS_NODE).mean() > 0.3
-    for persistent in (0, 1):
+    for persistent in (0, 1, 2):
         r.SetOption("persistent", persistent)
         img, node, child, t = _render_gpu(r, cam, 1920, 1080)
         _check(o, img, node, child, t, "config2/%d" % persistent)

@@ -21,8 +21,9 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--frames", type=int, default=12)
     ap.add_argument("--persistent", default="0,1")
-    ap.add_argument("--stack", default="0,1,2,4")
-    ap.add_argument("--smem", default="0,73,585")
+    ap.add_argument("--stack", default="0")
+    ap.add_argument("--smem", default="0")
+    ap.add_argument("--refill", default="20")
     ap.add_argument("--secondary", action="store_true")
     ap.add_argument("--scene", default="fractal", choices=["fractal", "iso"])
     ap.add_argument("--pos", default="0.5,0.5,0.3")
@@ -44,11 +45,15 @@ def main():
     buf = torch.zeros(a.height, a.width, 4, dtype=torch.uint8, device="cuda:0")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
     ref, results = None, []
-    combos = itertools.product([int(v) for v in a.persistent.split(",")], [int(v) for v in a.stack.split(",")],
-                               [int(v) for v in a.smem.split(",")])
+    combos = []
+    for persistent, stack, smem in itertools.product([int(v) for v in a.persistent.split(",")], [int(v) for v in a.stack.split(",")],
+                                                     [int(v) for v in a.smem.split(",")]):
+        for refill in ([int(v) for v in a.refill.split(",")] if persistent else [20]):
+            combos.append((persistent, stack, smem, refill))
     with torch.cuda.stream(st):
-        for persistent, stack, smem in combos:
+        for persistent, stack, smem, refill in combos:
             r.SetOption("persistent", persistent); r.SetOption("stack", stack); r.SetOption("smem_nodes", smem)
+            r.SetOption("refill", refill)
             try:
                 times = []
                 for i in range(a.frames + 3):
@@ -70,10 +75,10 @@ def main():
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record(st); r.Render(buf.data_ptr(), sync=False); e1.record(st); st.synchronize()
                     warm.append(e0.elapsed_time(e1))
-                res = dict(persistent=persistent, stack=stack, smem=smem, ms_median=float(np.median(times)),
+                res = dict(lib=os.environ.get("YV_B200_LIB", "default"), persistent=persistent, stack=stack, smem=smem, refill=refill, ms_median=float(np.median(times)),
                            ms_min=float(min(times)), ms_warm_l2=float(np.median(warm[2:])), same_image=same)
             except yv.YVError as e:
-                res = dict(persistent=persistent, stack=stack, smem=smem, error=str(e))
+                res = dict(persistent=persistent, stack=stack, smem=smem, refill=refill, error=str(e))
             results.append(res)
             print(json.dumps(res), flush=True)
     os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)

@@ -32,6 +32,10 @@ class YVError(RuntimeError):
 
 
 def lib_path():
+    """In-tree library; YV_B200_LIB selects an ablation build (csrc/Makefile `variant`) for sweeps."""
+    override = os.environ.get("YV_B200_LIB")
+    if override:
+        return override if os.path.isabs(override) else os.path.join(os.path.dirname(os.path.abspath(__file__)), override)
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libyv_b200.so")
 
 

@@ -13,7 +13,7 @@
 //     (trace_core.cuh) — test the current child, then one sibling step or one (descend | pop);
 //   * PERSISTENT = false: one CTA per 16x8 pixel tile, one pixel per lane (8x4 pixels per warp);
 //     PERSISTENT = true : resident CTAs; each warp pulls 8x8-pixel tiles from an atomic counter and
-//     re-fills idle lanes (ballot + popc prefix) once <= kRefillThreshold lanes are still traversing;
+//     re-fills idle lanes (ballot + popc prefix) once <= refill_threshold lanes are still traversing;
 //   * STAGED: the top `smem_nodes` records of the breadth-first pool are read from shared memory
 //     (precedent: the SPU's software node cache, cell/spu/trace_spu.cpp:15-35). Measured on B200 the
 //     126 MB L2 + L1 already serve these records (L1 hit rate 94 % without staging) and the extra
@@ -45,15 +45,21 @@ struct RenderParams {
   uint32_t *counters;          // COUNT: low 16 bits node visits, high 16 bits pop re-fetches
   unsigned int *tile_counter;  // persistent schedule: next tile to hand out
   int tiles_x, num_tiles;      // 8x8 tiles covering [0,width) x [y0,y1)
+  int refill_threshold;        // persistent schedule: refill once <= this many lanes are still traversing
   int shadow, ao_samples;      // secondary rays
   uint32_t seed;
   float voxel_size, ao_max_t;
 };
 
 constexpr unsigned kFullMask = 0xffffffffu;
-constexpr int kRefillThreshold = 20;   // refill once <= this many lanes are still traversing
 constexpr int kCtaThreads = 128;
-constexpr int kStepsPerVote = 4;       // lean_steps between two warp votes on "anyone still traversing?"
+#ifndef YV_MINBLOCKS
+#define YV_MINBLOCKS 8                 // __launch_bounds__ residency target (register cap = 65536 / (128 * this))
+#endif
+#ifndef YV_STEPS_PER_VOTE
+#define YV_STEPS_PER_VOTE 4            // lean_steps between two warp votes on "anyone still traversing?"
+#endif
+constexpr int kStepsPerVote = YV_STEPS_PER_VOTE;
 
 enum : int { kStackLocal = 0, kStackRing4 = 4 };
 
@@ -144,7 +150,7 @@ __device__ __forceinline__ uint32_t leaf_data(const RenderParams &p, const Rec &
 enum : int { kLaneIdle = 0, kLaneActive = 1, kLaneHit = 2, kLaneMiss = 3, kLaneNew = 4 };
 
 template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED>
-__global__ void __launch_bounds__(kCtaThreads) render_frame(const __grid_constant__ RenderParams p) {
+__global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_frame(const __grid_constant__ RenderParams p) {
   extern __shared__ uint4 smem[];
   uint4 *staged = smem;
   uint4 *stack_area = smem + (STAGED ? p.smem_nodes : 0u);
@@ -224,7 +230,7 @@ __global__ void __launch_bounds__(kCtaThreads) render_frame(const __grid_constan
     for (;;) {
       const unsigned am = __ballot_sync(kFullMask, state == kLaneActive);
       if (am == 0u) break;
-      if (PERSISTENT && !pool_empty && __popc(am) <= kRefillThreshold) break;
+      if (PERSISTENT && !pool_empty && __popc(am) <= p.refill_threshold) break;
 #pragma unroll
       for (int u = 0; u < kStepsPerVote; ++u) {
         if (state == kLaneActive) {
@@ -315,6 +321,152 @@ __global__ void __launch_bounds__(kCtaThreads) render_frame(const __grid_constan
 
     // ---- 5. the warp retires when no pixel is pending and the queue is dry -----------------------
     if (pool_empty && __ballot_sync(kFullMask, state != kLaneIdle) == 0u) break;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// schedule 2 ("queue"): a warp owns a 16x8-pixel tile and schedules its 128 rays over its 32 lanes
+// ---------------------------------------------------------------------------------------------
+// Ray lengths inside one warp differ (mean/max ~ 0.77 on config 2), and an in-loop refill is only
+// worth it if handing a lane its next ray is cheap. So the warp does the expensive, perfectly
+// parallel parts up front and at the end, converged over all 32 lanes, and keeps only the descent in
+// the divergent middle:
+//   phase 0  every lane sets up 4 rays (ray generation, SetupTrace, root entry test, FindFirstChild in
+//            the root) and parks the 7-word states in shared memory; rays that miss the cube outright
+//            are resolved here; the others are appended to the warp's queue (ballot + popc prefix);
+//   phase 1  lanes pull queue entries (7 LDS + 6 FADD), run lean_steps, and park the 3-word hit record
+//            in the ray's slot when done; a warp vote every kStepsPerVote steps refills idle lanes;
+//   phase 2  every lane shades and stores its 4 pixels.
+// Slot order is the Morton order of the 16x8 tile, so the rays in flight stay spatially close.
+constexpr int kQueueRays = 128;                      // rays per warp
+constexpr int kQueueSlotWords = 8;                   // 7 state words + 1 (visit counters)
+constexpr size_t kQueueSmemPerWarp = kQueueRays * kQueueSlotWords * 4 + kQueueRays;   // slots + queue bytes
+
+__device__ __forceinline__ void queue_slot_xy(int slot, int &dx, int &dy) {
+  // 7-bit Morton index -> (x in 0..15, y in 0..7): bits x0 y0 x1 y1 x2 y2 x3
+  dx = (slot & 1) | ((slot >> 1) & 2) | ((slot >> 2) & 4) | ((slot >> 3) & 8);
+  dy = ((slot >> 1) & 1) | ((slot >> 2) & 2) | ((slot >> 3) & 4);
+}
+
+template <bool COUNT, int STACK>
+__global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_queue(const __grid_constant__ RenderParams p) {
+  extern __shared__ uint4 smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  uint4 *stack_area = smem;                                // ring stack first (16-byte aligned), then the slots
+  uint32_t *slots = reinterpret_cast<uint32_t *>(smem) + stack_smem_bytes(STACK) / 4 + warp * (kQueueSmemPerWarp / 4);   // [word][slot]
+  uint8_t *queue = reinterpret_cast<uint8_t *>(slots + kQueueRays * kQueueSlotWords);
+
+  // CTA tile: 32x16 pixels = 2x2 warp tiles of 16x8
+  const int tiles_x32 = (p.width + 31) >> 5;
+  const int tx = blockIdx.x % tiles_x32, ty = blockIdx.x / tiles_x32;
+  const int wx0 = tx * 32 + (warp & 1) * 16, wy0 = p.y0 + ty * 16 + (warp >> 1) * 8;
+
+  NodeFetch<COUNT, false> fetch = { p.recs, nullptr, 0u, 0u, 0u };
+  typename StackOf<STACK>::type stk(stack_area);
+  LeanState s;
+  const bool root_valid = p.root_valid != 0u;
+  uint32_t root_masks = 0u, root_child_base = 0u;
+  if (root_valid) { const Rec r = fetch.load(0u); root_masks = r.masks; root_child_base = r.child_base; }
+
+  // ---- phase 0: set up 4 rays per lane, build the queue --------------------------------------------
+  int qcount = 0;
+#pragma unroll 1
+  for (int k = 0; k < kQueueRays / 32; ++k) {
+    const int slot = k * 32 + lane;
+    int ox, oy; queue_slot_xy(slot, ox, oy);
+    const int x = wx0 + ox, y = wy0 + oy;
+    bool live = false;
+    if (x < p.width && y < p.y1) {
+      float dx, dy, dz;
+      primary_dir(p.dir0, p.du, p.dv, x, y, dx, dy, dz);
+      dx = adjust_dir1(dx); dy = adjust_dir1(dy); dz = adjust_dir1(dz);
+      live = lean_setup_root(s, root_valid, p.pos[0], p.pos[1], p.pos[2], dx, dy, dz);
+    }
+    if (live) {
+      slots[0 * kQueueRays + slot] = __float_as_uint(s.t1x); slots[1 * kQueueRays + slot] = __float_as_uint(s.t1y);
+      slots[2 * kQueueRays + slot] = __float_as_uint(s.t1z); slots[3 * kQueueRays + slot] = __float_as_uint(s.Tx);
+      slots[4 * kQueueRays + slot] = __float_as_uint(s.Ty);  slots[5 * kQueueRays + slot] = __float_as_uint(s.Tz);
+      slots[6 * kQueueRays + slot] = s.ch | (s.flags << 3);
+    } else {
+      slots[0 * kQueueRays + slot] = 0xffffffffu;          // resolved: miss (or outside the frame)
+    }
+    if (COUNT) slots[7 * kQueueRays + slot] = live ? 1u : 0u;   // the root visit
+    const unsigned lv = __ballot_sync(kFullMask, live);
+    if (live) queue[qcount + __popc(lv & lt_mask)] = (uint8_t)slot;
+    qcount += __popc(lv);
+  }
+  __syncwarp();
+
+  // ---- phase 1: lanes pull rays from the queue -------------------------------------------------------
+  int qnext = 0;
+  int cur = -1;                                            // slot of the ray this lane is tracing
+  for (;;) {
+    const unsigned idle = __ballot_sync(kFullMask, cur < 0);
+    if (idle != 0u && qnext < qcount) {
+      const int take = min(__popc(idle), qcount - qnext);
+      const int rank = __popc(idle & lt_mask);
+      if (cur < 0 && rank < take) {
+        cur = queue[qnext + rank];
+        s.t1x = __uint_as_float(slots[0 * kQueueRays + cur]); s.t1y = __uint_as_float(slots[1 * kQueueRays + cur]);
+        s.t1z = __uint_as_float(slots[2 * kQueueRays + cur]); s.Tx = __uint_as_float(slots[3 * kQueueRays + cur]);
+        s.Ty = __uint_as_float(slots[4 * kQueueRays + cur]);  s.Tz = __uint_as_float(slots[5 * kQueueRays + cur]);
+        const uint32_t w = slots[6 * kQueueRays + cur];
+        s.ch = w & 7u; s.flags = w >> 3; s.idx = 0u; s.sp = 0;
+        s.masks = root_masks; s.child_base = root_child_base;
+        stk.reset();
+        lean_eval_next(s);
+        if (COUNT) { fetch.visits = 1u; fetch.revisits = 0u; }
+      }
+      qnext += take;
+    }
+    if (__ballot_sync(kFullMask, cur >= 0) == 0u) break;
+#pragma unroll
+    for (int u = 0; u < kStepsPerVote; ++u) {
+      if (cur >= 0) {
+        const int r = lean_step(s, fetch, stk, false);
+        if (r != kStepContinue) {
+          const bool hit = r == kStepHit;
+          slots[0 * kQueueRays + cur] = hit ? s.idx : 0xffffffffu;
+          slots[1 * kQueueRays + cur] = s.ch ^ s.flags;
+          slots[2 * kQueueRays + cur] = __float_as_uint(max3f(s.t1x, s.t1y, s.t1z));
+          if (COUNT) slots[7 * kQueueRays + cur] = (fetch.visits & 0xffffu) | (fetch.revisits << 16);
+          cur = -1;
+        }
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- phase 2: shade and store 4 pixels per lane ------------------------------------------------------
+#pragma unroll 1
+  for (int k = 0; k < kQueueRays / 32; ++k) {
+    const int slot = k * 32 + lane;
+    int ox, oy; queue_slot_xy(slot, ox, oy);
+    const int x = wx0 + ox, y = wy0 + oy;
+    if (x >= p.width || y >= p.y1) continue;
+    const uint32_t pixel = (uint32_t)y * (uint32_t)p.width + (uint32_t)x;
+    const uint32_t idx = slots[0 * kQueueRays + slot];
+    uint32_t rgba = 0u, hn = YV_MISS_NODE; int32_t hc = YV_MISS_CHILD; float ht = 0.0f;
+    if (idx != 0xffffffffu) {
+      const Rec rec = fetch.load(idx);
+      const uint32_t c = slots[1 * kQueueRays + slot];
+      ht = __uint_as_float(slots[2 * kQueueRays + slot]);
+      hn = rec.orig_id; hc = (int32_t)c;
+      const uint32_t data = leaf_data(p, rec, c);
+      float nx, ny, nz, dx, dy, dz;
+      unpack_normal(data, nx, ny, nz);
+      primary_dir(p.dir0, p.du, p.dv, x, y, dx, dy, dz);
+      dx = adjust_dir1(dx); dy = adjust_dir1(dy); dz = adjust_dir1(dz);
+      const float Px = YV_FADD(p.pos[0], YV_FMUL(dx, ht));
+      const float Py = YV_FADD(p.pos[1], YV_FMUL(dy, ht));
+      const float Pz = YV_FADD(p.pos[2], YV_FMUL(dz, ht));
+      const float dl = lambert(nx, ny, nz, Px, Py, Pz, p.light[0], p.light[1], p.light[2]);
+      rgba = shade_rgba(data, YV_FADD(YV_SHADE_AMBIENT, YV_FMUL(YV_SHADE_DIFFUSE, YV_FMUL(dl, 1.0f))));
+    }
+    p.out_rgba[pixel] = rgba;
+    if (p.hit_node) { p.hit_node[pixel] = hn; p.hit_child[pixel] = hc; p.hit_t[pixel] = ht; }
+    if (COUNT) p.counters[pixel] = slots[7 * kQueueRays + slot];
   }
 }
 

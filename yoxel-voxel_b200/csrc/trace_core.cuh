@@ -289,34 +289,54 @@ YV_HD void lean_load_node(LeanState &s, const Fetch &fetch, const bool visit) {
   s.masks = r.masks; s.child_base = r.child_base;
 }
 
-// SetupTrace + RecTrace's entry test on the root. Returns false on an immediate miss.
-template <class Fetch>
-YV_HD bool lean_begin(LeanState &s, const Fetch &fetch, const bool root_valid,
-                      float px, float py, float pz, float dx, float dy, float dz) {
+// SetupTrace + RecTrace's entry test on the root + FindFirstChild in the root (needs no node data).
+// Returns false on an immediate miss. The caller loads the root record and evaluates N.
+YV_HD bool lean_setup_root(LeanState &s, const bool root_valid,
+                           float px, float py, float pz, float dx, float dy, float dz) {
   RayState r;
   if (!setup_trace(px, py, pz, dx, dy, dz, r)) return false;
   if (!root_valid || fminf(fminf(r.t2x, r.t2y), r.t2z) <= 0.0f) return false;
   s.t1x = r.t1x; s.t1y = r.t1y; s.t1z = r.t1z; s.Tx = r.t2x; s.Ty = r.t2y; s.Tz = r.t2z;
   s.flags = r.flags; s.sp = 0; s.idx = 0u;
-  lean_load_node(s, fetch, true);
   lean_first_child(s);
+  return true;
+}
+
+template <class Fetch>
+YV_HD bool lean_begin(LeanState &s, const Fetch &fetch, const bool root_valid,
+                      float px, float py, float pz, float dx, float dy, float dz) {
+  if (!lean_setup_root(s, root_valid, px, py, pz, dx, dy, dz)) return false;
+  lean_load_node(s, fetch, true);
   lean_eval_next(s);
   return true;
 }
 
-// One micro-step: test the current child; then either take one sibling step, or (descend | pop).
+// One call = up to YV_STEPS_PER_CALL sibling steps followed by at most one (descend | pop): test the
+// current child; while it is empty and a sibling follows, step (register-only); then descend or pop.
+// Folding the cheap steps into the call that performs the expensive node entry means a warp issues the
+// (descend | pop) block once per node visit instead of once per loop trip.
 // Stack: push(sp, U4, U4) / pop(sp, U4&, U4&).
+#ifndef YV_STEPS_PER_CALL
+#define YV_STEPS_PER_CALL 2
+#endif
 template <class Fetch, class Stack>
 YV_HD int lean_step(LeanState &s, const Fetch &fetch, Stack &stk, const bool front_only) {
-  const uint32_t bit = 1u << (s.ch ^ s.flags);
-  const bool xy = s.Tx > s.Ty;
-  const bool nz = xy ? (s.Ty < s.Tz) : (s.Tx < s.Tz);
-  const uint32_t e = nz ? (xy ? 2u : 1u) : 4u;                     // argmin(t2), one-hot, the reference's tie order
-  const float tmin = fminf(fminf(s.Tx, s.Ty), s.Tz);               // compared only
-  if (((s.masks & bit) != 0u) && (!front_only || tmin > 0.0f)) return kStepHit;             // :27
-  const bool descend = (((s.masks >> 8) & bit) != 0u) && (tmin > 0.0f);                      // :20,:35
-  const bool can_adv = (s.ch & e) == 0u;                                                     // :38
-  if (!descend && can_adv) { lean_apply_step(s, e); return kStepContinue; }
+  uint32_t bit, e;
+  bool descend, can_adv;
+#pragma unroll
+  for (int k = 0;; ++k) {
+    bit = 1u << (s.ch ^ s.flags);
+    const bool xy = s.Tx > s.Ty;
+    const bool nz = xy ? (s.Ty < s.Tz) : (s.Tx < s.Tz);
+    e = nz ? (xy ? 2u : 1u) : 4u;                                  // argmin(t2), one-hot, the reference's tie order
+    const float tmin = fminf(fminf(s.Tx, s.Ty), s.Tz);             // compared only
+    if (((s.masks & bit) != 0u) && (!front_only || tmin > 0.0f)) return kStepHit;           // :27
+    descend = (((s.masks >> 8) & bit) != 0u) && (tmin > 0.0f);                               // :20,:35
+    can_adv = (s.ch & e) == 0u;                                                              // :38
+    if (descend || !can_adv) break;
+    lean_apply_step(s, e);
+    if (k + 1 == YV_STEPS_PER_CALL) return kStepContinue;
+  }
 
   uint32_t pending = 0u;                                           // exit axis (one-hot) to apply after a pop
   if (descend) {

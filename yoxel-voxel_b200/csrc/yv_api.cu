@@ -77,6 +77,7 @@ struct yv_renderer {
   // options
   int opt_smem_nodes = 0;             // records staged in shared memory (585 = four levels)
   int opt_persistent = 0;
+  int opt_refill = 20;                // persistent schedule: refill when <= this many lanes are live
   int opt_stack = 0;                  // yv::kStackLocal / kStackRing4
 };
 
@@ -198,6 +199,17 @@ int launch_kernel(yv_renderer *r, const yv::RenderParams &p, size_t smem) {
   return YV_OK;
 }
 
+template <bool COUNT, int STACK>
+int launch_queue(yv_renderer *r, const yv::RenderParams &p) {
+  auto kern = yv::render_queue<COUNT, STACK>;
+  const size_t smem = yv::stack_smem_bytes(STACK) + yv::kQueueSmemPerWarp * (yv::kCtaThreads / 32);
+  YV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long grid = (long)((p.width + 31) / 32) * ((p.y1 - p.y0 + 15) / 16);
+  if (grid > 0) kern<<<(unsigned)grid, yv::kCtaThreads, smem, r->stream>>>(p);
+  YV_CUDA(cudaGetLastError());
+  return YV_OK;
+}
+
 template <bool SEC, bool COUNT, int STACK, bool PERSISTENT>
 int launch_staged(yv_renderer *r, const yv::RenderParams &p, size_t smem) {
   return p.smem_nodes > 0 ? launch_kernel<SEC, COUNT, STACK, PERSISTENT, true>(r, p, smem)
@@ -206,7 +218,7 @@ int launch_staged(yv_renderer *r, const yv::RenderParams &p, size_t smem) {
 
 template <bool SEC, bool COUNT, int STACK>
 int launch_schedule(yv_renderer *r, const yv::RenderParams &p, size_t smem) {
-  return r->opt_persistent ? launch_staged<SEC, COUNT, STACK, true>(r, p, smem)
+  return r->opt_persistent == 1 ? launch_staged<SEC, COUNT, STACK, true>(r, p, smem)
                            : launch_staged<SEC, COUNT, STACK, false>(r, p, smem);
 }
 
@@ -245,6 +257,7 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
   p.tile_counter = r->d_tile_counter;
   p.tiles_x = (p.width + 7) / 8;
   p.num_tiles = p.tiles_x * ((p.y1 - p.y0 + 7) / 8);
+  p.refill_threshold = r->opt_refill;
   p.shadow = r->shadow; p.ao_samples = r->ao_samples; p.seed = r->seed;
   p.voxel_size = r->voxel_size; p.ao_max_t = r->ao_max_t;
   const size_t smem = (size_t)p.smem_nodes * sizeof(uint4) + yv::stack_smem_bytes(r->opt_stack);
@@ -252,6 +265,10 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
 
   YV_CUDA(cudaEventRecord(r->ev0, r->stream));
   const int key = (sec ? 2 : 0) | (r->counters ? 1 : 0);
+  if (r->opt_persistent == 2 && !sec) {        // per-warp ray queue (primary rays)
+    if (r->opt_stack == yv::kStackRing4) rc = r->counters ? launch_queue<true, yv::kStackRing4>(r, p) : launch_queue<false, yv::kStackRing4>(r, p);
+    else rc = r->counters ? launch_queue<true, yv::kStackLocal>(r, p) : launch_queue<false, yv::kStackLocal>(r, p);
+  } else
   switch (key) {
     case 0: rc = launch_stack<false, false>(r, p, smem); break;
     case 1: rc = launch_stack<false, true>(r, p, smem); break;
@@ -602,7 +619,11 @@ int yv_set_option(yv_renderer *r, const char *name, int value) {
   if (!r || !name) return fail(YV_ERR_ARG, "null argument");
   std::string n(name);
   if (n == "smem_nodes") { if (value < 0 || value > 12288) return fail(YV_ERR_ARG, "smem_nodes must be 0..12288"); r->opt_smem_nodes = value; }
-  else if (n == "persistent") r->opt_persistent = value ? 1 : 0;
+  else if (n == "persistent" || n == "schedule") {
+    if (value < 0 || value > 2) return fail(YV_ERR_ARG, "schedule must be 0 (tiles), 1 (persistent) or 2 (queue)");
+    r->opt_persistent = value;
+  }
+  else if (n == "refill") { if (value < 0 || value > 31) return fail(YV_ERR_ARG, "refill must be 0..31"); r->opt_refill = value; }
   else if (n == "stack") {
     if (value != yv::kStackLocal && value != yv::kStackRing4)
       return fail(YV_ERR_ARG, "stack must be 0 (local memory) or 4 (4-entry shared ring + local spill)");
@@ -616,7 +637,8 @@ int yv_get_option(const yv_renderer *r, const char *name, int *value) {
   if (!r || !name || !value) return fail(YV_ERR_ARG, "null argument");
   std::string n(name);
   if (n == "smem_nodes") *value = r->opt_smem_nodes;
-  else if (n == "persistent") *value = r->opt_persistent;
+  else if (n == "persistent" || n == "schedule") *value = r->opt_persistent;
+  else if (n == "refill") *value = r->opt_refill;
   else if (n == "stack") *value = r->opt_stack;
   else return fail(YV_ERR_ARG, "unknown option " + n);
   return YV_OK;
