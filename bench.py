@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--partition", default="frames", choices=["frames", "tiles"],
                     help="N>1: one frame per rank (weak) or one frame split into row bands (strong)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--flythrough", action="store_true",
+                    help="tiles partition: move the camera every step (BASELINE config 5: 64-frame flythrough)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-l2-flush", action="store_true")
     return ap.parse_args()
@@ -69,12 +71,37 @@ def build_scene(yv, a, threads):
     return yv.SVOData.SphereFractal(a.depth, threads=threads)                               # gen_spheres.py:8-32
 
 
-def camera_for(frame):
-    """Deterministic flythrough: frame 0 is the base camera; later frames orbit the eye a little."""
+def _catmull_rom(pts, u):
+    """Closed uniform Catmull-Rom spline through pts (n,3) at parameter u in [0, n)."""
+    n = len(pts)
+    i = int(np.floor(u)) % n
+    t = u - np.floor(u)
+    p0, p1, p2, p3 = pts[(i - 1) % n], pts[i], pts[(i + 1) % n], pts[(i + 2) % n]
+    return 0.5 * ((2 * p1) + (-p0 + p2) * t + (2 * p0 - 5 * p1 + 4 * p2 - p3) * t * t + (-p0 + 3 * p1 - 3 * p2 + p3) * t ** 3)
+
+
+_ISO_PATH = None
+
+
+def camera_for(frame, n_frames=64):
+    """Deterministic flythrough. Sphere fractal: frame 0 is the base camera, later frames orbit the eye a
+    little. Iso volume (config 5): a seeded closed Catmull-Rom path inside the cube, above the terrain slab,
+    looking along the tangent with a downward pitch; frame 0 is the fixed config-3 camera."""
+    global _ISO_PATH
     if SCENE == "iso":
-        a = 0.15 * frame
-        return ((ISO_POS[0] + 0.02 * frame, ISO_POS[1] + 0.015 * frame, ISO_POS[2]),
-                (ISO_DIR[0] + 0.1 * float(np.sin(a)), ISO_DIR[1], ISO_DIR[2]))
+        if frame == 0:
+            return ISO_POS, ISO_DIR
+        if _ISO_PATH is None:
+            rng = np.random.RandomState(219)
+            ang = np.sort(rng.rand(8)) * 2 * np.pi
+            rad = 0.22 + 0.12 * rng.rand(8)
+            _ISO_PATH = np.stack([0.5 + rad * np.cos(ang), 0.5 + rad * np.sin(ang), 0.40 + 0.08 * rng.rand(8)], axis=1)
+        u = 8.0 * (frame % n_frames) / n_frames
+        pos = _catmull_rom(_ISO_PATH, u)
+        tan = _catmull_rom(_ISO_PATH, u + 0.05) - pos
+        tan /= max(1e-9, np.linalg.norm(tan))
+        d = (tan[0], tan[1], -0.55)
+        return tuple(float(np.float32(v)) for v in pos), tuple(float(np.float32(v)) for v in d)
     if frame == 0:
         return BASE_POS, BASE_DIR
     a = 0.35 * frame
@@ -199,8 +226,22 @@ def main():
     cores = os.cpu_count() or 1
 
     # ---- scene: replicated on every GPU ----------------------------------------------------------
+    # N>1: rank 0 builds with all host cores and parks the .vox in /dev/shm, the other ranks load it
+    # (SVOData::Load) — the build is host work shared by the box, the replica per GPU is not.
     t0 = time.time()
-    svo = build_scene(yv, a, max(1, cores // world))
+    if world > 1:
+        shm = "/dev/shm/yv_%s_d%d_%d.vox" % (a.scene, a.depth, os.getuid())
+        if rank == 0:
+            svo = build_scene(yv, a, cores)
+            svo.Save(shm)
+        dist.barrier()
+        if rank != 0:
+            svo = yv.SVOData().Load(shm)
+        dist.barrier()
+        if rank == 0:
+            os.unlink(shm)
+    else:
+        svo = build_scene(yv, a, cores)
     build_s = time.time() - t0
     dev_bytes = svo.Upload(local)
     n_rec, n_leaf = (x.shape[0] for x in svo.packed())
@@ -262,7 +303,10 @@ def main():
             return target_ptr + (0 if tiles_mode else rank * frame_bytes)
         return local_fb.data_ptr()
 
-    def render_step():
+    def render_step(step=None):
+        if a.flythrough and step is not None:
+            fpos, fdir = camera_for(frame_of(step))
+            r.SetViewPos(fpos); r.SetViewDir(fdir)
         r.Render(dst_ptr(), sync=False)
         if gather == "nccl":
             dist.gather(local_fb, gather_list, dst=0)
@@ -270,16 +314,28 @@ def main():
     # ---- V-bar for the roofline: the kernel's own node-visit counters on this workload -----------
     # (tests/test_gpu_parity.py::test_counters_equal_oracle_visits pins them to the oracle's count of
     # the node fetch at cell/ppu_renderer.cpp:23)
+    def frame_of(step):
+        return step if (tiles_mode or world == 1) else step * world + rank
+
     r.EnableCounters(True)
     probe = torch.zeros(a.height, a.width, 4, dtype=torch.uint8, device=dev)
-    r.Render(probe.data_ptr(), sync=True)
-    visits, pops = r.GetCounters()
+    vis_sum = pop_sum = hit_px = 0
+    probe_frames = range(a.steps) if a.flythrough else [None]
+    for st in probe_frames:                                   # untimed pass: per-frame node-visit counters
+        if st is not None:
+            fpos, fdir = camera_for(frame_of(st))
+            r.SetViewPos(fpos); r.SetViewDir(fdir)
+        r.Render(probe.data_ptr(), sync=True)
+        visits, pops = r.GetCounters()
+        vis_sum += int(visits[y0:y1].sum())
+        pop_sum += int(pops[y0:y1].sum())
+        hit_px += int((probe[y0:y1, :, 3] == 255).sum().item())
     r.EnableCounters(False)
-    vis_sum = int(visits[y0:y1].sum())
-    pop_sum = int(pops[y0:y1].sum())
-    hit_px = int((probe[y0:y1, :, 3] == 255).sum().item())
+    n_probe = len(probe_frames)
     my_px = (y1 - y0) * a.width
-    my_rays = my_px + (5 * hit_px if a.secondary else 0)      # shadow + 4 AO per hit pixel
+    my_rays = my_px + (5 * hit_px // n_probe if a.secondary else 0)      # shadow + 4 AO per hit pixel
+    vis_sum //= n_probe; pop_sum //= n_probe                  # per-step averages
+    hit_frac = hit_px / float(n_probe * max(1, my_px))
     del probe
 
     flush = None if a.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -306,7 +362,7 @@ def main():
         if flush is not None:
             flush.zero_()                           # evict the node pool from L2 between frames (not timed)
         evs[i][0].record(stream)
-        render_step()
+        render_step(i)
         evs[i][1].record(stream)
         if world > 1:
             torch.cuda.synchronize()
@@ -410,7 +466,7 @@ def main():
                          else "not flushed; node pool %d MB > L2" % (dev_bytes >> 20),
                    "nodes": svo.nodecount, "packed_bytes": dev_bytes, "scene_build_s": round(build_s, 2),
                    "partition": ("row bands of one frame" if tiles_mode else "one frame per GPU") if world > 1 else "single GPU",
-                   "gather": gather},
+                   "gather": gather, "flythrough": bool(a.flythrough), "hit_fraction": round(hit_frac, 4)},
         "frame_ms": 1e3 * total_s / a.steps, "rays_per_step": rays_step,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
         "gpu_launches": a.steps * world, "parity": parity,
