@@ -42,8 +42,10 @@ def parse():
     ap.add_argument("--smem-nodes", type=int, default=-1)
     ap.add_argument("--stack", type=int, default=-1, choices=[-1, 0, 1, 2, 4])
     ap.add_argument("--secondary", action="store_true", help="BASELINE config 4: shadow + 4 AO rays")
-    ap.add_argument("--partition", default="frames", choices=["frames", "tiles"],
-                    help="N>1: one frame per rank (weak) or one frame split into row bands (strong)")
+    ap.add_argument("--partition", default="frames", choices=["frames", "tiles", "bands"],
+                    help="N>1: one frame per rank (weak), or one frame split (strong) into interleaved "
+                         "blocks of --band-rows rows (tiles) or contiguous row bands (bands)")
+    ap.add_argument("--band-rows", type=int, default=32)
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--flythrough", action="store_true",
                     help="tiles partition: move the camera every step (BASELINE config 5: 64-frame flythrough)")
@@ -265,11 +267,18 @@ def main():
 
     # ---- partition ----------------------------------------------------------------------------
     frame_bytes = a.width * a.height * 4
-    tiles_mode = world > 1 and a.partition == "tiles"
+    tiles_mode = world > 1 and a.partition in ("tiles", "bands")
+    my_rows = np.arange(a.height)
     if tiles_mode:
-        y0, y1 = multigpu.row_band(rank, world, a.height)
-        r.SetRows(y0, y1)
-        my_frame, my_rays_px = 0, (y1 - y0) * a.width
+        if a.partition == "bands":
+            y0, y1 = multigpu.row_band(rank, world, a.height)
+            r.SetRows(y0, y1)
+            my_rows = np.arange(y0, y1)
+        else:
+            r.SetInterleave(a.band_rows, world, rank)
+            my_rows = multigpu.interleaved_rows(rank, world, a.height, a.band_rows)
+        y0, y1 = 0, a.height
+        my_frame = 0
         target_bytes = frame_bytes
     else:
         y0, y1 = 0, a.height
@@ -327,12 +336,12 @@ def main():
             r.SetViewPos(fpos); r.SetViewDir(fdir)
         r.Render(probe.data_ptr(), sync=True)
         visits, pops = r.GetCounters()
-        vis_sum += int(visits[y0:y1].sum())
-        pop_sum += int(pops[y0:y1].sum())
-        hit_px += int((probe[y0:y1, :, 3] == 255).sum().item())
+        vis_sum += int(visits[my_rows].sum())
+        pop_sum += int(pops[my_rows].sum())
+        hit_px += int((probe[torch.as_tensor(my_rows, device=dev), :, 3] == 255).sum().item())
     r.EnableCounters(False)
     n_probe = len(probe_frames)
-    my_px = (y1 - y0) * a.width
+    my_px = len(my_rows) * a.width
     my_rays = my_px + (5 * hit_px // n_probe if a.secondary else 0)      # shadow + 4 AO per hit pixel
     vis_sum //= n_probe; pop_sum //= n_probe                  # per-step averages
     hit_frac = hit_px / float(n_probe * max(1, my_px))
@@ -465,7 +474,8 @@ def main():
                    "l2": "flushed between frames (256 MiB write, untimed)" if flush is not None
                          else "not flushed; node pool %d MB > L2" % (dev_bytes >> 20),
                    "nodes": svo.nodecount, "packed_bytes": dev_bytes, "scene_build_s": round(build_s, 2),
-                   "partition": ("row bands of one frame" if tiles_mode else "one frame per GPU") if world > 1 else "single GPU",
+                   "partition": (("interleaved %d-row blocks of one frame" % a.band_rows if a.partition == "tiles" else "contiguous row bands of one frame")
+                                 if tiles_mode else "one frame per GPU") if world > 1 else "single GPU",
                    "gather": gather, "flythrough": bool(a.flythrough), "hit_fraction": round(hit_frac, 4)},
         "frame_ms": 1e3 * total_s / a.steps, "rays_per_step": rays_step,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,

@@ -102,6 +102,10 @@ int yv_device_framebuffer(yv_renderer *r, void **d_rgba);
 /* Screen-space partition for multi-GPU rendering (SPURenderer splits blocks across SPEs,
  * cell/spu_renderer.cpp:73-87): render only rows [y0,y1). Default: the whole frame. */
 int yv_set_rows(yv_renderer *r, int y0, int y1);
+/* Interleaved partition for load balance (the SPU program's block stride, cell/spu/trace_spu.cpp:164):
+ * the frame is cut into blocks of band_rows rows (multiple of 16); this renderer draws the blocks b with
+ * b % stride == phase. stride 1 restores the contiguous mode. Cancels yv_set_rows and vice versa. */
+int yv_set_interleave(yv_renderer *r, int band_rows, int stride, int phase);
 
 /* Secondary rays (BASELINE config 4). shadow: 0/1; ao_samples: 0..16. light_pos is used for
  * the Lambert term and the shadow ray when shadow != 0 (otherwise the light rides on the eye). */

@@ -170,6 +170,29 @@ def test_row_bands_compose_to_the_full_frame(renderer):
     renderer.SetResolution(640, 363)      # resets the band
 
 
+@pytest.mark.parametrize("schedule", [0, 1, 2], ids=["tiles", "persistent", "queue"])
+@pytest.mark.parametrize("world,band", [(2, 16), (3, 32), (8, 32)])
+def test_interleaved_blocks_compose_to_the_full_frame(renderer, schedule, world, band):
+    """Round-robin row blocks (yv_set_interleave) over `world` ranks reproduce the 1-GPU frame byte for byte."""
+    from yoxel_voxel_b200 import multigpu
+    svo = scenes.fractal(10)
+    renderer.SetOption("schedule", 0)
+    renderer.SetScene(svo)
+    cam = scenes.CAMERAS[1]
+    W, H = 640, 363
+    full, *_ = _render_gpu(renderer, cam, W, H)
+    renderer.SetOption("schedule", schedule)
+    out = np.zeros_like(full)
+    for rank in range(world):
+        renderer.SetInterleave(band, world, rank)
+        part = renderer.RenderFrame()
+        rows = multigpu.interleaved_rows(rank, world, H, band)
+        out[rows] = part[rows]
+    renderer.SetInterleave(16, 1, 0)
+    renderer.SetOption("schedule", 0)
+    assert (out == full).all()
+
+
 def test_trace_rays_matches_oracle(renderer):
     """DynamicSVO::TraceRay (ore/src/main.cpp:125) batched on the device."""
     svo = scenes.fractal(9)

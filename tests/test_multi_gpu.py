@@ -29,6 +29,16 @@ def test_row_bands_are_a_partition(world, height):
     assert (covered == 1).all()
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("height,band", [(1080, 32), (4320, 64), (67, 16), (16, 16)])
+def test_interleaved_blocks_are_a_partition(world, height, band):
+    covered = np.zeros(height, int)
+    for r in range(world):
+        rows = multigpu.interleaved_rows(r, world, height, band)
+        covered[rows] += 1
+    assert (covered == 1).all()
+
+
 def _worker(rank, world, port, tmpdir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)

@@ -90,6 +90,7 @@ def lib():
         "yv_sync": (i32, [vp]),
         "yv_device_framebuffer": (i32, [vp, P(vp)]),
         "yv_set_rows": (i32, [vp, i32, i32]),
+        "yv_set_interleave": (i32, [vp, i32, i32, i32]),
         "yv_set_secondary": (i32, [vp, i32, i32, u32, P(f32), f32, f32]),
         "yv_enable_hits": (i32, [vp, i32]),
         "yv_get_hits": (i32, [vp, vp, vp, vp]),
@@ -307,6 +308,9 @@ class SVORenderer:
 
     def SetRows(self, y0, y1):
         _check(lib().yv_set_rows(self._h, int(y0), int(y1)))
+
+    def SetInterleave(self, band_rows, stride, phase):
+        _check(lib().yv_set_interleave(self._h, int(band_rows), int(stride), int(phase)))
 
     def SetSecondary(self, shadow=0, ao_samples=0, seed=1, light_pos=(0.5, 0.5, 1.0), voxel_size=0.0, ao_max_t=0.05):
         _check(lib().yv_set_secondary(self._h, int(shadow), int(ao_samples), int(seed), _vec3(light_pos),

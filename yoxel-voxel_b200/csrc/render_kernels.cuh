@@ -38,6 +38,8 @@ struct RenderParams {
   float light[3];              // shader lightPos
   int width, height;           // m_viewSize
   int y0, y1;                  // row band rendered by this launch
+  int band_rows8, band_stride, band_phase;   // interleaved partition: blocks of band_rows8*8 rows, this launch
+                                             // renders blocks b with b % band_stride == band_phase (stride 1 = all)
   uint32_t *out_rgba;          // full-frame addressed: out_rgba[y*width + x]
   uint32_t *hit_node;          // optional TraceResult planes (ppu_renderer.cpp:7-12); NULL = off
   int32_t *hit_child;
@@ -147,6 +149,12 @@ __device__ __forceinline__ uint32_t leaf_data(const RenderParams &p, const Rec &
   return __ldg(p.leaves + rec.leaf_base + (uint32_t)__popc(rec.masks & 0xffu & ((1u << c) - 1u)));
 }
 
+// tile row (8 pixel rows) of this launch -> first pixel row, for contiguous and interleaved partitions
+__device__ __forceinline__ int tile_row_y(const RenderParams &p, int ty) {
+  const int blk = ty / p.band_rows8, within = ty - blk * p.band_rows8;
+  return p.y0 + ((blk * p.band_stride + p.band_phase) * p.band_rows8 + within) * 8;
+}
+
 enum : int { kLaneIdle = 0, kLaneActive = 1, kLaneHit = 2, kLaneMiss = 3, kLaneNew = 4 };
 
 template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED>
@@ -184,7 +192,7 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_frame(const 
     const int tiles_x16 = (p.width + 15) >> 4;
     const int tx = blockIdx.x % tiles_x16, ty = blockIdx.x / tiles_x16;
     x = tx * 16 + (warp & 1) * 8 + (lane & 7);
-    y = p.y0 + ty * 8 + (warp >> 1) * 4 + (lane >> 3);
+    y = tile_row_y(p, ty) + (warp >> 1) * 4 + (lane >> 3);
     if (x < p.width && y < p.y1) state = kLaneNew;
   }
 
@@ -199,7 +207,7 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_frame(const 
           t = __shfl_sync(kFullMask, t, 0);
           if (t >= (unsigned)p.num_tiles) { pool_empty = true; break; }
           tile_x0 = (int)(t % (unsigned)p.tiles_x) * 8;
-          tile_y0 = p.y0 + (int)(t / (unsigned)p.tiles_x) * 8;
+          tile_y0 = tile_row_y(p, (int)(t / (unsigned)p.tiles_x));
           pool_next = 0;
         }
         const int take = min(__popc(idle), kTilePix - pool_next);
@@ -360,7 +368,7 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_queue(const 
   // CTA tile: 32x16 pixels = 2x2 warp tiles of 16x8
   const int tiles_x32 = (p.width + 31) >> 5;
   const int tx = blockIdx.x % tiles_x32, ty = blockIdx.x / tiles_x32;
-  const int wx0 = tx * 32 + (warp & 1) * 16, wy0 = p.y0 + ty * 16 + (warp >> 1) * 8;
+  const int wx0 = tx * 32 + (warp & 1) * 16, wy0 = tile_row_y(p, ty * 2 + (warp >> 1));
 
   NodeFetch<COUNT, false> fetch = { p.recs, nullptr, 0u, 0u, 0u };
   typename StackOf<STACK>::type stk(stack_area);

@@ -57,6 +57,7 @@ struct yv_renderer {
   int width = 0, height = 0;
   int y0 = 0, y1 = 0;
   bool rows_set = false;
+  int il_rows = 0, il_stride = 1, il_phase = 0;   // interleaved partition (il_stride > 1)
   // secondary rays
   int shadow = 0, ao_samples = 0;
   uint32_t seed = 1;
@@ -192,7 +193,7 @@ int launch_kernel(yv_renderer *r, const yv::RenderParams &p, size_t smem) {
     if (grid > max_useful) grid = std::max(1l, max_useful);
     YV_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(unsigned int), r->stream));
   } else {
-    grid = (long)((p.width + 15) / 16) * ((p.y1 - p.y0 + 7) / 8);
+    grid = (long)((p.width + 15) / 16) * (p.num_tiles / p.tiles_x);
   }
   if (grid > 0) kern<<<(unsigned)grid, yv::kCtaThreads, smem, r->stream>>>(p);
   YV_CUDA(cudaGetLastError());
@@ -204,7 +205,7 @@ int launch_queue(yv_renderer *r, const yv::RenderParams &p) {
   auto kern = yv::render_queue<COUNT, STACK>;
   const size_t smem = yv::stack_smem_bytes(STACK) + yv::kQueueSmemPerWarp * (yv::kCtaThreads / 32);
   YV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long grid = (long)((p.width + 31) / 32) * ((p.y1 - p.y0 + 15) / 16);
+  const long grid = (long)((p.width + 31) / 32) * ((p.num_tiles / p.tiles_x + 1) / 2);
   if (grid > 0) kern<<<(unsigned)grid, yv::kCtaThreads, smem, r->stream>>>(p);
   YV_CUDA(cudaGetLastError());
   return YV_OK;
@@ -255,8 +256,20 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
   if (r->hits) { p.hit_node = r->d_hit_node; p.hit_child = r->d_hit_child; p.hit_t = r->d_hit_t; }
   p.counters = r->d_counters;
   p.tile_counter = r->d_tile_counter;
+  // tile rows (8 pixel rows each) this launch covers
+  int tile_rows;
+  if (r->il_stride > 1) {
+    p.y0 = 0; p.y1 = r->height;
+    p.band_rows8 = r->il_rows / 8; p.band_stride = r->il_stride; p.band_phase = r->il_phase;
+    const int blocks_total = (r->height + r->il_rows - 1) / r->il_rows;
+    const int my_blocks = blocks_total > r->il_phase ? (blocks_total - r->il_phase + r->il_stride - 1) / r->il_stride : 0;
+    tile_rows = my_blocks * p.band_rows8;
+  } else {
+    tile_rows = (p.y1 - p.y0 + 7) / 8;
+    p.band_rows8 = std::max(1, tile_rows + 1); p.band_stride = 1; p.band_phase = 0;
+  }
   p.tiles_x = (p.width + 7) / 8;
-  p.num_tiles = p.tiles_x * ((p.y1 - p.y0 + 7) / 8);
+  p.num_tiles = p.tiles_x * tile_rows;
   p.refill_threshold = r->opt_refill;
   p.shadow = r->shadow; p.ao_samples = r->ao_samples; p.seed = r->seed;
   p.voxel_size = r->voxel_size; p.ao_max_t = r->ao_max_t;
@@ -485,6 +498,7 @@ int yv_set_resolution(yv_renderer *r, int width, int height) {
     return fail(YV_ERR_ARG, "bad resolution");
   r->width = width; r->height = height;
   r->rows_set = false;
+  r->il_stride = 1;
   return YV_OK;
 }
 int yv_get_resolution(const yv_renderer *r, int *width, int *height) {
@@ -508,6 +522,16 @@ int yv_set_rows(yv_renderer *r, int y0, int y1) {
   if (!r) return fail(YV_ERR_ARG, "null renderer");
   if (y0 < 0 || y1 < y0) return fail(YV_ERR_ARG, "bad row band");
   r->y0 = y0; r->y1 = y1; r->rows_set = true;
+  r->il_stride = 1;
+  return YV_OK;
+}
+
+int yv_set_interleave(yv_renderer *r, int band_rows, int stride, int phase) {
+  if (!r) return fail(YV_ERR_ARG, "null renderer");
+  if (stride < 1 || phase < 0 || phase >= stride || band_rows < 16 || band_rows % 16 != 0)
+    return fail(YV_ERR_ARG, "interleave: band_rows must be a multiple of 16, 0 <= phase < stride");
+  r->il_rows = band_rows; r->il_stride = stride; r->il_phase = phase;
+  if (stride > 1) r->rows_set = false;
   return YV_OK;
 }
 
@@ -568,7 +592,7 @@ int yv_render_frame(yv_renderer *r, const uint8_t **rgba) {
   if (rc) return rc;
   const int y0 = r->rows_set ? std::max(0, r->y0) : 0;
   const int y1 = r->rows_set ? std::min(r->height, r->y1) : r->height;
-  if (y1 > y0) {
+  if (y1 > y0) {   // (interleaved partitions copy the whole frame; rows of other ranks keep their old content)
     const size_t off = (size_t)y0 * r->width * 4, bytes = (size_t)(y1 - y0) * r->width * 4;
     YV_CUDA(cudaMemcpyAsync(r->h_fb + off, (const uint8_t *)r->d_fb + off, bytes, cudaMemcpyDeviceToHost, r->stream));
   }

@@ -29,6 +29,13 @@ def row_band(rank, world, height, align=8):
     return y0, y1
 
 
+def interleaved_rows(rank, world, height, band_rows=32):
+    """Row indices rank `rank` renders under yv_set_interleave(band_rows, world, rank): blocks of
+    `band_rows` rows dealt round-robin (load balance when cost varies down the image)."""
+    rows = np.arange(height)
+    return rows[(rows // band_rows) % world == rank]
+
+
 class DeviceBuffer:
     """A cudaMalloc'ed buffer owned by libyv_b200 (exportable over CUDA IPC)."""
 
