@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_queue(const 
         s.t1z = __uint_as_float(slots[2 * kQueueRays + cur]); s.Tx = __uint_as_float(slots[3 * kQueueRays + cur]);
         s.Ty = __uint_as_float(slots[4 * kQueueRays + cur]);  s.Tz = __uint_as_float(slots[5 * kQueueRays + cur]);
         const uint32_t w = slots[6 * kQueueRays + cur];
-        s.ch = w & 7u; s.flags = w >> 3; s.idx = 0u; s.sp = 0;
+        s.ch = w & 7u; s.flags = w >> 3; s.idx = 0u; s.sp = 0; s.pend = 0u;
         s.masks = root_masks; s.child_base = root_child_base;
         stk.reset();
         lean_eval_next(s);

@@ -238,6 +238,7 @@ struct LeanState {
   float Nx, Ny, Nz;      // t2 + (t2 - t1) per axis, valid while that axis' ch bit is clear
   uint32_t ch, flags, idx;
   uint32_t masks, child_base;
+  uint32_t pend;         // exit axis (one-hot) of a sibling step chosen but not yet applied; 0 = none
   int sp;
 };
 
@@ -297,7 +298,7 @@ YV_HD bool lean_setup_root(LeanState &s, const bool root_valid,
   if (!setup_trace(px, py, pz, dx, dy, dz, r)) return false;
   if (!root_valid || fminf(fminf(r.t2x, r.t2y), r.t2z) <= 0.0f) return false;
   s.t1x = r.t1x; s.t1y = r.t1y; s.t1z = r.t1z; s.Tx = r.t2x; s.Ty = r.t2y; s.Tz = r.t2z;
-  s.flags = r.flags; s.sp = 0; s.idx = 0u;
+  s.flags = r.flags; s.sp = 0; s.idx = 0u; s.pend = 0u;
   lean_first_child(s);
   return true;
 }
@@ -315,6 +316,9 @@ YV_HD bool lean_begin(LeanState &s, const Fetch &fetch, const bool root_valid,
 // current child; while it is empty and a sibling follows, step (register-only); then descend or pop.
 // Folding the cheap steps into the call that performs the expensive node entry means a warp issues the
 // (descend | pop) block once per node visit instead of once per loop trip.
+// A sibling step is *deferred*: the chosen exit axis is parked in s.pend and applied at the top of the
+// next trip, which is also where a popped parent's GoNext is applied — one copy of the step code
+// serves both.
 // Stack: push(sp, U4, U4) / pop(sp, U4&, U4&).
 #ifndef YV_STEPS_PER_CALL
 #define YV_STEPS_PER_CALL 2
@@ -325,6 +329,8 @@ YV_HD int lean_step(LeanState &s, const Fetch &fetch, Stack &stk, const bool fro
   bool descend, can_adv;
 #pragma unroll
   for (int k = 0;; ++k) {
+    lean_apply_step(s, s.pend);                                    // deferred GoNext (no-op when pend == 0)
+    s.pend = 0u;
     bit = 1u << (s.ch ^ s.flags);
     const bool xy = s.Tx > s.Ty;
     const bool nz = xy ? (s.Ty < s.Tz) : (s.Tx < s.Tz);
@@ -334,11 +340,10 @@ YV_HD int lean_step(LeanState &s, const Fetch &fetch, Stack &stk, const bool fro
     descend = (((s.masks >> 8) & bit) != 0u) && (tmin > 0.0f);                               // :20,:35
     can_adv = (s.ch & e) == 0u;                                                              // :38
     if (descend || !can_adv) break;
-    lean_apply_step(s, e);
+    s.pend = e;
     if (k + 1 == YV_STEPS_PER_CALL) return kStepContinue;
   }
 
-  uint32_t pending = 0u;                                           // exit axis (one-hot) to apply after a pop
   if (descend) {
     if (can_adv) {
       const U4 a = { YV_F2U(s.t1x), YV_F2U(s.t1y), YV_F2U(s.t1z), s.idx };
@@ -354,12 +359,11 @@ YV_HD int lean_step(LeanState &s, const Fetch &fetch, Stack &stk, const bool fro
     stk.pop(s.sp, a, b);
     s.t1x = YV_U2F(a.x); s.t1y = YV_U2F(a.y); s.t1z = YV_U2F(a.z); s.idx = a.w;
     s.Tx = YV_U2F(b.x); s.Ty = YV_U2F(b.y); s.Tz = YV_U2F(b.z);
-    s.ch = b.w & 7u; pending = b.w >> 3;
+    s.ch = b.w & 7u; s.pend = b.w >> 3;                            // the parent's GoNext, applied next trip
   }
   lean_load_node(s, fetch, descend);                                                         // :23
   if (descend) lean_first_child(s);                                                          // :24
   lean_eval_next(s);
-  lean_apply_step(s, pending);                                     // the parent's deferred GoNext (no-op for 0)
   return kStepContinue;
 }
 
