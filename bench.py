@@ -47,6 +47,8 @@ def parse():
                          "blocks of --band-rows rows (tiles) or contiguous row bands (bands)")
     ap.add_argument("--band-rows", type=int, default=32)
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--detail", type=float, default=0.0,
+                    help="SVORenderer::SetDetailCoef LOD cut-off (0 = off, the CPU tracer's behaviour; the CUDA demo used 1.0)")
     ap.add_argument("--flythrough", action="store_true",
                     help="tiles partition: move the camera every step (BASELINE config 5: 64-frame flythrough)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -157,15 +159,16 @@ class ClockSampler:
 
 def workload_name(a):
     scene = "gen_spheres sphere-fractal SVO" if a.scene == "fractal" else "gen_largevol-style synthetic iso-volume SVO (seed 219, iso 200)"
-    return ("%s depth %d, %dx%d primary rays + Lambert%s" %
-            (scene, a.depth, a.width, a.height, " + shadow + 4 AO" if a.secondary else ""))
+    return ("%s depth %d, %dx%d primary rays + Lambert%s%s" %
+            (scene, a.depth, a.width, a.height, " + shadow + 4 AO" if a.secondary else "",
+             ", LOD detailCoef %g" % a.detail if a.detail > 0 else ""))
 
 
 def oracle_frame(svo_nodes, root, a, frame, threads, want_visits=False):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import yvo
     pos, d = camera_for(frame)
-    cam = yvo.camera(pos, d, UP, FOV, a.width, a.height)
+    cam = yvo.camera(pos, d, UP, FOV, a.width, a.height, detail_coef=a.detail)
     sec = None
     if a.secondary:
         sec = yvo.secondary(shadow=1, ao_samples=4, seed=1, light_pos=(0.6, 0.4, 1.2),
@@ -258,6 +261,7 @@ def main():
     r.SetScene(svo)
     r.SetResolution(a.width, a.height)
     r.SetViewUp(UP); r.SetFOV(FOV)
+    r.SetDetailCoef(a.detail)
     if a.secondary:
         r.SetSecondary(shadow=1, ao_samples=4, seed=1, light_pos=(0.6, 0.4, 1.2),
                        voxel_size=1.0 / (1 << a.depth), ao_max_t=0.05)

@@ -84,6 +84,12 @@ int yv_set_resolution(yv_renderer *r, int width, int height);  /* SetResolution 
 int yv_get_resolution(const yv_renderer *r, int *width, int *height);   /* GetResolution (:19)   */
 int yv_set_fov(yv_renderer *r, float fov_deg);                 /* SetFOV        (:21)            */
 int yv_get_fov(const yv_renderer *r, float *fov_deg);          /* GetFOV (demo/SVORenderer.h:23) */
+/* SetDetailCoef / GetDetailCoef (demo/SVORenderer.h:25-26): level-of-detail cut-off of the CUDA tracer.
+ * With coef > 0 a child node whose cube is smaller than coef * rad(fov/2) / width * (entry distance)
+ * (rp.detailCoef, demo/SVORenderer.cpp:104) is not descended into: it is the hit, reported with child = -1
+ * and shaded with its sub-tree average VoxNode::data (demo/SVORenderer.cpp:176-179). 0 (default) = off. */
+int yv_set_detail_coef(yv_renderer *r, float coef);
+int yv_get_detail_coef(const yv_renderer *r, float *coef);
 
 /* const Color32* RenderFrame()  (cell/svorenderer.h:23): synchronous; *rgba aliases
  * renderer-owned pinned host memory (width*height*4 bytes, R,G,B,A), valid until the next

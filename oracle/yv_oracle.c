@@ -129,6 +129,9 @@ typedef struct {
   uint32_t dir_flags;
   int front_only;        /* 0 = reference behaviour; 1 = secondary rays: a leaf counts only
                             if its own min(t2) > 0 (no hits behind the origin)              */
+  float detail;          /* rp.detailCoef (demo/SVORenderer.cpp:104); 0 = off. A child node whose
+                            cube is smaller than detail * entry distance is not entered: it is the
+                            hit, child = -1, shaded with VoxNode::data (SVORenderer.cpp:176-179)  */
   /* result (TraceResult, ppu_renderer.cpp:7-12) */
   yv_node_id node;
   int child;
@@ -137,8 +140,8 @@ typedef struct {
   uint64_t visits, iters;
 } trace_ctx;
 
-/* PPURendererBase::RecTrace (cell/ppu_renderer.cpp:18-41) */
-static int rec_trace(trace_ctx *c, yv_node_id id, v3 t1, v3 t2) {
+/* PPURendererBase::RecTrace (cell/ppu_renderer.cpp:18-41); `level` = depth of node `id` (root 0) */
+static int rec_trace(trace_ctx *c, yv_node_id id, v3 t1, v3 t2, int level) {
   if (YV_IS_NULL(id) || min3(t2) <= 0) return 0;            /* :20 */
   if (id >= c->count) return 0;                             /* malformed pool: assert in ref (:54) */
   const yv_vox_node *node = &c->nodes[id];                  /* :23  <- counted node fetch */
@@ -151,8 +154,18 @@ static int rec_trace(trace_ctx *c, yv_node_id id, v3 t1, v3 t2) {
       c->node = id; c->child = cc; c->t = max3(t1);         /* :29-31 */
       return 1;
     }
-    if (!YV_LEAF_FLAG(node->flags, cc) && rec_trace(c, node->child[cc], t1, t2))  /* :35 */
-      return 1;
+    if (!YV_LEAF_FLAG(node->flags, cc)) {
+      const yv_node_id kid = node->child[cc];
+      if (c->detail > 0 && !YV_IS_NULL(kid) && min3(t2) > 0) {           /* LOD cut-off (CUDA tracer) */
+        float tent = max3(t1);
+        float csize = ldexpf(1.0f, -(level + 1));
+        if (tent > 0 && csize < c->detail * tent) {
+          c->node = kid; c->child = -1; c->t = tent;
+          return 1;
+        }
+      }
+      if (rec_trace(c, kid, t1, t2, level + 1)) return 1;                /* :35 */
+    }
     if (!go_next(&ch, &t1, &t2)) return 0;                  /* :38 */
   }
 }
@@ -161,7 +174,7 @@ static int trace_ray(trace_ctx *c, yv_node_id root, v3 pos, v3 dir) {
   v3 t1, t2;
   dir = adjust_dir(dir);
   if (!setup_trace(pos, dir, &t1, &t2, &c->dir_flags)) return 0;
-  return rec_trace(c, root, t1, t2);
+  return rec_trace(c, root, t1, t2, 0);
 }
 
 /* ---- VoxData unpack + SimpleShader::Shade restatement (spec: include/yv_format.h) ------- */
@@ -260,6 +273,11 @@ static void *render_strip(void *arg) {
   trace_ctx c;
   memset(&c, 0, sizeof c);
   c.nodes = j->nodes; c.count = j->count;
+  if (j->cam->detail_coef > 0) {
+    /* rp.detailCoef = m_detailCoef * grad2rad(m_fov / 2) / m_viewSize.x  (demo/SVORenderer.cpp:104) */
+    float half_rad = (j->cam->fov_deg / 2) * (float)(3.14159265358979323846 / 180.0);
+    c.detail = (j->cam->detail_coef * half_rad) / (float)W;
+  }
 
   for (int y = j->y0; y < j->y1; ++y) {
     for (int x = 0; x < W; ++x) {
@@ -276,7 +294,7 @@ static void *render_strip(void *arg) {
       if (trace_ray(&c, j->root, pos, d)) {                                  /* :60-65 */
         hn = c.node; hc = c.child; ht = c.t;
         j->stats.hits++;
-        yv_vox_data data = j->nodes[hn].child[hc];                           /* :67 */
+        yv_vox_data data = hc < 0 ? j->nodes[hn].data : j->nodes[hn].child[hc];   /* :67; LOD: node.data */
         float dd[3] = { d.x, d.y, d.z };
         if (!want_sec) {
           yvo_shade(data, dd, ht, j->cam->pos, j->cam->pos, 1.0f, px);       /* light = eye (:33-34) */

@@ -27,6 +27,7 @@ typedef struct yvo_camera {
   float fov_deg;      /* horizontal, degrees; default 70 (renderer_base.h:25) */
   int32_t width;
   int32_t height;
+  float detail_coef;  /* SVORenderer::SetDetailCoef (demo/SVORenderer.h:25); 0 = no LOD cut-off   */
 } yvo_camera;
 
 /* RayDirData{dir0,du,dv} (cell/renderer_base.h:50-61) */

@@ -11,6 +11,9 @@
 using namespace yv;
 
 namespace {
+float g_detail = 0.0f;   // rp.detailCoef; > 0 switches the LOD cut-off on (lean mode only)
+bool g_lod_hit = false;
+const uint32_t *g_node_data = nullptr;
 int g_mode = 2;   // 0 = trace_step, 1 = seek_child/enter_node, 2 = lean_step (what render_frame runs)
 struct HostStack {
   StackEntry e[kMaxStack];
@@ -40,12 +43,14 @@ bool trace(const HostFetch &fetch, bool root_valid, HostStack &stk, float ox, fl
     if (!lean_begin(ls, fetch, root_valid, ox, oy, oz, dx, dy, dz)) return false;
     for (;;) {
       ++steps;
-      const int r = lean_step(ls, fetch, g_lean_stack, front_only);
+      const int r = g_detail > 0.0f ? lean_step<true>(ls, fetch, g_lean_stack, front_only, g_detail)
+                                    : lean_step<false>(ls, fetch, g_lean_stack, front_only);
       if (r == kStepContinue) continue;
       if (g_lean_stack.max_sp > stk.max_sp) stk.max_sp = g_lean_stack.max_sp;
       if (r == kStepMiss) return false;
+      g_lod_hit = r == kStepLodHit;
       // present the result through the classic state the caller reads
-      s.t1x = ls.t1x; s.t1y = ls.t1y; s.t1z = ls.t1z; s.ch = ls.ch; s.flags = ls.flags;
+      s.t1x = ls.t1x; s.t1y = ls.t1y; s.t1z = ls.t1z; s.ch = ls.ch; s.flags = ls.flags; s.idx = ls.idx;
       rec = fetch.recs[ls.idx];
       return true;
     }
@@ -71,6 +76,7 @@ bool trace(const HostFetch &fetch, bool root_valid, HostStack &stk, float ox, fl
 }  // namespace
 
 extern "C" void yve_set_mode(int mode) { g_mode = mode; }
+extern "C" void yve_set_lod(float detail, const uint32_t *node_data) { g_detail = detail; g_node_data = node_data; }
 
 extern "C" int yve_render(const uint32_t *records, const uint32_t *leaves, int root_valid,
                           const float pos[3], const float dir0[3], const float du[3], const float dv[3],
@@ -91,10 +97,13 @@ extern "C" int yve_render(const uint32_t *records, const uint32_t *leaves, int r
       dx = adjust_dir1(dx); dy = adjust_dir1(dy); dz = adjust_dir1(dz);
       RayState s; Rec rec;
       uint32_t out = 0, hn = YV_MISS_NODE; int32_t hc = YV_MISS_CHILD; float ht = 0.0f;
+      g_lod_hit = false;
       if (trace(fetch, root_valid != 0, stk, pos[0], pos[1], pos[2], dx, dy, dz, false, s, rec, steps)) {
         const uint32_t c = s.ch ^ s.flags;
-        hn = rec.orig_id; hc = (int32_t)c; ht = max3f(s.t1x, s.t1y, s.t1z);
-        const uint32_t data = leaves[rec.leaf_base + (uint32_t)YV_POPC(rec.masks & 0xffu & ((1u << c) - 1u))];
+        const bool lod = g_lod_hit;
+        hn = rec.orig_id; hc = lod ? -1 : (int32_t)c; ht = max3f(s.t1x, s.t1y, s.t1z);
+        const uint32_t data = lod ? g_node_data[s.idx]
+                                  : leaves[rec.leaf_base + (uint32_t)YV_POPC(rec.masks & 0xffu & ((1u << c) - 1u))];
         float nx, ny, nz;
         unpack_normal(data, nx, ny, nz);
         const float Px = YV_FADD(pos[0], YV_FMUL(dx, ht)), Py = YV_FADD(pos[1], YV_FMUL(dy, ht)), Pz = YV_FADD(pos[2], YV_FMUL(dz, ht));

@@ -63,3 +63,33 @@ def test_empty_scene():
     s = yv.SVOData.FromNodes(yv.EMPTY_NODE, np.zeros(0, yv.NODE_DTYPE))
     o, e = _compare(s, scenes.CAMERAS[2], 32, 32)
     assert (o["rgba"] == 0).all()
+
+
+@pytest.mark.parametrize("coef", [2.0, 6.0, 15.0])
+def test_lod_cutoff(coef):
+    """SetDetailCoef (demo/SVORenderer.h:25): LOD hits report child = -1 and shade with VoxNode::data."""
+    svo = scenes.fractal(9)
+    nodes = svo.nodes()
+    recs, leaves = svo.packed()
+    node_data = nodes["data"][recs[:, 3]]
+    W, H = 200, 150
+    n_lod = 0
+    for cam_spec in (scenes.CAMERAS[1], scenes.CAMERAS[2], scenes.CAMERAS[4]):
+        name, pos, d, up, fov = cam_spec
+        o = yvo.render(nodes, svo.GetRoot(), yvo.camera(pos, d, up, fov, W, H, detail_coef=coef), threads=4)
+        d0, du, dv = yv.init_ray_dir(d, up, fov, W, H)
+        half_rad = np.float32(np.float32(fov) / np.float32(2)) * np.float32(np.pi / 180.0)
+        detail = np.float32(np.float32(coef) * half_rad) / np.float32(W)
+        e = yve.render(recs, leaves, 1, pos, d0, du, dv, pos, W, H, detail=float(detail), node_data=node_data)
+        assert (o["node"] == e["node"]).all() and (o["child"] == e["child"]).all()
+        assert o["t"].tobytes() == e["t"].tobytes() and (o["rgba"] == e["rgba"]).all()
+        lod = (o["child"] == -1) & (o["node"] != yvo.MISS_NODE)
+        n_lod += int(lod.sum())
+        if lod.any():
+            # an LOD hit names an internal node; cutting the descent short saves node visits
+            full = yvo.render(nodes, svo.GetRoot(), yvo.camera(pos, d, up, fov, W, H), threads=4)
+            assert o["stats"]["node_visits"] < full["stats"]["node_visits"]
+            both = lod & (full["node"] != yvo.MISS_NODE)       # a coarse node can be hit where the fine ray slips through
+            assert (o["t"][both] <= full["t"][both]).all()
+    if coef >= 6.0:
+        assert n_lod > 100

@@ -26,9 +26,10 @@ def _check(o, img, node, child, t, tag):
     assert (img == o["rgba"]).all(), "%s: rgba not identical" % tag
 
 
-def _render_gpu(r, cam_spec, W, H, sec=None):
+def _render_gpu(r, cam_spec, W, H, sec=None, detail=0.0):
     name, pos, d, up, fov = cam_spec
     r.SetResolution(W, H)
+    r.SetDetailCoef(detail)
     r.SetViewPos(pos); r.SetViewDir(d); r.SetViewUp(up); r.SetFOV(fov)
     if sec:
         r.SetSecondary(**sec)
@@ -39,9 +40,9 @@ def _render_gpu(r, cam_spec, W, H, sec=None):
     return img, node, child, t
 
 
-def _render_cpu(svo, cam_spec, W, H, sec=None, visits=False):
+def _render_cpu(svo, cam_spec, W, H, sec=None, visits=False, detail=0.0):
     name, pos, d, up, fov = cam_spec
-    return yvo.render(svo.nodes(), svo.GetRoot(), yvo.camera(pos, d, up, fov, W, H),
+    return yvo.render(svo.nodes(), svo.GetRoot(), yvo.camera(pos, d, up, fov, W, H, detail_coef=detail),
                       sec=yvo.secondary(**sec) if sec else None, threads=8, want_visits=visits)
 
 
@@ -136,6 +137,30 @@ def test_other_scenes(renderer, persistent):
         for cam in scenes.CAMERAS:
             img, node, child, t = _render_gpu(renderer, cam, 200, 160)
             _check(_render_cpu(svo, cam, 200, 160), img, node, child, t, cam[0])
+
+
+@pytest.mark.parametrize("persistent", [0, 1], ids=["tiles", "persistent"])
+@pytest.mark.parametrize("coef", [1.0, 4.0, 12.0])
+def test_lod_detail_coef(renderer, coef, persistent):
+    """SVORenderer::SetDetailCoef (demo/SVORenderer.h:25-26): LOD-terminated traversal, primary and secondary."""
+    svo = scenes.fractal(11)
+    renderer.SetOption("schedule", persistent)
+    renderer.SetScene(svo)
+    sec = dict(shadow=1, ao_samples=2, seed=3, light_pos=(0.6, 0.4, 1.2), voxel_size=1.0 / 2048, ao_max_t=0.05)
+    n_lod = 0
+    for cam in (scenes.CAMERAS[1], scenes.CAMERAS[2], scenes.CAMERAS[4]):
+        img, node, child, t = _render_gpu(renderer, cam, 640, 400, detail=coef)
+        o = _render_cpu(svo, cam, 640, 400, detail=coef)
+        _check(o, img, node, child, t, "lod%g" % coef)
+        n_lod += int(((child == -1) & (node != yvo.MISS_NODE)).sum())
+        img, node, child, t = _render_gpu(renderer, cam, 320, 200, sec, detail=coef)
+        _check(_render_cpu(svo, cam, 320, 200, sec, detail=coef), img, node, child, t, "lod%g/sec" % coef)
+    assert renderer.GetDetailCoef() == coef
+    if coef >= 4.0:
+        assert n_lod > 1000
+    renderer.SetDetailCoef(0.0)
+    renderer.SetSecondary(0, 0)
+    renderer.SetOption("schedule", 0)
 
 
 def test_empty_scene_and_no_scene():

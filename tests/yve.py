@@ -21,13 +21,14 @@ def lib():
                                  C.c_uint32, C.c_float, C.c_float, vp, vp, vp, vp,
                                  C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
         L.yve_set_mode.argtypes = [C.c_int]
+        L.yve_set_lod.argtypes = [C.c_float, C.c_void_p]
         L.yve_render.restype = C.c_int
         _lib = L
     return _lib
 
 
 def render(records, leaves, root_valid, pos, dir0, du, dv, light, width, height,
-           shadow=0, ao_samples=0, seed=1, voxel_size=0.0, ao_max_t=0.05, mode=2):
+           shadow=0, ao_samples=0, seed=1, voxel_size=0.0, ao_max_t=0.05, mode=2, detail=0.0, node_data=None):
     records = np.ascontiguousarray(records, np.uint32)
     leaves = np.ascontiguousarray(leaves, np.uint32)
     n = width * height
@@ -35,6 +36,8 @@ def render(records, leaves, root_valid, pos, dir0, du, dv, light, width, height,
     rgba = np.zeros(n, np.uint32)
     fetches, max_sp, visits = C.c_uint64(), C.c_int(), C.c_uint64()
     lib().yve_set_mode(int(mode))
+    nd = np.ascontiguousarray(node_data, np.uint32) if node_data is not None else None
+    lib().yve_set_lod(float(detail), nd.ctypes.data_as(C.c_void_p) if nd is not None else None)
     v = lambda a: (C.c_float * 3)(*[float(x) for x in a])
     rc = lib().yve_render(records.ctypes.data_as(C.c_void_p), leaves.ctypes.data_as(C.c_void_p), int(root_valid),
                           v(pos), v(dir0), v(du), v(dv), v(light), width, height, shadow, ao_samples, seed,

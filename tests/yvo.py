@@ -12,7 +12,7 @@ MISS_NODE = 0x80000000
 
 class Camera(C.Structure):
     _fields_ = [("pos", C.c_float * 3), ("dir", C.c_float * 3), ("up", C.c_float * 3),
-                ("fov_deg", C.c_float), ("width", C.c_int32), ("height", C.c_int32)]
+                ("fov_deg", C.c_float), ("width", C.c_int32), ("height", C.c_int32), ("detail_coef", C.c_float)]
 
 
 class RayDir(C.Structure):
@@ -62,7 +62,7 @@ def lib():
     return _lib
 
 
-def camera(pos, dir, up=(0, 0, 1), fov=70.0, width=64, height=64):
+def camera(pos, dir, up=(0, 0, 1), fov=70.0, width=64, height=64, detail_coef=0.0):
     c = Camera()
     c.pos[:] = [float(v) for v in pos]
     c.dir[:] = [float(v) for v in dir]
@@ -70,6 +70,7 @@ def camera(pos, dir, up=(0, 0, 1), fov=70.0, width=64, height=64):
     c.fov_deg = float(fov)
     c.width = int(width)
     c.height = int(height)
+    c.detail_coef = float(detail_coef)
     return c
 
 

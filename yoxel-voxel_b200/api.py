@@ -84,6 +84,8 @@ def lib():
         "yv_get_resolution": (i32, [vp, P(i32), P(i32)]),
         "yv_set_fov": (i32, [vp, f32]),
         "yv_get_fov": (i32, [vp, P(f32)]),
+        "yv_set_detail_coef": (i32, [vp, f32]),
+        "yv_get_detail_coef": (i32, [vp, P(f32)]),
         "yv_render_frame": (i32, [vp, P(vp)]),
         "yv_render_frame_device": (i32, [vp, vp]),
         "yv_render_frame_device_async": (i32, [vp, vp]),
@@ -280,6 +282,14 @@ class SVORenderer:
     def GetFOV(self):                                     # demo/SVORenderer.h:23
         f = C.c_float()
         _check(lib().yv_get_fov(self._h, C.byref(f)))
+        return f.value
+
+    def SetDetailCoef(self, coef):                        # demo/SVORenderer.h:25
+        _check(lib().yv_set_detail_coef(self._h, float(coef)))
+
+    def GetDetailCoef(self):                              # demo/SVORenderer.h:26
+        f = C.c_float()
+        _check(lib().yv_get_detail_coef(self._h, C.byref(f)))
         return f.value
 
     def RenderFrame(self):

@@ -31,6 +31,8 @@ namespace yv {
 struct RenderParams {
   const uint4 *recs;           // packed records (svo_pack.h)
   const uint32_t *leaves;      // inline VoxData words
+  const uint32_t *node_data;   // VoxNode::data per record (LOD hits only; NULL when detail == 0)
+  float detail;                // rp.detailCoef (demo/SVORenderer.cpp:104); 0 = no LOD cut-off
   uint32_t root_valid;
   uint32_t smem_nodes;         // records staged in shared memory (<= record count)
   float pos[3];                // eye (m_pos) — also shader viewerPos (renderer_base.h:30-35)
@@ -155,9 +157,9 @@ __device__ __forceinline__ int tile_row_y(const RenderParams &p, int ty) {
   return p.y0 + ((blk * p.band_stride + p.band_phase) * p.band_rows8 + within) * 8;
 }
 
-enum : int { kLaneIdle = 0, kLaneActive = 1, kLaneHit = 2, kLaneMiss = 3, kLaneNew = 4 };
+enum : int { kLaneIdle = 0, kLaneActive = 1, kLaneHit = 2, kLaneMiss = 3, kLaneNew = 4, kLaneLodHit = 5 };
 
-template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED>
+template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED, bool LOD>
 __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_frame(const __grid_constant__ RenderParams p) {
   extern __shared__ uint4 smem[];
   uint4 *staged = smem;
@@ -242,16 +244,18 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_frame(const 
 #pragma unroll
       for (int u = 0; u < kStepsPerVote; ++u) {
         if (state == kLaneActive) {
-          const int r = lean_step(s, fetch, stk, SEC && stage > 0);
+          const int r = lean_step<LOD>(s, fetch, stk, SEC && stage > 0, p.detail);
           if (r == kStepHit) state = kLaneHit;
           else if (r == kStepMiss) state = kLaneMiss;
+          else if (LOD && r == kStepLodHit) state = kLaneLodHit;
         }
       }
     }
 
     // ---- 4. finished rays: shade / spawn the next secondary ray / store -------------------------
-    if (state == kLaneHit || state == kLaneMiss) {
-      const bool hit = state == kLaneHit;
+    if (state == kLaneHit || state == kLaneMiss || (LOD && state == kLaneLodHit)) {
+      const bool lod_hit = LOD && state == kLaneLodHit;
+      const bool hit = state == kLaneHit || lod_hit;
       const uint32_t pixel = (uint32_t)y * (uint32_t)p.width + (uint32_t)x;
       bool done = true;
       uint32_t rgba = 0u;
@@ -261,8 +265,8 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_frame(const 
         if (hit) {
           const Rec rec = fetch.load(s.idx);                      // re-read the hit node's record
           const uint32_t c = s.ch ^ s.flags;
-          hn = rec.orig_id; hc = (int32_t)c; ht = max3f(s.t1x, s.t1y, s.t1z);
-          sdata = leaf_data(p, rec, c);
+          hn = rec.orig_id; hc = lod_hit ? -1 : (int32_t)c; ht = max3f(s.t1x, s.t1y, s.t1z);
+          sdata = lod_hit ? __ldg(p.node_data + s.idx) : leaf_data(p, rec, c);
           unpack_normal(sdata, nx, ny, nz);
           float dx, dy, dz;                                       // the primary direction, recomputed
           primary_dir(p.dir0, p.du, p.dv, x, y, dx, dy, dz);
@@ -432,7 +436,7 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_queue(const 
 #pragma unroll
     for (int u = 0; u < kStepsPerVote; ++u) {
       if (cur >= 0) {
-        const int r = lean_step(s, fetch, stk, false);
+        const int r = lean_step<false>(s, fetch, stk, false);
         if (r != kStepContinue) {
           const bool hit = r == kStepHit;
           slots[0 * kQueueRays + cur] = hit ? s.idx : 0xffffffffu;

@@ -4,7 +4,7 @@
 namespace yv {
 
 int pack_svo(const HostSVO &svo, PackedSVO &out, std::string &err) {
-  out.records.clear(); out.leaves.clear(); out.level_start.clear();
+  out.records.clear(); out.leaves.clear(); out.level_start.clear(); out.node_data.clear();
   out.root_null = YV_IS_NULL(svo.root);
   if (out.root_null) { out.level_start.push_back(0); return 0; }
   if (svo.root >= svo.nodes.size()) { err = "root id outside node pool"; return -1; }
@@ -13,6 +13,7 @@ int pack_svo(const HostSVO &svo, PackedSVO &out, std::string &err) {
   const int kMaxLevels = 32;
   std::vector<uint32_t> cur{ svo.root }, nxt;      // reference ids of the current / next level
   out.records.reserve(svo.nodes.size());
+  out.node_data.reserve(svo.nodes.size());
   uint64_t emitted = 0;
   for (int level = 0; !cur.empty(); ++level) {
     if (level >= kMaxLevels) { err = "node pool deeper than 32 levels (cycle?)"; return -2; }
@@ -37,6 +38,7 @@ int pack_svo(const HostSVO &svo, PackedSVO &out, std::string &err) {
       r.masks = leaf_mask | (child_mask << 8);
       r.orig_id = id;
       out.records.push_back(r);
+      out.node_data.push_back(nd.data);
     }
     emitted += cur.size();
     if (emitted + nxt.size() > kMaxRecords) { err = "packed pool exceeds 2^31 records"; return -4; }

@@ -31,6 +31,7 @@ static_assert(sizeof(PackedRecord) == 16, "record must be 16 bytes");
 struct PackedSVO {
   std::vector<PackedRecord> records;     // records[0] is the root when !root_null
   std::vector<uint32_t> leaves;          // inline VoxData words, grouped per node
+  std::vector<uint32_t> node_data;       // VoxNode::data (sub-tree average) per record, read only by LOD hits
   std::vector<uint32_t> level_start;     // first record index of each tree level (+ end sentinel)
   bool root_null = true;
 };

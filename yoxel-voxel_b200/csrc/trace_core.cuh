@@ -239,6 +239,7 @@ struct LeanState {
   uint32_t ch, flags, idx;
   uint32_t masks, child_base;
   uint32_t pend;         // exit axis (one-hot) of a sibling step chosen but not yet applied; 0 = none
+  uint32_t level;        // depth of the current node (root = 0); only maintained when LOD is on
   int sp;
 };
 
@@ -298,7 +299,7 @@ YV_HD bool lean_setup_root(LeanState &s, const bool root_valid,
   if (!setup_trace(px, py, pz, dx, dy, dz, r)) return false;
   if (!root_valid || fminf(fminf(r.t2x, r.t2y), r.t2z) <= 0.0f) return false;
   s.t1x = r.t1x; s.t1y = r.t1y; s.t1z = r.t1z; s.Tx = r.t2x; s.Ty = r.t2y; s.Tz = r.t2z;
-  s.flags = r.flags; s.sp = 0; s.idx = 0u; s.pend = 0u;
+  s.flags = r.flags; s.sp = 0; s.idx = 0u; s.pend = 0u; s.level = 0u;
   lean_first_child(s);
   return true;
 }
@@ -323,8 +324,14 @@ YV_HD bool lean_begin(LeanState &s, const Fetch &fetch, const bool root_valid,
 #ifndef YV_STEPS_PER_CALL
 #define YV_STEPS_PER_CALL 2
 #endif
-template <class Fetch, class Stack>
-YV_HD int lean_step(LeanState &s, const Fetch &fetch, Stack &stk, const bool front_only) {
+//
+// LOD (SVORenderer::SetDetailCoef, demo/SVORenderer.h:25; rp.detailCoef, demo/SVORenderer.cpp:104): with
+// LOD on, a child NODE whose cube is smaller than detail * (distance at which the ray enters it) is not
+// entered; it is reported as the hit with child = -1 and shaded with its sub-tree average VoxNode::data
+// (endNodeChild < 0 -> node.data, demo/SVORenderer.cpp:176-179). Returns kStepLodHit with s.idx = that node.
+enum : int { kStepLodHit = 3 };
+template <bool LOD, class Fetch, class Stack>
+YV_HD int lean_step(LeanState &s, const Fetch &fetch, Stack &stk, const bool front_only, const float detail = 0.0f) {
   uint32_t bit, e;
   bool descend, can_adv;
 #pragma unroll
@@ -339,6 +346,17 @@ YV_HD int lean_step(LeanState &s, const Fetch &fetch, Stack &stk, const bool fro
     if (((s.masks & bit) != 0u) && (!front_only || tmin > 0.0f)) return kStepHit;           // :27
     descend = (((s.masks >> 8) & bit) != 0u) && (tmin > 0.0f);                               // :20,:35
     can_adv = (s.ch & e) == 0u;                                                              // :38
+    if (LOD) {
+      // child cube edge 2^-(level+1) < detail * t_enter   <=>   t_enter * (detail * 2^(level+1)) > 1
+      // (scaling by a power of two commutes with rounding); t_enter is only compared here, the stored
+      // hit distance is recomputed in the exact form by the caller.
+      const float tent = fmaxf(fmaxf(s.t1x, s.t1y), s.t1z);
+      const float lodk = YV_U2F(YV_F2U(detail) + ((s.level + 1u) << 23));
+      if (descend && tent > 0.0f && YV_FMUL(tent, lodk) > 1.0f) {
+        s.idx = s.child_base + (uint32_t)YV_POPC((s.masks >> 8) & (bit - 1u));
+        return kStepLodHit;
+      }
+    }
     if (descend || !can_adv) break;
     s.pend = e;
     if (k + 1 == YV_STEPS_PER_CALL) return kStepContinue;
@@ -347,11 +365,12 @@ YV_HD int lean_step(LeanState &s, const Fetch &fetch, Stack &stk, const bool fro
   if (descend) {
     if (can_adv) {
       const U4 a = { YV_F2U(s.t1x), YV_F2U(s.t1y), YV_F2U(s.t1z), s.idx };
-      const U4 b = { YV_F2U(s.Tx), YV_F2U(s.Ty), YV_F2U(s.Tz), s.ch | (e << 3) };
+      const U4 b = { YV_F2U(s.Tx), YV_F2U(s.Ty), YV_F2U(s.Tz), s.ch | (e << 3) | (LOD ? (s.level << 6) : 0u) };
       stk.push(s.sp, a, b);
       ++s.sp;
     }
     s.idx = s.child_base + (uint32_t)YV_POPC((s.masks >> 8) & (bit - 1u));
+    if (LOD) ++s.level;
   } else {
     if (s.sp == 0) return kStepMiss;
     --s.sp;
@@ -359,7 +378,8 @@ YV_HD int lean_step(LeanState &s, const Fetch &fetch, Stack &stk, const bool fro
     stk.pop(s.sp, a, b);
     s.t1x = YV_U2F(a.x); s.t1y = YV_U2F(a.y); s.t1z = YV_U2F(a.z); s.idx = a.w;
     s.Tx = YV_U2F(b.x); s.Ty = YV_U2F(b.y); s.Tz = YV_U2F(b.z);
-    s.ch = b.w & 7u; s.pend = b.w >> 3;                            // the parent's GoNext, applied next trip
+    s.ch = b.w & 7u; s.pend = (b.w >> 3) & 7u;                     // the parent's GoNext, applied next trip
+    if (LOD) s.level = b.w >> 6;
   }
   lean_load_node(s, fetch, descend);                                                         // :23
   if (descend) lean_first_child(s);                                                          // :24

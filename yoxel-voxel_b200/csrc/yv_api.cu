@@ -34,6 +34,7 @@ int fail(int code, const std::string &msg) { g_err = msg; return code; }
 struct DeviceSVO {
   uint4 *recs = nullptr;
   uint32_t *leaves = nullptr;
+  uint32_t *node_data = nullptr;      // uploaded on first use of the LOD cut-off
   size_t n_recs = 0, n_leaves = 0;
 };
 
@@ -54,6 +55,7 @@ struct yv_renderer {
   // RendererBase state (renderer_base.h:10-18,25)
   float pos[3] = { 0, 0, 0 }, dir[3] = { 1, 0, 0 }, up[3] = { 0, 0, 1 };
   float fov = 70.0f;
+  float detail_coef = 0.0f;           // SVORenderer::m_detailCoef (demo/SVORenderer.h:56); 0 = off
   int width = 0, height = 0;
   int y0 = 0, y1 = 0;
   bool rows_set = false;
@@ -178,9 +180,9 @@ void init_ray_dir(const yv_renderer *r, float dir0[3], float du[3], float dv[3])
   init_ray_dir_raw(r->dir, r->up, r->fov, r->width, r->height, dir0, du, dv);
 }
 
-template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED>
+template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED, bool LOD = false>
 int launch_kernel(yv_renderer *r, const yv::RenderParams &p, size_t smem) {
-  auto kern = yv::render_frame<SEC, COUNT, STACK, PERSISTENT, STAGED>;
+  auto kern = yv::render_frame<SEC, COUNT, STACK, PERSISTENT, STAGED, LOD>;
   YV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long grid;
   if (PERSISTENT) {
@@ -221,6 +223,13 @@ template <bool SEC, bool COUNT, int STACK>
 int launch_schedule(yv_renderer *r, const yv::RenderParams &p, size_t smem) {
   return r->opt_persistent == 1 ? launch_staged<SEC, COUNT, STACK, true>(r, p, smem)
                            : launch_staged<SEC, COUNT, STACK, false>(r, p, smem);
+}
+
+// LOD variants exist for the local-memory stack without staging (the defaults)
+template <bool SEC, bool COUNT>
+int launch_lod(yv_renderer *r, const yv::RenderParams &p) {
+  return r->opt_persistent == 1 ? launch_kernel<SEC, COUNT, yv::kStackLocal, true, false, true>(r, p, 0)
+                                : launch_kernel<SEC, COUNT, yv::kStackLocal, false, false, true>(r, p, 0);
 }
 
 template <bool SEC, bool COUNT>
@@ -273,12 +282,32 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
   p.refill_threshold = r->opt_refill;
   p.shadow = r->shadow; p.ao_samples = r->ao_samples; p.seed = r->seed;
   p.voxel_size = r->voxel_size; p.ao_max_t = r->ao_max_t;
-  const size_t smem = (size_t)p.smem_nodes * sizeof(uint4) + yv::stack_smem_bytes(r->opt_stack);
+  const bool lod = r->detail_coef > 0.0f;
+  if (lod) {
+    if (!ds->node_data) {
+      const std::vector<uint32_t> &nd = r->svo->packed.node_data;
+      YV_CUDA(cudaMalloc(&ds->node_data, std::max<size_t>(1, nd.size()) * sizeof(uint32_t)));
+      if (!nd.empty()) YV_CUDA(cudaMemcpy(ds->node_data, nd.data(), nd.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    // rp.detailCoef = m_detailCoef * grad2rad(m_fov / 2) / m_viewSize.x   (demo/SVORenderer.cpp:104)
+    const float half_rad = (r->fov / 2) * (float)(3.14159265358979323846 / 180.0);
+    p.detail = (r->detail_coef * half_rad) / (float)r->width;
+    p.node_data = ds->node_data;
+    p.smem_nodes = 0;
+  }
+  const size_t smem = lod ? 0 : (size_t)p.smem_nodes * sizeof(uint4) + yv::stack_smem_bytes(r->opt_stack);
   if (smem > 227 * 1024) return fail(YV_ERR_ARG, "shared-memory request exceeds 227 KB (lower smem_nodes or change stack)");
 
   YV_CUDA(cudaEventRecord(r->ev0, r->stream));
   const int key = (sec ? 2 : 0) | (r->counters ? 1 : 0);
-  if (r->opt_persistent == 2 && !sec) {        // per-warp ray queue (primary rays)
+  if (lod) {
+    switch (key) {
+      case 0: rc = launch_lod<false, false>(r, p); break;
+      case 1: rc = launch_lod<false, true>(r, p); break;
+      case 2: rc = launch_lod<true, false>(r, p); break;
+      default: rc = launch_lod<true, true>(r, p); break;
+    }
+  } else if (r->opt_persistent == 2 && !sec) {        // per-warp ray queue (primary rays)
     if (r->opt_stack == yv::kStackRing4) rc = r->counters ? launch_queue<true, yv::kStackRing4>(r, p) : launch_queue<false, yv::kStackRing4>(r, p);
     else rc = r->counters ? launch_queue<true, yv::kStackLocal>(r, p) : launch_queue<false, yv::kStackLocal>(r, p);
   } else
@@ -339,6 +368,7 @@ void yv_svo_free(yv_svo *svo) {
     cudaSetDevice(kv.first);
     cudaFree(kv.second.recs);
     cudaFree(kv.second.leaves);
+    cudaFree(kv.second.node_data);
   }
   delete svo;
 }
@@ -387,7 +417,8 @@ uint64_t yv_svo_device_bytes(const yv_svo *svo, int device) {
   if (!svo) return 0;
   auto it = svo->dev.find(device);
   if (it == svo->dev.end()) return 0;
-  return (uint64_t)it->second.n_recs * 16u + (uint64_t)it->second.n_leaves * 4u;
+  return (uint64_t)it->second.n_recs * 16u + (uint64_t)it->second.n_leaves * 4u +
+         (it->second.node_data ? (uint64_t)it->second.n_recs * 4u : 0u);
 }
 
 int yv_svo_packed_counts(yv_svo *svo, uint32_t *records, uint32_t *leaves) {
@@ -510,6 +541,17 @@ int yv_get_resolution(const yv_renderer *r, int *width, int *height) {
 int yv_set_fov(yv_renderer *r, float fov_deg) {
   if (!r) return fail(YV_ERR_ARG, "null renderer");
   r->fov = fov_deg;
+  return YV_OK;
+}
+int yv_set_detail_coef(yv_renderer *r, float coef) {
+  if (!r) return fail(YV_ERR_ARG, "null renderer");
+  if (!(coef >= 0.0f)) return fail(YV_ERR_ARG, "detail coefficient must be >= 0");
+  r->detail_coef = coef;
+  return YV_OK;
+}
+int yv_get_detail_coef(const yv_renderer *r, float *coef) {
+  if (!r || !coef) return fail(YV_ERR_ARG, "null argument");
+  *coef = r->detail_coef;
   return YV_OK;
 }
 int yv_get_fov(const yv_renderer *r, float *fov_deg) {
