@@ -59,6 +59,29 @@ int yv_svo_build_single_sphere(int depth, int cx, int cy, int cz, int radius,
 int yv_svo_build_from_dense(int depth, const uint32_t *voxdata, yv_svo **out);
 uint32_t yv_pack_voxdata(uint8_t r, uint8_t g, uint8_t b, float nx, float ny, float nz);
 
+/* ---- editing: DynamicSVO + VoxelSource (ore/src/main.cpp:101-129; demo/Demo.cpp:82-114) ------------- */
+typedef struct yv_source yv_source;        /* VoxelSource (ore/src/main.cpp:106-117)                         */
+int yv_svo_create(yv_svo **out);                                         /* DynamicSVO() — empty scene        */
+int yv_source_sphere(int radius, uint8_t r, uint8_t g, uint8_t b, int inverted, yv_source **out);   /* MakeSphereSource (:69) */
+int yv_source_raw(const int size[3], const uint32_t *voxdata, yv_source **out);                      /* MakeRawSource (:37-52): VoxData words, x fastest, 0 = empty */
+int yv_source_iso(const int size[3], const uint8_t *data, int iso_level, int inside,
+                  uint8_t r, uint8_t g, uint8_t b, yv_source **out);     /* MakeIsoSource + SetIsoLevel/SetInside/SetColor (:54-67,112-116) */
+void yv_source_free(yv_source *src);
+int yv_source_size(const yv_source *src, int size[3], int pivot[3]);     /* GetSize / GetPivot (:107-108)     */
+/* DynamicSVO::BuildRange(level, pos, mode, src) (:121): merge the source, placed with its pivot at voxel `pos`
+ * of the 2^level grid, into the scene. mode 0 = BUILD_MODE_GROW (union), 1 = BUILD_MODE_CLEAR (subtraction;
+ * the source's surface voxels become the cavity wall — use an inverted sphere as demo/Demo.cpp:109 does). */
+int yv_svo_build_range(yv_svo *svo, int level, const int pos[3], int mode, const yv_source *src);
+uint32_t yv_svo_live_node_count(const yv_svo *svo);                      /* nodecount (:126), free-list excluded */
+int yv_svo_node_count_by_level(const yv_svo *svo, int *counts, int capacity);   /* GetNodeCountByLevel1 (:129) */
+/* page versions (256-node pages, reaction/report/main.tex:71) */
+uint32_t yv_svo_version(const yv_svo *svo);
+int yv_svo_count_changed_pages(const yv_svo *svo, uint32_t since_version);      /* CountChangedPages (:127)  */
+/* CudaSVO::Update for a scene under edit: copy only the pages written since the last call into the device's
+ * raw (reference-layout) mirror; *bytes_transferred = CountTransfrerSize (:128). Renderers with option
+ * "layout" = 1 read that mirror (and call this implicitly before every frame). */
+int yv_svo_update(yv_svo *svo, int device, uint64_t *bytes_transferred);
+
 /* CudaSVO::Update (demo/SVORenderer.cpp:33-53): repack the pool into the 16-byte GPU record
  * form and copy it to `device`. Implicit at the first render if not called. */
 int yv_svo_upload(yv_svo *svo, int device);
@@ -142,6 +165,8 @@ int yv_set_stream(yv_renderer *r, void *cuda_stream);
  *                 16x8 tile over its lanes; primary rays). "persistent" is an alias.
  *                 (with warp-level lane refill: ballot + popc compaction of finished rays)
  *   "refill"      persistent schedule: refill a warp once <= this many lanes are still traversing
+ *   "layout"      0 = packed 16-byte records (default; re-packed and re-uploaded in full after an edit),
+ *                 1 = the raw reference pool mirrored page by page (yv_svo_update) — for scenes under edit
  *   "stack"       where the traversal stack lives: 0 local memory, 4 = four-entry
  *                 shared-memory ring spilling to local memory */
 int yv_set_option(yv_renderer *r, const char *name, int value);

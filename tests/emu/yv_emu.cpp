@@ -14,7 +14,7 @@ namespace {
 float g_detail = 0.0f;   // rp.detailCoef; > 0 switches the LOD cut-off on (lean mode only)
 bool g_lod_hit = false;
 const uint32_t *g_node_data = nullptr;
-int g_mode = 2;   // 0 = trace_step, 1 = seek_child/enter_node, 2 = lean_step (what render_frame runs)
+int g_mode = 2;   // 0 = trace_step (classic form), 2 = lean_step (what render_frame runs)
 struct HostStack {
   StackEntry e[kMaxStack];
   int max_sp = 0;
@@ -33,6 +33,14 @@ struct HostFetch {
   mutable uint64_t fetches = 0, visits = 0;
   Rec operator()(uint32_t idx) const { ++fetches; ++visits; return recs[idx]; }
   Rec get(uint32_t idx, bool visit) const { ++fetches; if (visit) ++visits; return recs[idx]; }
+  // layout policy used by the lean form (packed pool)
+  void node(uint32_t idx, bool visit, uint32_t &masks, uint32_t &child_base) const {
+    const Rec r = get(idx, visit); masks = r.masks; child_base = r.child_base;
+  }
+  uint32_t child_index(uint32_t, uint32_t child_base, uint32_t masks, uint32_t c) const {
+    return child_base + (uint32_t)YV_POPC((masks >> 8) & ((1u << c) - 1u));
+  }
+  uint32_t root_index() const { return 0u; }
 };
 
 bool trace(const HostFetch &fetch, bool root_valid, HostStack &stk, float ox, float oy, float oz,
@@ -57,15 +65,6 @@ bool trace(const HostFetch &fetch, bool root_valid, HostStack &stk, float ox, fl
   }
   if (!setup_trace(ox, oy, oz, dx, dy, dz, s)) return false;
   if (!trace_enter_root(s, rec, fetch, root_valid)) return false;
-  if (g_mode == 1) {
-    SeekResult sk;
-    for (;;) {
-      ++steps;
-      const int need = seek_child(s, rec, front_only, sk);
-      if (need == kSeekHit) return true;
-      if (enter_node(s, rec, fetch, stk, need, sk) == kStepMiss) return false;
-    }
-  }
   for (;;) {
     ++steps;
     int r = trace_step(s, rec, fetch, stk, front_only);

@@ -14,7 +14,8 @@ import numpy as np
 
 __all__ = [
     "YVError", "lib", "lib_path", "SVOData", "SVORenderer", "CreateB200Renderer",
-    "pack_voxdata", "device_count", "init_ray_dir", "NODE_DTYPE", "EMPTY_NODE", "FULL_NODE",
+    "pack_voxdata", "device_count", "init_ray_dir", "BuildMode", "VoxelSource",
+    "MakeSphereSource", "MakeRawSource", "MakeIsoSource", "DynamicSVO", "NODE_DTYPE", "EMPTY_NODE", "FULL_NODE",
 ]
 
 EMPTY_NODE = 0x80000000
@@ -70,6 +71,18 @@ def lib():
         "yv_svo_build_single_sphere": (i32, [i32, i32, i32, i32, i32, C.c_uint8, C.c_uint8, C.c_uint8, P(vp)]),
         "yv_svo_build_from_dense": (i32, [i32, vp, P(vp)]),
         "yv_pack_voxdata": (u32, [C.c_uint8, C.c_uint8, C.c_uint8, f32, f32, f32]),
+        "yv_svo_create": (i32, [P(vp)]),
+        "yv_source_sphere": (i32, [i32, C.c_uint8, C.c_uint8, C.c_uint8, i32, P(vp)]),
+        "yv_source_raw": (i32, [P(i32), vp, P(vp)]),
+        "yv_source_iso": (i32, [P(i32), vp, i32, i32, C.c_uint8, C.c_uint8, C.c_uint8, P(vp)]),
+        "yv_source_free": (None, [vp]),
+        "yv_source_size": (i32, [vp, P(i32), P(i32)]),
+        "yv_svo_build_range": (i32, [vp, i32, P(i32), i32, vp]),
+        "yv_svo_live_node_count": (u32, [vp]),
+        "yv_svo_node_count_by_level": (i32, [vp, P(i32), i32]),
+        "yv_svo_version": (u32, [vp]),
+        "yv_svo_count_changed_pages": (i32, [vp, u32]),
+        "yv_svo_update": (i32, [vp, i32, P(C.c_uint64)]),
         "yv_svo_upload": (i32, [vp, i32]),
         "yv_svo_device_bytes": (C.c_uint64, [vp, i32]),
         "yv_svo_packed_counts": (i32, [vp, P(u32), P(u32)]),
@@ -148,11 +161,98 @@ def device_count():
     return int(lib().yv_device_count())
 
 
+class BuildMode:
+    """enum BuildMode (ore/src/main.cpp:101-103)"""
+    GROW = 0
+    CLEAR = 1
+
+
+class VoxelSource:
+    """VoxelSource handle (ore/src/main.cpp:106-117)."""
+
+    def __init__(self, handle, keepalive=None):
+        self._h = handle
+        self._keep = keepalive
+
+    def _sizes(self):
+        size, pivot = (C.c_int * 3)(), (C.c_int * 3)()
+        _check(lib().yv_source_size(self._h, size, pivot))
+        return tuple(size), tuple(pivot)
+
+    def GetSize(self):
+        return self._sizes()[0]
+
+    def GetPivot(self):
+        return self._sizes()[1]
+
+    def __del__(self):
+        try:
+            if self._h and self._h.value:
+                lib().yv_source_free(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+
+def MakeSphereSource(radius, color, inverted=False):          # ore/src/main.cpp:69
+    h = C.c_void_p()
+    _check(lib().yv_source_sphere(int(radius), int(color[0]), int(color[1]), int(color[2]), 1 if inverted else 0, C.byref(h)))
+    return VoxelSource(h)
+
+
+def MakeRawSource(voxdata):                                   # ore/src/main.cpp:37-52; array [z][y][x] of VoxData words
+    vox = np.ascontiguousarray(voxdata, dtype=np.uint32)
+    size = (C.c_int * 3)(vox.shape[2], vox.shape[1], vox.shape[0])
+    h = C.c_void_p()
+    _check(lib().yv_source_raw(size, vox.ctypes.data_as(C.c_void_p), C.byref(h)))
+    return VoxelSource(h)
+
+
+def MakeIsoSource(data, iso_level=128, inside=False, color=(200, 200, 200)):   # ore/src/main.cpp:54-67; uint8 [z][y][x]
+    d = np.ascontiguousarray(data, dtype=np.uint8)
+    size = (C.c_int * 3)(d.shape[2], d.shape[1], d.shape[0])
+    h = C.c_void_p()
+    _check(lib().yv_source_iso(size, d.ctypes.data_as(C.c_void_p), int(iso_level), 1 if inside else 0,
+                               int(color[0]), int(color[1]), int(color[2]), C.byref(h)))
+    return VoxelSource(h)
+
+
 class SVOData:
-    """SVOData (cell/svodata.h:22-55) plus the DynamicSVO surface the scene scripts use."""
+    """SVOData (cell/svodata.h:22-55) plus the DynamicSVO surface the scene scripts use
+    (ore/src/main.cpp:119-129: BuildRange, Save, Load, nodecount, CountChangedPages, ...)."""
 
     def __init__(self, handle=None):
         self._h = C.c_void_p(handle) if handle else C.c_void_p()
+        if not handle:
+            _check(lib().yv_svo_create(C.byref(self._h)))
+
+    # -- editing (DynamicSVO) ----------------------------------------------------------------
+    def BuildRange(self, level, pos, mode, src):          # ore/src/main.cpp:121
+        p = (C.c_int * 3)(int(pos[0]), int(pos[1]), int(pos[2]))
+        _check(lib().yv_svo_build_range(self._h, int(level), p, int(mode), src._h))
+
+    def GetNodeCountByLevel1(self):                       # ore/src/main.cpp:129
+        buf = (C.c_int * 40)()
+        n = lib().yv_svo_node_count_by_level(self._h, buf, 40)
+        return list(buf[:min(n, 40)])
+
+    @property
+    def version(self):
+        return int(lib().yv_svo_version(self._h))
+
+    def CountChangedPages(self, since_version=0):         # ore/src/main.cpp:127
+        return int(lib().yv_svo_count_changed_pages(self._h, int(since_version)))
+
+    def Update(self, device=0):
+        """CudaSVO::Update: ship the pages written since the last call; returns the bytes transferred
+        (CountTransfrerSize, ore/src/main.cpp:128)."""
+        b = C.c_uint64()
+        _check(lib().yv_svo_update(self._h, int(device), C.byref(b)))
+        return int(b.value)
+
+    @property
+    def livenodes(self):
+        return int(lib().yv_svo_live_node_count(self._h))
 
     # -- construction ------------------------------------------------------------------------
     def Load(self, fn):                                   # svodata.h:31
@@ -160,45 +260,51 @@ class SVOData:
         _check(lib().yv_svo_load(os.fsencode(fn), C.byref(self._h)))
         return self
 
+    @classmethod
+    def _adopt(cls, handle):
+        s = cls.__new__(cls)
+        s._h = handle
+        return s
+
     def Save(self, fn):                                   # ore/src/main.cpp:123
         _check(lib().yv_svo_save(self._h, os.fsencode(fn)))
 
     @classmethod
     def FromNodes(cls, root, nodes):
         nodes = np.ascontiguousarray(nodes, dtype=NODE_DTYPE)
-        s = cls()
-        _check(lib().yv_svo_from_memory(int(root), nodes.ctypes.data_as(C.c_void_p), len(nodes), C.byref(s._h)))
-        return s
+        h = C.c_void_p()
+        _check(lib().yv_svo_from_memory(int(root), nodes.ctypes.data_as(C.c_void_p), len(nodes), C.byref(h)))
+        return cls._adopt(h)
 
     @classmethod
     def SphereFractal(cls, depth, threads=0):             # gen_spheres.py
-        s = cls()
-        _check(lib().yv_svo_build_sphere_fractal(int(depth), int(threads or os.cpu_count() or 1), C.byref(s._h)))
-        return s
+        h = C.c_void_p()
+        _check(lib().yv_svo_build_sphere_fractal(int(depth), int(threads or os.cpu_count() or 1), C.byref(h)))
+        return cls._adopt(h)
 
     @classmethod
     def IsoVolume(cls, depth, seed=219, iso_level=200, threads=0):   # gen_largevol.py
-        s = cls()
+        h = C.c_void_p()
         _check(lib().yv_svo_build_iso_volume(int(depth), int(seed), int(iso_level),
-                                             int(threads or os.cpu_count() or 1), C.byref(s._h)))
-        return s
+                                             int(threads or os.cpu_count() or 1), C.byref(h)))
+        return cls._adopt(h)
 
     @classmethod
     def SingleSphere(cls, depth, center, radius, color=(128, 128, 255)):
-        s = cls()
+        h = C.c_void_p()
         _check(lib().yv_svo_build_single_sphere(int(depth), int(center[0]), int(center[1]), int(center[2]),
                                                 int(radius), int(color[0]), int(color[1]), int(color[2]),
-                                                C.byref(s._h)))
-        return s
+                                                C.byref(h)))
+        return cls._adopt(h)
 
     @classmethod
     def FromDense(cls, vox):
         vox = np.ascontiguousarray(vox, dtype=np.uint32)
         n = vox.shape[0]
         assert vox.shape == (n, n, n) and n & (n - 1) == 0, "dense grid must be a power-of-two cube [z][y][x]"
-        s = cls()
-        _check(lib().yv_svo_build_from_dense(int(n).bit_length() - 1, vox.ctypes.data_as(C.c_void_p), C.byref(s._h)))
-        return s
+        h = C.c_void_p()
+        _check(lib().yv_svo_build_from_dense(int(n).bit_length() - 1, vox.ctypes.data_as(C.c_void_p), C.byref(h)))
+        return cls._adopt(h)
 
     # -- accessors ---------------------------------------------------------------------------
     def GetRoot(self):                                    # svodata.h:52
@@ -387,6 +493,9 @@ class SVORenderer:
             self.close()
         except Exception:
             pass
+
+
+DynamicSVO = SVOData     # the scripts' name for the editable scene (ore/src/main.cpp:119)
 
 
 def CreateB200Renderer(device=0):

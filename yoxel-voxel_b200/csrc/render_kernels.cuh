@@ -34,6 +34,7 @@ struct RenderParams {
   const uint32_t *node_data;   // VoxNode::data per record (LOD hits only; NULL when detail == 0)
   float detail;                // rp.detailCoef (demo/SVORenderer.cpp:104); 0 = no LOD cut-off
   uint32_t root_valid;
+  uint32_t root_index;         // packed pool: 0; raw pool: the reference root id
   uint32_t smem_nodes;         // records staged in shared memory (<= record count)
   float pos[3];                // eye (m_pos) — also shader viewerPos (renderer_base.h:30-35)
   float dir0[3], du[3], dv[3]; // RayDirData (renderer_base.h:50-61), computed on the host
@@ -125,13 +126,18 @@ __host__ __device__ inline size_t stack_smem_bytes(int stack) {
   return stack == kStackRing4 ? 4 * 2 * sizeof(uint4) * kCtaThreads : 0;
 }
 
-// node fetch: shared memory for the staged top of the tree (STAGED), read-only global path otherwise
-template <bool COUNT, bool STAGED>
+// node fetch policy (see trace_core.cuh). RAW = false: packed 16-byte records, optionally with the top of
+// the tree staged in shared memory; RAW = true: the reference's 40-byte VoxNode pool as uploaded page by
+// page for scenes under edit (CudaSVO::Update, demo/SVORenderer.cpp:33-53): `recs` then points at the
+// pool viewed as uint32 words (flags, data, child[8]).
+template <bool COUNT, bool STAGED, bool RAW = false>
 struct NodeFetch {
   const uint4 *recs;
   const uint4 *staged;
   uint32_t staged_n;
+  uint32_t root;                 // index of the root node (0 for the packed pool)
   mutable uint32_t visits, revisits;
+  __device__ __forceinline__ const uint32_t *pool() const { return reinterpret_cast<const uint32_t *>(recs); }
   __device__ __forceinline__ Rec load(uint32_t idx) const {
     uint4 v;
     if (STAGED && idx < staged_n) v = staged[idx];
@@ -139,17 +145,42 @@ struct NodeFetch {
     Rec r = { v.x, v.y, v.z, v.w };
     return r;
   }
-  __device__ __forceinline__ Rec operator()(uint32_t idx) const { if (COUNT) ++visits; return load(idx); }
-  // one load instruction for both the descend (counted visit) and the pop (re-fetch) case
-  __device__ __forceinline__ Rec get(uint32_t idx, bool visit) const {
+  __device__ __forceinline__ Rec get(uint32_t idx, bool visit) const {      // classic form (trace_step)
     if (COUNT) { if (visit) ++visits; else ++revisits; }
     return load(idx);
   }
+  __device__ __forceinline__ uint32_t root_index() const { return root; }
+  // one node dereference: the two child masks (+ child base for the packed layout)
+  __device__ __forceinline__ void node(uint32_t idx, bool visit, uint32_t &masks, uint32_t &child_base) const {
+    if (COUNT) { if (visit) ++visits; else ++revisits; }
+    if (RAW) {
+      const uint32_t flags = __ldg(pool() + (size_t)idx * 10u);
+      const uint32_t leaf = flags & 0xffu;
+      masks = leaf | ((~(flags >> 8) & ~leaf & 0xffu) << 8);              // child = not leaf, not null
+      child_base = 0u;
+    } else {
+      const Rec r = load(idx);
+      masks = r.masks; child_base = r.child_base;
+    }
+  }
+  __device__ __forceinline__ uint32_t child_index(uint32_t idx, uint32_t child_base, uint32_t masks, uint32_t c) const {
+    if (RAW) return __ldg(pool() + (size_t)idx * 10u + 2u + c);
+    return child_base + (uint32_t)__popc((masks >> 8) & ((1u << c) - 1u));
+  }
+  // a finished ray: reference node id and the VoxData to shade (leaf slot c, or the node's own data for LOD)
+  __device__ __forceinline__ void hit_info(const uint32_t *leaves, const uint32_t *node_data, uint32_t idx, uint32_t c,
+                                           bool lod_hit, uint32_t &orig_id, uint32_t &data) const {
+    if (RAW) {
+      orig_id = idx;
+      data = __ldg(pool() + (size_t)idx * 10u + (lod_hit ? 1u : 2u + c));
+    } else {
+      const Rec r = load(idx);
+      orig_id = r.orig_id;
+      data = lod_hit ? __ldg(node_data + idx)
+                     : __ldg(leaves + r.leaf_base + (uint32_t)__popc(r.masks & 0xffu & ((1u << c) - 1u)));
+    }
+  }
 };
-
-__device__ __forceinline__ uint32_t leaf_data(const RenderParams &p, const Rec &rec, uint32_t c) {
-  return __ldg(p.leaves + rec.leaf_base + (uint32_t)__popc(rec.masks & 0xffu & ((1u << c) - 1u)));
-}
 
 // tile row (8 pixel rows) of this launch -> first pixel row, for contiguous and interleaved partitions
 __device__ __forceinline__ int tile_row_y(const RenderParams &p, int ty) {
@@ -159,7 +190,7 @@ __device__ __forceinline__ int tile_row_y(const RenderParams &p, int ty) {
 
 enum : int { kLaneIdle = 0, kLaneActive = 1, kLaneHit = 2, kLaneMiss = 3, kLaneNew = 4, kLaneLodHit = 5 };
 
-template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED, bool LOD>
+template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED, bool LOD, bool RAW>
 __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_frame(const __grid_constant__ RenderParams p) {
   extern __shared__ uint4 smem[];
   uint4 *staged = smem;
@@ -171,7 +202,7 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_frame(const 
 
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  NodeFetch<COUNT, STAGED> fetch = { p.recs, staged, p.smem_nodes, 0u, 0u };
+  NodeFetch<COUNT, STAGED, RAW> fetch = { p.recs, staged, p.smem_nodes, p.root_index, 0u, 0u };
   typename StackOf<STACK>::type stk(stack_area);
   LeanState s;
 
@@ -263,10 +294,9 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_frame(const 
       if (!SEC || stage == 0) {
         uint32_t hn = YV_MISS_NODE; int32_t hc = YV_MISS_CHILD; float ht = 0.0f;
         if (hit) {
-          const Rec rec = fetch.load(s.idx);                      // re-read the hit node's record
           const uint32_t c = s.ch ^ s.flags;
-          hn = rec.orig_id; hc = lod_hit ? -1 : (int32_t)c; ht = max3f(s.t1x, s.t1y, s.t1z);
-          sdata = lod_hit ? __ldg(p.node_data + s.idx) : leaf_data(p, rec, c);
+          fetch.hit_info(p.leaves, p.node_data, s.idx, c, lod_hit, hn, sdata);   // re-reads the hit node
+          hc = lod_hit ? -1 : (int32_t)c; ht = max3f(s.t1x, s.t1y, s.t1z);
           unpack_normal(sdata, nx, ny, nz);
           float dx, dy, dz;                                       // the primary direction, recomputed
           primary_dir(p.dir0, p.du, p.dv, x, y, dx, dy, dz);
@@ -374,7 +404,7 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_queue(const 
   const int tx = blockIdx.x % tiles_x32, ty = blockIdx.x / tiles_x32;
   const int wx0 = tx * 32 + (warp & 1) * 16, wy0 = tile_row_y(p, ty * 2 + (warp >> 1));
 
-  NodeFetch<COUNT, false> fetch = { p.recs, nullptr, 0u, 0u, 0u };
+  NodeFetch<COUNT, false> fetch = { p.recs, nullptr, 0u, 0u, 0u, 0u };
   typename StackOf<STACK>::type stk(stack_area);
   LeanState s;
   const bool root_valid = p.root_valid != 0u;
@@ -461,11 +491,11 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_queue(const 
     const uint32_t idx = slots[0 * kQueueRays + slot];
     uint32_t rgba = 0u, hn = YV_MISS_NODE; int32_t hc = YV_MISS_CHILD; float ht = 0.0f;
     if (idx != 0xffffffffu) {
-      const Rec rec = fetch.load(idx);
       const uint32_t c = slots[1 * kQueueRays + slot];
       ht = __uint_as_float(slots[2 * kQueueRays + slot]);
-      hn = rec.orig_id; hc = (int32_t)c;
-      const uint32_t data = leaf_data(p, rec, c);
+      hc = (int32_t)c;
+      uint32_t data;
+      fetch.hit_info(p.leaves, p.node_data, idx, c, false, hn, data);
       float nx, ny, nz, dx, dy, dz;
       unpack_normal(data, nx, ny, nz);
       primary_dir(p.dir0, p.du, p.dv, x, y, dx, dy, dz);
@@ -485,25 +515,27 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_queue(const 
 // ---------------------------------------------------------------------------------------------
 // arbitrary rays (DynamicSVO::TraceRay, ore/src/main.cpp:125)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) trace_rays_kernel(const uint4 *recs, uint32_t root_valid,
+template <bool RAW>
+__global__ void __launch_bounds__(128) trace_rays_kernel(const uint4 *recs, const uint32_t *leaves, uint32_t root_valid, uint32_t root_index,
                                                          const float *pos, const float *dir, uint32_t count,
                                                          uint32_t *node, int32_t *child, float *t) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  NodeFetch<false, false> fetch = { recs, nullptr, 0u, 0u, 0u };
+  NodeFetch<false, false, RAW> fetch = { recs, nullptr, 0u, root_index, 0u, 0u };
   LocalStack stk(nullptr);
-  RayState s; Rec rec;
-  float dx = adjust_dir1(dir[3 * i]), dy = adjust_dir1(dir[3 * i + 1]), dz = adjust_dir1(dir[3 * i + 2]);
+  LeanState s;
+  const float dx = adjust_dir1(dir[3 * i]), dy = adjust_dir1(dir[3 * i + 1]), dz = adjust_dir1(dir[3 * i + 2]);
   bool hit = false;
-  if (setup_trace(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], dx, dy, dz, s) &&
-      trace_enter_root(s, rec, fetch, root_valid != 0u)) {
+  if (lean_begin(s, fetch, root_valid != 0u, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], dx, dy, dz)) {
     for (;;) {
-      const int r = trace_step(s, rec, fetch, stk, false);
+      const int r = lean_step<false>(s, fetch, stk, false);
       if (r == kStepHit) { hit = true; break; }
       if (r == kStepMiss) break;
     }
   }
-  node[i] = hit ? rec.orig_id : YV_MISS_NODE;
+  uint32_t hn = YV_MISS_NODE, data;
+  if (hit) fetch.hit_info(leaves, nullptr, s.idx, s.ch ^ s.flags, false, hn, data);
+  node[i] = hn;
   child[i] = hit ? (int32_t)(s.ch ^ s.flags) : YV_MISS_CHILD;
   t[i] = hit ? max3f(s.t1x, s.t1y, s.t1z) : 0.0f;
 }

@@ -160,68 +160,6 @@ YV_HD int trace_step(RayState &s, Rec &rec, const Fetch &fetch, Stack &stk, cons
   return kStepContinue;
 }
 
-// ---- phase-split form of the same loop (what the kernels run) ------------------------------------
-// A warp executes the union of its lanes' paths, so the kernels split a node visit into two phases
-// and re-converge between them:
-//   seek_child : cheap, register-only. Walk the current node's children in ray order (leaf test,
-//                entry test, GoNext) until the ray hits a leaf, finds a child node to enter, or
-//                runs out of siblings. At most 4 iterations.
-//   enter_node : the expensive part every live lane needs next — push+descend or pop, ONE node fetch,
-//                FindFirstChild.
-// seek_child followed by enter_node is exactly trace_step iterated until it fetches (or ends).
-enum : int { kSeekHit = 1, kSeekDescend = 2, kSeekPop = 3 };
-
-struct SeekResult {
-  StackEntry resume;   // parent's state after GoNext (valid when can_adv)
-  bool can_adv;
-};
-
-YV_HD int seek_child(RayState &s, const Rec &rec, const bool front_only, SeekResult &out) {
-  for (;;) {
-    const uint32_t c = s.ch ^ s.flags;
-    const uint32_t bit = 1u << c;
-    const float t2min = min3f(s.t2x, s.t2y, s.t2z);
-    const bool leaf = ((rec.masks & bit) != 0u) && (!front_only || t2min > 0.0f);             // :27
-    const bool descend = (((rec.masks >> 8) & bit) != 0u) && (t2min > 0.0f);                   // :20,:35
-    const uint32_t e = (s.t2x > s.t2y) ? ((s.t2y < s.t2z) ? 1u : 2u) : ((s.t2x < s.t2z) ? 0u : 2u);
-    const bool can_adv = (s.ch & (1u << e)) == 0u;                                             // :38
-    const float a = e == 0u ? s.t1x : (e == 1u ? s.t1y : s.t1z);
-    const float b = e == 0u ? s.t2x : (e == 1u ? s.t2y : s.t2z);
-    const float nb = YV_FADD(b, YV_FSUB(b, a));
-    const float n1x = e == 0u ? b : s.t1x, n1y = e == 1u ? b : s.t1y, n1z = e == 2u ? b : s.t1z;
-    const float n2x = e == 0u ? nb : s.t2x, n2y = e == 1u ? nb : s.t2y, n2z = e == 2u ? nb : s.t2z;
-    const uint32_t nch = s.ch ^ (1u << e);
-    if (leaf) return kSeekHit;
-    if (descend || !can_adv) {
-      out.resume.t1x = n1x; out.resume.t1y = n1y; out.resume.t1z = n1z; out.resume.idx = s.idx;
-      out.resume.t2x = n2x; out.resume.t2y = n2y; out.resume.t2z = n2z; out.resume.ch = nch;
-      out.can_adv = can_adv;
-      return descend ? kSeekDescend : kSeekPop;
-    }
-    s.t1x = n1x; s.t1y = n1y; s.t1z = n1z; s.t2x = n2x; s.t2y = n2y; s.t2z = n2z; s.ch = nch;
-  }
-}
-
-// returns kStepContinue, or kStepMiss when a pop finds the stack empty
-template <class Fetch, class Stack>
-YV_HD int enter_node(RayState &s, Rec &rec, const Fetch &fetch, Stack &stk, const int need, const SeekResult &sk) {
-  const bool descend = need == kSeekDescend;
-  if (descend) {
-    if (sk.can_adv) { stk.push(s.sp, sk.resume); ++s.sp; }
-    const uint32_t bit = 1u << (s.ch ^ s.flags);
-    s.idx = rec.child_base + (uint32_t)YV_POPC((rec.masks >> 8) & (bit - 1u));
-  } else {
-    if (s.sp == 0) return kStepMiss;
-    --s.sp;
-    const StackEntry en = stk.pop(s.sp);
-    s.t1x = en.t1x; s.t1y = en.t1y; s.t1z = en.t1z; s.t2x = en.t2x; s.t2y = en.t2y; s.t2z = en.t2z;
-    s.idx = en.idx; s.ch = en.ch;
-  }
-  rec = fetch.get(s.idx, descend);                                                             // :23
-  if (descend) find_first_child(s);                                                            // :24
-  return kStepContinue;
-}
-
 // ---- lean form (what render_frame runs) ----------------------------------------------------------
 // Same decisions and the same float operations as trace_step, arranged for instruction count:
 //   * the exit parameter an axis takes when it is stepped, N = t2 + (t2 - t1) (GoNext,
@@ -285,10 +223,15 @@ YV_HD void lean_first_child(LeanState &s) {
   s.ch = (fx ? 1u : 0u) | (fy ? 2u : 0u) | (fz ? 4u : 0u);
 }
 
+// The Fetch policy hides the node-pool layout:
+//   fetch.node(idx, visit, masks, child_base)  one node dereference -> leaf|child masks (+ child base)
+//   fetch.child_index(idx, child_base, masks, c)  index of existing child c
+//   fetch.root_index()
+// packed pool (svo_pack.h): one 16-byte record, children contiguous; raw pool (the reference's 40-byte
+// VoxNode array, used for scenes that are being edited): flags word, then the child slot itself.
 template <class Fetch>
 YV_HD void lean_load_node(LeanState &s, const Fetch &fetch, const bool visit) {
-  const Rec r = fetch.get(s.idx, visit);
-  s.masks = r.masks; s.child_base = r.child_base;
+  fetch.node(s.idx, visit, s.masks, s.child_base);
 }
 
 // SetupTrace + RecTrace's entry test on the root + FindFirstChild in the root (needs no node data).
@@ -308,6 +251,7 @@ template <class Fetch>
 YV_HD bool lean_begin(LeanState &s, const Fetch &fetch, const bool root_valid,
                       float px, float py, float pz, float dx, float dy, float dz) {
   if (!lean_setup_root(s, root_valid, px, py, pz, dx, dy, dz)) return false;
+  s.idx = fetch.root_index();
   lean_load_node(s, fetch, true);
   lean_eval_next(s);
   return true;
@@ -353,7 +297,7 @@ YV_HD int lean_step(LeanState &s, const Fetch &fetch, Stack &stk, const bool fro
       const float tent = fmaxf(fmaxf(s.t1x, s.t1y), s.t1z);
       const float lodk = YV_U2F(YV_F2U(detail) + ((s.level + 1u) << 23));
       if (descend && tent > 0.0f && YV_FMUL(tent, lodk) > 1.0f) {
-        s.idx = s.child_base + (uint32_t)YV_POPC((s.masks >> 8) & (bit - 1u));
+        s.idx = fetch.child_index(s.idx, s.child_base, s.masks, s.ch ^ s.flags);
         return kStepLodHit;
       }
     }
@@ -369,7 +313,7 @@ YV_HD int lean_step(LeanState &s, const Fetch &fetch, Stack &stk, const bool fro
       stk.push(s.sp, a, b);
       ++s.sp;
     }
-    s.idx = s.child_base + (uint32_t)YV_POPC((s.masks >> 8) & (bit - 1u));
+    s.idx = fetch.child_index(s.idx, s.child_base, s.masks, s.ch ^ s.flags);
     if (LOD) ++s.level;
   } else {
     if (s.sp == 0) return kStepMiss;

@@ -15,6 +15,7 @@
 
 #include "../../include/yv_b200.h"
 #include "render_kernels.cuh"
+#include "dynamic_svo.h"
 #include "svo_host.h"
 #include "svo_pack.h"
 
@@ -36,14 +37,21 @@ struct DeviceSVO {
   uint32_t *leaves = nullptr;
   uint32_t *node_data = nullptr;      // uploaded on first use of the LOD cut-off
   size_t n_recs = 0, n_leaves = 0;
+  uint32_t packed_version = 0;        // scene edit version the packed copy was made from
+  // raw mirror of the reference-layout pool, kept in step page by page (CudaSVO::Update)
+  yv_vox_node *raw = nullptr;
+  size_t raw_capacity = 0;            // nodes
+  uint32_t raw_version = 0;           // every page with a version <= this is on the device
 };
 
 }  // namespace
 
 struct yv_svo {
   yv::HostSVO host;
+  yv::DynamicSVO dyn{ host };         // editing state (free list, page versions) over `host`
   yv::PackedSVO packed;
   bool packed_ok = false;
+  uint32_t packed_version = 0;
   std::map<int, DeviceSVO> dev;
   std::mutex mu;
 };
@@ -81,18 +89,59 @@ struct yv_renderer {
   int opt_smem_nodes = 0;             // records staged in shared memory (585 = four levels)
   int opt_persistent = 0;
   int opt_refill = 20;                // persistent schedule: refill when <= this many lanes are live
+  int opt_layout = 0;                 // 0 = packed records (static scenes), 1 = raw reference pool (scenes under edit)
   int opt_stack = 0;                  // yv::kStackLocal / kStackRing4
 };
 
 namespace {
 
 int ensure_packed(yv_svo *svo) {
-  if (svo->packed_ok) return YV_OK;
+  if (svo->packed_ok && svo->packed_version == svo->dyn.version()) return YV_OK;
   std::string err;
   if (yv::pack_svo(svo->host, svo->packed, err) != 0) return fail(YV_ERR_FORMAT, err);
   if ((int)svo->packed.level_start.size() - 1 > yv::kMaxStack + 1)
     return fail(YV_ERR_FORMAT, "tree deeper than the traversal stack supports");
   svo->packed_ok = true;
+  svo->packed_version = svo->dyn.version();
+  return YV_OK;
+}
+
+void free_packed_device(DeviceSVO &d) {
+  cudaFree(d.recs); cudaFree(d.leaves); cudaFree(d.node_data);
+  d.recs = nullptr; d.leaves = nullptr; d.node_data = nullptr; d.n_recs = d.n_leaves = 0;
+}
+
+// CudaSVO::Update (demo/SVORenderer.cpp:33-53; paging: reaction/report/main.tex:71): bring the device's raw
+// mirror of the pool up to date by copying only the 256-node pages written since the last call.
+int sync_raw(yv_svo *svo, int device, DeviceSVO **out, uint64_t *bytes_out) {
+  std::lock_guard<std::mutex> lock(svo->mu);
+  YV_CUDA(cudaSetDevice(device));
+  DeviceSVO &d = svo->dev[device];
+  if (svo->dyn.page_versions().empty() && !svo->host.nodes.empty()) svo->dyn.adopt_existing();
+  const size_t n = svo->host.nodes.size();
+  uint64_t bytes = 0;
+  if (n > d.raw_capacity) {                       // (re)allocate with slack, then everything is dirty
+    cudaFree(d.raw); d.raw = nullptr;
+    d.raw_capacity = std::max<size_t>(n + n / 2, 1u << 16);
+    YV_CUDA(cudaMalloc(&d.raw, d.raw_capacity * sizeof(yv_vox_node)));
+    d.raw_version = 0;
+  }
+  const std::vector<uint32_t> &pv = svo->dyn.page_versions();
+  size_t page = 0;
+  while (page < pv.size()) {
+    if (pv[page] <= d.raw_version) { ++page; continue; }
+    size_t end = page;
+    while (end < pv.size() && pv[end] > d.raw_version) ++end;          // one copy per run of dirty pages
+    const size_t first = page * yv::kPageNodes, last = std::min(n, end * yv::kPageNodes);
+    if (last > first) {
+      YV_CUDA(cudaMemcpy(d.raw + first, svo->host.nodes.data() + first, (last - first) * sizeof(yv_vox_node), cudaMemcpyHostToDevice));
+      bytes += (last - first) * sizeof(yv_vox_node);
+    }
+    page = end;
+  }
+  d.raw_version = svo->dyn.version();
+  if (out) *out = &d;
+  if (bytes_out) *bytes_out = bytes;
   return YV_OK;
 }
 
@@ -101,9 +150,12 @@ int ensure_uploaded(yv_svo *svo, int device, DeviceSVO **out) {
   int rc = ensure_packed(svo);
   if (rc) return rc;
   auto it = svo->dev.find(device);
-  if (it == svo->dev.end()) {
+  if (it != svo->dev.end() && it->second.recs && it->second.packed_version != svo->packed_version)
+    free_packed_device(it->second);               // the scene was edited since this copy was made
+  if (it == svo->dev.end() || !it->second.recs) {
     YV_CUDA(cudaSetDevice(device));
-    DeviceSVO d;
+    DeviceSVO d = it == svo->dev.end() ? DeviceSVO() : it->second;
+    d.packed_version = svo->packed_version;
     d.n_recs = svo->packed.records.size();
     d.n_leaves = svo->packed.leaves.size();
     YV_CUDA(cudaMalloc(&d.recs, std::max<size_t>(1, d.n_recs) * sizeof(uint4)));
@@ -112,7 +164,8 @@ int ensure_uploaded(yv_svo *svo, int device, DeviceSVO **out) {
       YV_CUDA(cudaMemcpy(d.recs, svo->packed.records.data(), d.n_recs * sizeof(uint4), cudaMemcpyHostToDevice));
     if (d.n_leaves)
       YV_CUDA(cudaMemcpy(d.leaves, svo->packed.leaves.data(), d.n_leaves * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    it = svo->dev.emplace(device, d).first;
+    svo->dev[device] = d;
+    it = svo->dev.find(device);
   }
   if (out) *out = &it->second;
   return YV_OK;
@@ -180,9 +233,9 @@ void init_ray_dir(const yv_renderer *r, float dir0[3], float du[3], float dv[3])
   init_ray_dir_raw(r->dir, r->up, r->fov, r->width, r->height, dir0, du, dv);
 }
 
-template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED, bool LOD = false>
+template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED, bool LOD = false, bool RAW = false>
 int launch_kernel(yv_renderer *r, const yv::RenderParams &p, size_t smem) {
-  auto kern = yv::render_frame<SEC, COUNT, STACK, PERSISTENT, STAGED, LOD>;
+  auto kern = yv::render_frame<SEC, COUNT, STACK, PERSISTENT, STAGED, LOD, RAW>;
   YV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long grid;
   if (PERSISTENT) {
@@ -225,6 +278,12 @@ int launch_schedule(yv_renderer *r, const yv::RenderParams &p, size_t smem) {
                            : launch_staged<SEC, COUNT, STACK, false>(r, p, smem);
 }
 
+// raw (reference-layout) pool: tiles schedule, local-memory stack
+template <bool SEC, bool COUNT, bool LOD>
+int launch_raw(yv_renderer *r, const yv::RenderParams &p) {
+  return launch_kernel<SEC, COUNT, yv::kStackLocal, false, false, LOD, true>(r, p, 0);
+}
+
 // LOD variants exist for the local-memory stack without staging (the defaults)
 template <bool SEC, bool COUNT>
 int launch_lod(yv_renderer *r, const yv::RenderParams &p) {
@@ -242,7 +301,8 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
   if (!r->svo) return fail(YV_ERR_NOSCENE, "no scene set");
   if (r->width <= 0 || r->height <= 0) return fail(YV_ERR_ARG, "resolution not set");
   DeviceSVO *ds = nullptr;
-  int rc = ensure_uploaded(r->svo, r->device, &ds);
+  const bool raw = r->opt_layout == 1;
+  int rc = raw ? sync_raw(r->svo, r->device, &ds, nullptr) : ensure_uploaded(r->svo, r->device, &ds);
   if (rc) return rc;
   rc = ensure_frame_buffers(r);
   if (rc) return rc;
@@ -250,9 +310,15 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
 
   yv::RenderParams p;
   std::memset(&p, 0, sizeof p);
-  p.recs = ds->recs; p.leaves = ds->leaves;
-  p.root_valid = r->svo->packed.root_null ? 0u : 1u;
-  p.smem_nodes = (uint32_t)std::min<size_t>((size_t)std::max(0, r->opt_smem_nodes), ds->n_recs);
+  if (raw) {
+    p.recs = reinterpret_cast<const uint4 *>(ds->raw);
+    p.root_valid = YV_IS_NULL(r->svo->host.root) ? 0u : 1u;
+    p.root_index = p.root_valid ? r->svo->host.root : 0u;
+  } else {
+    p.recs = ds->recs; p.leaves = ds->leaves;
+    p.root_valid = r->svo->packed.root_null ? 0u : 1u;
+  }
+  p.smem_nodes = raw ? 0u : (uint32_t)std::min<size_t>((size_t)std::max(0, r->opt_smem_nodes), ds->n_recs);
   for (int i = 0; i < 3; ++i) p.pos[i] = r->pos[i];
   init_ray_dir(r, p.dir0, p.du, p.dv);
   const bool sec = r->shadow || r->ao_samples > 0;
@@ -284,7 +350,7 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
   p.voxel_size = r->voxel_size; p.ao_max_t = r->ao_max_t;
   const bool lod = r->detail_coef > 0.0f;
   if (lod) {
-    if (!ds->node_data) {
+    if (!raw && !ds->node_data) {
       const std::vector<uint32_t> &nd = r->svo->packed.node_data;
       YV_CUDA(cudaMalloc(&ds->node_data, std::max<size_t>(1, nd.size()) * sizeof(uint32_t)));
       if (!nd.empty()) YV_CUDA(cudaMemcpy(ds->node_data, nd.data(), nd.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -295,12 +361,23 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
     p.node_data = ds->node_data;
     p.smem_nodes = 0;
   }
-  const size_t smem = lod ? 0 : (size_t)p.smem_nodes * sizeof(uint4) + yv::stack_smem_bytes(r->opt_stack);
+  const size_t smem = (lod || raw) ? 0 : (size_t)p.smem_nodes * sizeof(uint4) + yv::stack_smem_bytes(r->opt_stack);
   if (smem > 227 * 1024) return fail(YV_ERR_ARG, "shared-memory request exceeds 227 KB (lower smem_nodes or change stack)");
 
   YV_CUDA(cudaEventRecord(r->ev0, r->stream));
   const int key = (sec ? 2 : 0) | (r->counters ? 1 : 0);
-  if (lod) {
+  if (raw) {
+    switch (key | (lod ? 4 : 0)) {
+      case 0: rc = launch_raw<false, false, false>(r, p); break;
+      case 1: rc = launch_raw<false, true, false>(r, p); break;
+      case 2: rc = launch_raw<true, false, false>(r, p); break;
+      case 3: rc = launch_raw<true, true, false>(r, p); break;
+      case 4: rc = launch_raw<false, false, true>(r, p); break;
+      case 5: rc = launch_raw<false, true, true>(r, p); break;
+      case 6: rc = launch_raw<true, false, true>(r, p); break;
+      default: rc = launch_raw<true, true, true>(r, p); break;
+    }
+  } else if (lod) {
     switch (key) {
       case 0: rc = launch_lod<false, false>(r, p); break;
       case 1: rc = launch_lod<false, true>(r, p); break;
@@ -369,6 +446,7 @@ void yv_svo_free(yv_svo *svo) {
     cudaFree(kv.second.recs);
     cudaFree(kv.second.leaves);
     cudaFree(kv.second.node_data);
+    cudaFree(kv.second.raw);
   }
   delete svo;
 }
@@ -689,6 +767,7 @@ int yv_set_option(yv_renderer *r, const char *name, int value) {
     if (value < 0 || value > 2) return fail(YV_ERR_ARG, "schedule must be 0 (tiles), 1 (persistent) or 2 (queue)");
     r->opt_persistent = value;
   }
+  else if (n == "layout") { if (value != 0 && value != 1) return fail(YV_ERR_ARG, "layout must be 0 (packed) or 1 (raw)"); r->opt_layout = value; }
   else if (n == "refill") { if (value < 0 || value > 31) return fail(YV_ERR_ARG, "refill must be 0..31"); r->opt_refill = value; }
   else if (n == "stack") {
     if (value != yv::kStackLocal && value != yv::kStackRing4)
@@ -704,6 +783,7 @@ int yv_get_option(const yv_renderer *r, const char *name, int *value) {
   std::string n(name);
   if (n == "smem_nodes") *value = r->opt_smem_nodes;
   else if (n == "persistent" || n == "schedule") *value = r->opt_persistent;
+  else if (n == "layout") *value = r->opt_layout;
   else if (n == "refill") *value = r->opt_refill;
   else if (n == "stack") *value = r->opt_stack;
   else return fail(YV_ERR_ARG, "unknown option " + n);
@@ -716,7 +796,8 @@ int yv_trace_rays(yv_renderer *r, const float *pos, const float *dir, uint32_t c
   if (!r->svo) return fail(YV_ERR_NOSCENE, "no scene set");
   if (count == 0) return YV_OK;
   DeviceSVO *ds = nullptr;
-  int rc = ensure_uploaded(r->svo, r->device, &ds);
+  const bool raw = r->opt_layout == 1;
+  int rc = raw ? sync_raw(r->svo, r->device, &ds, nullptr) : ensure_uploaded(r->svo, r->device, &ds);
   if (rc) return rc;
   YV_CUDA(cudaSetDevice(r->device));
   float *d_pos = nullptr, *d_dir = nullptr, *d_t = nullptr; uint32_t *d_node = nullptr; int32_t *d_child = nullptr;
@@ -729,8 +810,15 @@ int yv_trace_rays(yv_renderer *r, const float *pos, const float *dir, uint32_t c
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_pos, pos, n * 12, cudaMemcpyHostToDevice, r->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_dir, dir, n * 12, cudaMemcpyHostToDevice, r->stream);
   if (e == cudaSuccess) {
-    yv::trace_rays_kernel<<<(unsigned)((n + 127) / 128), 128, 0, r->stream>>>(
-        ds->recs, r->svo->packed.root_null ? 0u : 1u, d_pos, d_dir, count, d_node, d_child, d_t);
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    if (raw) {
+      const uint32_t valid = YV_IS_NULL(r->svo->host.root) ? 0u : 1u;
+      yv::trace_rays_kernel<true><<<grid, 128, 0, r->stream>>>(reinterpret_cast<const uint4 *>(ds->raw), nullptr, valid,
+                                                               valid ? r->svo->host.root : 0u, d_pos, d_dir, count, d_node, d_child, d_t);
+    } else {
+      yv::trace_rays_kernel<false><<<grid, 128, 0, r->stream>>>(ds->recs, ds->leaves, r->svo->packed.root_null ? 0u : 1u, 0u,
+                                                                d_pos, d_dir, count, d_node, d_child, d_t);
+    }
     e = cudaGetLastError();
   }
   if (e == cudaSuccess && node) e = cudaMemcpyAsync(node, d_node, n * 4, cudaMemcpyDeviceToHost, r->stream);
@@ -740,6 +828,66 @@ int yv_trace_rays(yv_renderer *r, const float *pos, const float *dir, uint32_t c
   cudaFree(d_pos); cudaFree(d_dir); cudaFree(d_node); cudaFree(d_child); cudaFree(d_t);
   if (e != cudaSuccess) return fail(YV_ERR_CUDA, cudaGetErrorString(e));
   return YV_OK;
+}
+
+// ---- DynamicSVO editing (ore/src/main.cpp:101-129) ------------------------------------------------------
+struct yv_source { yv::VoxelSource *src; };
+
+int yv_svo_create(yv_svo **out) {
+  if (!out) return fail(YV_ERR_ARG, "null argument");
+  *out = new yv_svo;
+  return YV_OK;
+}
+
+int yv_source_sphere(int radius, uint8_t r, uint8_t g, uint8_t b, int inverted, yv_source **out) {
+  if (!out || radius < 0) return fail(YV_ERR_ARG, "bad argument");
+  *out = new yv_source{ new yv::SphereSource(radius, r, g, b, inverted != 0) };
+  return YV_OK;
+}
+int yv_source_raw(const int size[3], const uint32_t *voxdata, yv_source **out) {
+  if (!out || !size || !voxdata || size[0] < 1 || size[1] < 1 || size[2] < 1) return fail(YV_ERR_ARG, "bad argument");
+  *out = new yv_source{ new yv::RawSource(size, voxdata) };
+  return YV_OK;
+}
+int yv_source_iso(const int size[3], const uint8_t *data, int iso_level, int inside, uint8_t r, uint8_t g, uint8_t b, yv_source **out) {
+  if (!out || !size || !data || size[0] < 1 || size[1] < 1 || size[2] < 1) return fail(YV_ERR_ARG, "bad argument");
+  yv::IsoBrickSource *s = new yv::IsoBrickSource(size, data);
+  s->SetIsoLevel(iso_level); s->SetInside(inside != 0); s->SetColor(r, g, b);
+  *out = new yv_source{ s };
+  return YV_OK;
+}
+void yv_source_free(yv_source *src) { if (src) { delete src->src; delete src; } }
+int yv_source_size(const yv_source *src, int size[3], int pivot[3]) {
+  if (!src) return fail(YV_ERR_ARG, "null source");
+  if (size) src->src->GetSize(size);
+  if (pivot) src->src->GetPivot(pivot);
+  return YV_OK;
+}
+
+int yv_svo_build_range(yv_svo *svo, int level, const int pos[3], int mode, const yv_source *src) {
+  if (!svo || !pos || !src) return fail(YV_ERR_ARG, "null argument");
+  if (mode != 0 && mode != 1) return fail(YV_ERR_ARG, "mode must be 0 (GROW) or 1 (CLEAR)");
+  std::lock_guard<std::mutex> lock(svo->mu);
+  std::string err;
+  if (svo->dyn.BuildRange(level, pos, mode ? yv::BuildMode::Clear : yv::BuildMode::Grow, *src->src, err))
+    return fail(YV_ERR_ARG, err);
+  return YV_OK;
+}
+
+uint32_t yv_svo_live_node_count(const yv_svo *svo) { return svo ? svo->dyn.GetNodeCount() : 0u; }
+int yv_svo_node_count_by_level(const yv_svo *svo, int *counts, int capacity) {
+  if (!svo) return 0;
+  const std::vector<int> c = svo->dyn.GetNodeCountByLevel();
+  for (int i = 0; i < (int)c.size() && i < capacity && counts; ++i) counts[i] = c[i];
+  return (int)c.size();
+}
+uint32_t yv_svo_version(const yv_svo *svo) { return svo ? svo->dyn.version() : 0u; }
+int yv_svo_count_changed_pages(const yv_svo *svo, uint32_t since_version) {
+  return svo ? svo->dyn.CountChangedPages(since_version) : 0;
+}
+int yv_svo_update(yv_svo *svo, int device, uint64_t *bytes_transferred) {
+  if (!svo) return fail(YV_ERR_ARG, "null scene");
+  return sync_raw(svo, device, nullptr, bytes_transferred);
 }
 
 int yv_device_alloc(int device, size_t bytes, void **d_ptr) {
