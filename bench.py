@@ -483,7 +483,7 @@ def main():
                    "gather": gather, "flythrough": bool(a.flythrough), "hit_fraction": round(hit_frac, 4)},
         "frame_ms": 1e3 * total_s / a.steps, "rays_per_step": rays_step,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
-        "gpu_launches": a.steps * world, "parity": parity,
+        "gpu_launches": a.steps * world, "e2e_gpu_launches_per_step": r.LastFrameLaunches(), "parity": parity,
     }
     print(json.dumps(line))
     if world > 1:

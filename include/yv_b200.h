@@ -146,6 +146,10 @@ int yv_set_secondary(yv_renderer *r, int shadow, int ao_samples, uint32_t seed,
  * arrays of width*height entries (any pointer may be NULL). */
 int yv_enable_hits(yv_renderer *r, int enable);
 int yv_get_hits(yv_renderer *r, uint32_t *node, int32_t *child, float *t);
+/* SVORenderer::DumpTraceData(fnbase) (demo/SVORenderer.cpp:158-192): writes <fnbase>_<W>x<H>.dist (f32 hit
+ * distance), .color (RGBA8 unpacked voxel colour) and .normal (3 x f32 unpacked normal) for the last frame.
+ * Needs yv_enable_hits. (The reference's .dist is zero-filled because its assignment is commented out.) */
+int yv_dump_trace_data(yv_renderer *r, const char *fnbase);
 /* optional per-ray counters (node fetches incl. re-fetches after a pop) for profiling */
 int yv_enable_counters(yv_renderer *r, int enable);
 int yv_get_counters(yv_renderer *r, uint32_t *fetches_per_ray);
@@ -165,6 +169,9 @@ int yv_set_stream(yv_renderer *r, void *cuda_stream);
  *                 16x8 tile over its lanes; primary rays). "persistent" is an alias.
  *                 (with warp-level lane refill: ballot + popc compaction of finished rays)
  *   "refill"      persistent schedule: refill a warp once <= this many lanes are still traversing
+ *   "pipeline"    number of row chunks (2..8, default 4) yv_render_frame cuts the frame into: chunks render on
+ *                 two alternating streams and each chunk's device->host copy overlaps the next chunk's kernel;
+ *                 0 or 1 = one launch, then one copy
  *   "layout"      0 = packed 16-byte records (default; re-packed and re-uploaded in full after an edit),
  *                 1 = the raw reference pool mirrored page by page (yv_svo_update) — for scenes under edit
  *   "stack"       where the traversal stack lives: 0 local memory, 4 = four-entry

@@ -267,6 +267,15 @@ def test_device_pointer_render_and_timing(renderer):
     renderer.Render(buf.data_ptr())
     assert (buf.cpu().numpy() == img).all()
     assert 0 < renderer.LastFrameMs() < 1000 and renderer.LastFrameLaunches() == 1
+    # RenderFrame pipelines 8 row chunks with their D2H copies; the pixels are the same either way
+    renderer.SetOption("pipeline", 8)
+    a = renderer.RenderFrame().copy()
+    assert renderer.LastFrameLaunches() == 8 and 0 < renderer.LastFrameMs() < 1000
+    renderer.SetOption("pipeline", 0)
+    b = renderer.RenderFrame().copy()
+    assert renderer.LastFrameLaunches() == 1
+    renderer.SetOption("pipeline", 8)
+    assert (a == img).all() and (b == img).all()
     # on torch's current stream
     renderer.SetStream(torch.cuda.current_stream().cuda_stream)
     buf.zero_()
@@ -316,3 +325,28 @@ def test_cpp_adapter_renders_like_cell_main(tmp_path):
     img = np.frombuffer(raw[len(hdr):], np.uint8).reshape(768, 1024, 3)
     o = _render_cpu(svo, ("m", (0.5, 0.5, 0.3), (-1, -1, 1.5), (0, 0, 1), 70.0), 1024, 768)
     assert (img == o["rgba"][:, :, :3]).all()
+
+
+def test_dump_trace_data(renderer, tmp_path):
+    """SVORenderer::DumpTraceData (demo/SVORenderer.cpp:158-192): .dist / .color / .normal of the last frame."""
+    svo = scenes.fractal(9)
+    renderer.SetOption("schedule", 0)
+    renderer.SetScene(svo)
+    cam = scenes.CAMERAS[1]
+    img, node, child, t = _render_gpu(renderer, cam, 200, 120, detail=8.0)
+    base = str(tmp_path / "dmp_0")
+    renderer.DumpTraceData(base)
+    dist = np.fromfile(base + "_200x120.dist", np.float32).reshape(120, 200)
+    color = np.fromfile(base + "_200x120.color", np.uint8).reshape(120, 200, 4)
+    normal = np.fromfile(base + "_200x120.normal", np.float32).reshape(120, 200, 3)
+    assert dist.tobytes() == t.tobytes()
+    hit = node != yvo.MISS_NODE
+    assert (color[~hit] == 0).all() and (normal[~hit] == 0).all() and (color[hit][:, 3] == 255).all()
+    nodes = svo.nodes()
+    ys, xs = np.nonzero(hit)
+    for y, x in list(zip(ys, xs))[::37]:
+        d = nodes["data"][node[y, x]] if child[y, x] < 0 else nodes["child"][node[y, x], child[y, x]]
+        assert np.allclose(normal[y, x], yvo.unpack_normal(int(d)), atol=1e-6)
+        r5, g6, b5 = (d >> 11) & 31, (d >> 5) & 63, d & 31
+        assert tuple(color[y, x][:3]) == ((r5 << 3) | (r5 >> 2), (g6 << 2) | (g6 >> 4), (b5 << 3) | (b5 >> 2))
+    renderer.SetDetailCoef(0.0)

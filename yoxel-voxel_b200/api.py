@@ -109,6 +109,7 @@ def lib():
         "yv_set_secondary": (i32, [vp, i32, i32, u32, P(f32), f32, f32]),
         "yv_enable_hits": (i32, [vp, i32]),
         "yv_get_hits": (i32, [vp, vp, vp, vp]),
+        "yv_dump_trace_data": (i32, [vp, C.c_char_p]),
         "yv_enable_counters": (i32, [vp, i32]),
         "yv_get_counters": (i32, [vp, vp]),
         "yv_last_frame_ms": (f32, [vp]),
@@ -443,6 +444,9 @@ class SVORenderer:
         _check(lib().yv_get_hits(self._h, node.ctypes.data_as(C.c_void_p), child.ctypes.data_as(C.c_void_p),
                                  t.ctypes.data_as(C.c_void_p)))
         return node.reshape(h, w), child.reshape(h, w), t.reshape(h, w)
+
+    def DumpTraceData(self, fnbase):                      # demo/SVORenderer.cpp:158
+        _check(lib().yv_dump_trace_data(self._h, os.fsencode(fnbase)))
 
     def EnableCounters(self, on=True):
         _check(lib().yv_enable_counters(self._h, 1 if on else 0))

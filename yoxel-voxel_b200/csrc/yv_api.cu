@@ -83,6 +83,12 @@ struct yv_renderer {
   // launch
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // RenderFrame pipelining: row chunks rendered on two alternating streams, each chunk's D2H copy overlapped
+  static constexpr int kChunks = 8;
+  cudaStream_t aux[2] = { nullptr, nullptr }, copy_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_chunk[kChunks] = {}, ev_copy = nullptr;
+  bool suppress_events = false;
+  int opt_pipeline = 4;               // row chunks per RenderFrame (0/1 = no pipelining); 4 measured best at 1080p
   bool timed = false;
   int launches = 0;
   // options
@@ -236,7 +242,7 @@ void init_ray_dir(const yv_renderer *r, float dir0[3], float du[3], float dv[3])
 template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED, bool LOD = false, bool RAW = false>
 int launch_kernel(yv_renderer *r, const yv::RenderParams &p, size_t smem) {
   auto kern = yv::render_frame<SEC, COUNT, STACK, PERSISTENT, STAGED, LOD, RAW>;
-  YV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024) YV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long grid;
   if (PERSISTENT) {
     int per_sm = 0;
@@ -364,7 +370,7 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
   const size_t smem = (lod || raw) ? 0 : (size_t)p.smem_nodes * sizeof(uint4) + yv::stack_smem_bytes(r->opt_stack);
   if (smem > 227 * 1024) return fail(YV_ERR_ARG, "shared-memory request exceeds 227 KB (lower smem_nodes or change stack)");
 
-  YV_CUDA(cudaEventRecord(r->ev0, r->stream));
+  if (!r->suppress_events) YV_CUDA(cudaEventRecord(r->ev0, r->stream));
   const int key = (sec ? 2 : 0) | (r->counters ? 1 : 0);
   if (raw) {
     switch (key | (lod ? 4 : 0)) {
@@ -395,9 +401,50 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
     default: rc = launch_stack<true, true>(r, p, smem); break;
   }
   if (rc) return rc;
-  YV_CUDA(cudaEventRecord(r->ev1, r->stream));
+  if (!r->suppress_events) {
+    YV_CUDA(cudaEventRecord(r->ev1, r->stream));
+    r->timed = true;
+    r->launches = 1;
+  }
+  return YV_OK;
+}
+
+// RenderFrame with the device->host copy overlapped: the frame is cut into row chunks, chunk k renders on
+// aux[k & 1] (so the tail wave of one chunk overlaps the head of the next) and its rows start travelling to the
+// pinned host buffer as soon as its kernel is done. One kernel launch per chunk.
+int render_frame_pipelined(yv_renderer *r) {
+  const int H = r->height, W = r->width;
+  const int chunks = std::min(std::max(r->opt_pipeline, 2), (int)yv_renderer::kChunks);
+  int rows = ((H + chunks - 1) / chunks + 7) / 8 * 8;
+  cudaStream_t main_stream = r->stream;
+  YV_CUDA(cudaEventRecord(r->ev0, main_stream));
+  YV_CUDA(cudaEventRecord(r->ev_fork, main_stream));
+  for (int i = 0; i < 2; ++i) YV_CUDA(cudaStreamWaitEvent(r->aux[i], r->ev_fork, 0));
+  int rc = YV_OK, launched = 0;
+  r->suppress_events = true;
+  for (int k = 0, y0 = 0; y0 < H && rc == YV_OK; ++k, y0 += rows) {
+    const int y1 = std::min(H, y0 + rows);
+    r->rows_set = true; r->y0 = y0; r->y1 = y1;
+    r->stream = r->aux[k & 1];
+    rc = launch_frame(r, r->d_fb);
+    if (rc == YV_OK) {
+      cudaEventRecord(r->ev_chunk[k], r->stream);
+      cudaStreamWaitEvent(r->copy_stream, r->ev_chunk[k], 0);
+      const size_t off = (size_t)y0 * W * 4, bytes = (size_t)(y1 - y0) * W * 4;
+      cudaMemcpyAsync(r->h_fb + off, (const uint8_t *)r->d_fb + off, bytes, cudaMemcpyDeviceToHost, r->copy_stream);
+      ++launched;
+    }
+  }
+  r->suppress_events = false;
+  r->rows_set = false;
+  r->stream = main_stream;
+  if (rc) { cudaDeviceSynchronize(); return rc; }
+  YV_CUDA(cudaEventRecord(r->ev_copy, r->copy_stream));
+  YV_CUDA(cudaStreamWaitEvent(main_stream, r->ev_copy, 0));
+  YV_CUDA(cudaEventRecord(r->ev1, main_stream));
   r->timed = true;
-  r->launches = 1;
+  r->launches = launched;
+  YV_CUDA(cudaStreamSynchronize(main_stream));
   return YV_OK;
 }
 
@@ -560,6 +607,11 @@ int yv_renderer_create(int device, yv_renderer **out) {
   if (e == cudaSuccess) e = cudaEventCreate(&r->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&r->ev1);
   if (e == cudaSuccess) e = cudaMalloc(&r->d_tile_counter, sizeof(unsigned int));
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&r->aux[i], cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_copy, cudaEventDisableTiming);
+  for (int i = 0; i < yv_renderer::kChunks && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&r->ev_chunk[i], cudaEventDisableTiming);
   if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); yv_renderer_destroy(r); return fail(YV_ERR_CUDA, m); }
   r->stream = r->own_stream;
   r->width = 640; r->height = 480;            // renderer_base.h:25
@@ -575,6 +627,11 @@ void yv_renderer_destroy(yv_renderer *r) {
   cudaFree(r->d_tile_counter);
   if (r->ev0) cudaEventDestroy(r->ev0);
   if (r->ev1) cudaEventDestroy(r->ev1);
+  if (r->ev_fork) cudaEventDestroy(r->ev_fork);
+  if (r->ev_copy) cudaEventDestroy(r->ev_copy);
+  for (int i = 0; i < yv_renderer::kChunks; ++i) if (r->ev_chunk[i]) cudaEventDestroy(r->ev_chunk[i]);
+  for (int i = 0; i < 2; ++i) if (r->aux[i]) cudaStreamDestroy(r->aux[i]);
+  if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
   if (r->own_stream) cudaStreamDestroy(r->own_stream);
   delete r;
 }
@@ -708,6 +765,12 @@ int yv_render_frame(yv_renderer *r, const uint8_t **rgba) {
   if (!r->svo) return fail(YV_ERR_NOSCENE, "no scene set");
   int rc = ensure_frame_buffers(r);
   if (rc) return rc;
+  if (r->opt_pipeline > 1 && !r->rows_set && r->il_stride == 1 && r->opt_persistent != 1 && r->height >= 256) {
+    rc = render_frame_pipelined(r);
+    if (rc) return rc;
+    *rgba = r->h_fb;
+    return YV_OK;
+  }
   rc = launch_frame(r, r->d_fb);
   if (rc) return rc;
   const int y0 = r->rows_set ? std::max(0, r->y0) : 0;
@@ -742,6 +805,43 @@ int yv_get_counters(yv_renderer *r, uint32_t *fetches_per_ray) {
   return YV_OK;
 }
 
+// SVORenderer::DumpTraceData (demo/SVORenderer.cpp:158-192): <base>_<W>x<H>.dist / .color / .normal
+int yv_dump_trace_data(yv_renderer *r, const char *fnbase) {
+  if (!r || !fnbase) return fail(YV_ERR_ARG, "null argument");
+  if (!r->svo) return fail(YV_ERR_NOSCENE, "no scene set");
+  const size_t n = r->fb_pixels;
+  std::vector<uint32_t> node(n); std::vector<int32_t> child(n); std::vector<float> dist(n);
+  int rc = yv_get_hits(r, node.data(), child.data(), dist.data());
+  if (rc) return rc;
+  std::vector<uint8_t> color(n * 4, 0); std::vector<float> normal(n * 3, 0.0f);
+  const std::vector<yv_vox_node> &pool = r->svo->host.nodes;
+  for (size_t i = 0; i < n; ++i) {
+    if (YV_IS_NULL(node[i]) || node[i] >= pool.size()) continue;                       // :171
+    const yv_vox_node &nd = pool[node[i]];
+    const uint32_t d = child[i] < 0 ? nd.data : nd.child[child[i] & 7];                // :176-179
+    const uint32_t r5 = (d >> 11) & 31u, g6 = (d >> 5) & 63u, b5 = d & 31u;            // UnpackColor
+    color[4 * i] = (uint8_t)((r5 << 3) | (r5 >> 2)); color[4 * i + 1] = (uint8_t)((g6 << 2) | (g6 >> 4));
+    color[4 * i + 2] = (uint8_t)((b5 << 3) | (b5 >> 2)); color[4 * i + 3] = 255;
+    float fx = (float)((d >> 16) & 255u) / 127.5f - 1.0f, fy = (float)((d >> 24) & 255u) / 127.5f - 1.0f;   // UnpackNormal
+    float fz = (1.0f - fabsf(fx)) - fabsf(fy);
+    if (fz < 0) { const float ox = (1.0f - fabsf(fy)) * (fx >= 0 ? 1.0f : -1.0f), oy = (1.0f - fabsf(fx)) * (fy >= 0 ? 1.0f : -1.0f); fx = ox; fy = oy; }
+    const float len = sqrtf((fx * fx + fy * fy) + fz * fz);
+    normal[3 * i] = fx / len; normal[3 * i + 1] = fy / len; normal[3 * i + 2] = fz / len;
+  }
+  const std::string base = std::string(fnbase) + "_" + std::to_string(r->width) + "x" + std::to_string(r->height);   // :188
+  auto write = [&](const std::string &fn, const void *data, size_t bytes) {
+    FILE *f = std::fopen(fn.c_str(), "wb");
+    if (!f) return false;
+    const bool ok = std::fwrite(data, 1, bytes, f) == bytes;
+    return (std::fclose(f) == 0) && ok;
+  };
+  // the reference leaves .dist zero-filled (its `distBuf[i] = rd.t` is commented out, :168); the hit distance is written here
+  if (!write(base + ".dist", dist.data(), n * 4) || !write(base + ".color", color.data(), n * 4) ||
+      !write(base + ".normal", normal.data(), n * 12))
+    return fail(YV_ERR_IO, "cannot write trace dump " + base);
+  return YV_OK;
+}
+
 float yv_last_frame_ms(const yv_renderer *r) {
   if (!r || !r->timed) return -1.0f;
   cudaSetDevice(r->device);
@@ -767,6 +867,7 @@ int yv_set_option(yv_renderer *r, const char *name, int value) {
     if (value < 0 || value > 2) return fail(YV_ERR_ARG, "schedule must be 0 (tiles), 1 (persistent) or 2 (queue)");
     r->opt_persistent = value;
   }
+  else if (n == "pipeline") { if (value < 0 || value > yv_renderer::kChunks) return fail(YV_ERR_ARG, "pipeline must be 0..8 chunks"); r->opt_pipeline = value; }
   else if (n == "layout") { if (value != 0 && value != 1) return fail(YV_ERR_ARG, "layout must be 0 (packed) or 1 (raw)"); r->opt_layout = value; }
   else if (n == "refill") { if (value < 0 || value > 31) return fail(YV_ERR_ARG, "refill must be 0..31"); r->opt_refill = value; }
   else if (n == "stack") {
@@ -783,6 +884,7 @@ int yv_get_option(const yv_renderer *r, const char *name, int *value) {
   std::string n(name);
   if (n == "smem_nodes") *value = r->opt_smem_nodes;
   else if (n == "persistent" || n == "schedule") *value = r->opt_persistent;
+  else if (n == "pipeline") *value = r->opt_pipeline;
   else if (n == "layout") *value = r->opt_layout;
   else if (n == "refill") *value = r->opt_refill;
   else if (n == "stack") *value = r->opt_stack;
