@@ -286,7 +286,9 @@ def main():
         target_bytes = frame_bytes
     else:
         y0, y1 = 0, a.height
-        my_frame, my_rays_px = rank, a.width * a.height
+        # weak scaling: every GPU renders one whole frame of the same workload (the base camera), or, with
+        # --flythrough, frame step*N+rank of the camera path
+        my_frame, my_rays_px = (rank if a.flythrough else 0), a.width * a.height
         target_bytes = frame_bytes * world
     pos, d = camera_for(my_frame)
     r.SetViewPos(pos); r.SetViewDir(d)

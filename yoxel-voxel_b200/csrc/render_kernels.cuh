@@ -79,17 +79,6 @@ struct LocalStack {
   __device__ __forceinline__ void reset() {}
   __device__ __forceinline__ void push(int sp, const U4 &a, const U4 &b) { w[2 * sp] = to_uint4(a); w[2 * sp + 1] = to_uint4(b); }
   __device__ __forceinline__ void pop(int sp, U4 &a, U4 &b) { a = to_u4(w[2 * sp]); b = to_u4(w[2 * sp + 1]); }
-  // classic StackEntry interface (trace_step, used by trace_rays_kernel)
-  __device__ __forceinline__ void push(int sp, const StackEntry &e) {
-    w[2 * sp]     = make_uint4(__float_as_uint(e.t1x), __float_as_uint(e.t1y), __float_as_uint(e.t1z), e.idx);
-    w[2 * sp + 1] = make_uint4(__float_as_uint(e.t2x), __float_as_uint(e.t2y), __float_as_uint(e.t2z), e.ch);
-  }
-  __device__ __forceinline__ StackEntry pop(int sp) {
-    const uint4 a = w[2 * sp], b = w[2 * sp + 1];
-    StackEntry e = { __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), a.w,
-                     __uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), b.w };
-    return e;
-  }
 };
 
 // the K most recent entries in shared memory ([slot][half][thread]: a warp's 128-bit accesses never
