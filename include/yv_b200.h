@@ -112,6 +112,14 @@ int yv_get_fov(const yv_renderer *r, float *fov_deg);          /* GetFOV (demo/S
  * (rp.detailCoef, demo/SVORenderer.cpp:104) is not descended into: it is the hit, reported with child = -1
  * and shaded with its sub-tree average VoxNode::data (demo/SVORenderer.cpp:176-179). 0 (default) = off. */
 int yv_set_detail_coef(yv_renderer *r, float coef);
+/* SetLigth(i, LightParams) (demo/SVORenderer.h:34; demo/Demo.cpp:141-167): point lights of the CUDA renderer's
+ * ShadeSimple. While any light is enabled, primary-ray frames are shaded with the Phong model written down in
+ * yv_format.h (ambient 0.1, specular exponent 10, attenuation 1/(a0 + a1 d + a2 d^2)) instead of the head-light
+ * Lambert of the CPU tracer. index 0..YV_MAX_LIGHTS-1. Secondary-ray frames keep the Lambert model. */
+int yv_set_light(yv_renderer *r, int index, const yv_light *light);
+/* SetShowNormals / GetShowNormals (demo/SVORenderer.h:31-32): write the unpacked normal as the colour */
+int yv_set_show_normals(yv_renderer *r, int enable);
+int yv_get_show_normals(const yv_renderer *r, int *enable);
 int yv_get_detail_coef(const yv_renderer *r, float *coef);
 
 /* const Color32* RenderFrame()  (cell/svorenderer.h:23): synchronous; *rgba aliases

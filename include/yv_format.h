@@ -101,6 +101,29 @@ typedef struct yv_vox_node {
 #define YV_SHADE_AMBIENT 0.1f
 #define YV_SHADE_DIFFUSE 0.9f
 
+/* ShadeSimple with point lights (the CUDA renderer's shader: rp.ambient = 0.1, rp.specularExp = 10,
+ * demo/SVORenderer.cpp:112-113; LightParams{enabled,pos,diffuse,specular,attenuationCoefs}, demo/Demo.cpp:141-147;
+ * kernel body absent). Restated as Phong, float32, no FMA, in this order, per enabled light i (index order), with
+ * c = the voxel colour channel as a float in 0..255, n = unpacked normal, P = viewer + dir*t:
+ *   V   = (viewer - P) / |viewer - P|                     (zero vector if the length is 0)
+ *   Lv  = pos_i - P ; d = sqrt((Lv.x*Lv.x + Lv.y*Lv.y) + Lv.z*Lv.z) ; L = Lv / d   (skip the light if d == 0)
+ *   att = 1 / ((a0 + a1*d) + (a2*d)*d)
+ *   nl  = (n.x*L.x + n.y*L.y) + n.z*L.z ; ndl = nl > 0 ? nl : 0
+ *   R   = (2*nl)*n - L ; rv = (R.x*V.x + R.y*V.y) + R.z*V.z ; rv = (nl > 0 && rv > 0) ? rv : 0
+ *   s2 = rv*rv ; s4 = s2*s2 ; s8 = s4*s4 ; spec = s8*s2            (rv^10)
+ *   acc_ch += att * ((diffuse_i.ch * ndl) * c_ch + (specular_i.ch * spec) * 255)
+ * starting from acc_ch = YV_SHADE_AMBIENT * c_ch; out_ch = (uint8) min(255, floorf(acc_ch + 0.5f)); alpha 255.
+ * SetShowNormals (demo/SVORenderer.h:31): out_ch = (uint8) floorf((n_ch * 0.5f + 0.5f) * 255.0f + 0.5f).      */
+#define YV_MAX_LIGHTS 4
+#define YV_SPECULAR_EXP 10
+typedef struct yv_light {            /* LightParams (demo/Demo.cpp:141-147) */
+  int32_t enabled;
+  float pos[3];
+  float diffuse[3];
+  float specular[3];
+  float attenuation[3];              /* constant, linear, quadratic */
+} yv_light;
+
 #ifdef __cplusplus
 }
 #endif

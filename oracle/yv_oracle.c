@@ -228,6 +228,49 @@ void yvo_shade(yv_vox_data data, const float dir[3], float t,
   write_color(data, k, out);
 }
 
+/* ShadeSimple with point lights / SetShowNormals, restated from the spec in include/yv_format.h
+ * (parameters: demo/SVORenderer.cpp:112-113, demo/Demo.cpp:141-147; kernel body absent) */
+static void shade_phong(yv_vox_data data, const float n[3], v3 P, v3 viewer, const yv_light *lights, uint8_t out[4]) {
+  uint32_t ci[3];
+  unpack_color(data, ci);
+  float c[3] = { (float)ci[0], (float)ci[1], (float)ci[2] };
+  float acc[3] = { YV_SHADE_AMBIENT * c[0], YV_SHADE_AMBIENT * c[1], YV_SHADE_AMBIENT * c[2] };
+  v3 V = v3_sub(viewer, P);
+  float vl = sqrtf((V.x * V.x + V.y * V.y) + V.z * V.z);
+  if (vl > 0) { V.x /= vl; V.y /= vl; V.z /= vl; } else { V.x = V.y = V.z = 0; }
+  for (int i = 0; i < YV_MAX_LIGHTS; ++i) {
+    const yv_light *lt = &lights[i];
+    if (!lt->enabled) continue;
+    v3 Lv = { lt->pos[0] - P.x, lt->pos[1] - P.y, lt->pos[2] - P.z };
+    float d = sqrtf((Lv.x * Lv.x + Lv.y * Lv.y) + Lv.z * Lv.z);
+    if (!(d > 0)) continue;
+    v3 L = { Lv.x / d, Lv.y / d, Lv.z / d };
+    float att = 1.0f / ((lt->attenuation[0] + lt->attenuation[1] * d) + (lt->attenuation[2] * d) * d);
+    float nl = (n[0] * L.x + n[1] * L.y) + n[2] * L.z;
+    float ndl = nl > 0 ? nl : 0.0f;
+    float k2 = 2.0f * nl;
+    v3 R = { k2 * n[0] - L.x, k2 * n[1] - L.y, k2 * n[2] - L.z };
+    float rv = (R.x * V.x + R.y * V.y) + R.z * V.z;
+    rv = (nl > 0 && rv > 0) ? rv : 0.0f;
+    float s2 = rv * rv, s4 = s2 * s2, s8 = s4 * s4, spec = s8 * s2;
+    for (int ch = 0; ch < 3; ++ch)
+      acc[ch] = acc[ch] + att * ((lt->diffuse[ch] * ndl) * c[ch] + (lt->specular[ch] * spec) * 255.0f);
+  }
+  for (int ch = 0; ch < 3; ++ch) {
+    float v = floorf(acc[ch] + 0.5f);
+    out[ch] = (uint8_t)(v < 255.0f ? (v > 0.0f ? v : 0.0f) : 255.0f);
+  }
+  out[3] = 255;
+}
+
+static void shade_normal(const float n[3], uint8_t out[4]) {
+  for (int ch = 0; ch < 3; ++ch) {
+    float v = floorf((n[ch] * 0.5f + 0.5f) * 255.0f + 0.5f);
+    out[ch] = (uint8_t)(v < 255.0f ? (v > 0.0f ? v : 0.0f) : 255.0f);
+  }
+  out[3] = 255;
+}
+
 /* ---- secondary rays (BASELINE config 4; our definition, mirrored by the kernel) ---------- */
 
 static inline uint32_t hash_u32(uint32_t x) {           /* lowbias32 */
@@ -296,7 +339,15 @@ static void *render_strip(void *arg) {
         j->stats.hits++;
         yv_vox_data data = hc < 0 ? j->nodes[hn].data : j->nodes[hn].child[hc];   /* :67; LOD: node.data */
         float dd[3] = { d.x, d.y, d.z };
-        if (!want_sec) {
+        int any_light = 0;
+        for (int li = 0; li < YV_MAX_LIGHTS; ++li) any_light |= j->cam->lights[li].enabled;
+        if (!want_sec && (j->cam->show_normals || any_light)) {
+          float n[3];
+          yvo_unpack_normal(data, n);
+          v3 P = { pos.x + d.x * ht, pos.y + d.y * ht, pos.z + d.z * ht };
+          if (j->cam->show_normals) shade_normal(n, px);
+          else shade_phong(data, n, P, pos, j->cam->lights, px);
+        } else if (!want_sec) {
           yvo_shade(data, dd, ht, j->cam->pos, j->cam->pos, 1.0f, px);       /* light = eye (:33-34) */
         } else {
           float n[3];

@@ -28,6 +28,8 @@ typedef struct yvo_camera {
   int32_t width;
   int32_t height;
   float detail_coef;  /* SVORenderer::SetDetailCoef (demo/SVORenderer.h:25); 0 = no LOD cut-off   */
+  int32_t show_normals;             /* SetShowNormals (demo/SVORenderer.h:31)                     */
+  yv_light lights[YV_MAX_LIGHTS];   /* SetLigth (demo/SVORenderer.h:34): any enabled light -> Phong */
 } yvo_camera;
 
 /* RayDirData{dir0,du,dv} (cell/renderer_base.h:50-61) */

@@ -350,3 +350,32 @@ def test_dump_trace_data(renderer, tmp_path):
         r5, g6, b5 = (d >> 11) & 31, (d >> 5) & 63, d & 31
         assert tuple(color[y, x][:3]) == ((r5 << 3) | (r5 >> 2), (g6 << 2) | (g6 >> 4), (b5 << 3) | (b5 >> 2))
     renderer.SetDetailCoef(0.0)
+
+
+@pytest.mark.parametrize("schedule", [0, 2], ids=["tiles", "queue"])
+def test_phong_lights_and_show_normals(renderer, schedule):
+    """SetLigth / SetShowNormals (demo/SVORenderer.h:31-34): ShadeSimple's point-light Phong model."""
+    svo = scenes.fractal(10)
+    renderer.SetOption("schedule", schedule)
+    renderer.SetScene(svo)
+    cam = scenes.CAMERAS[1]
+    lights = [dict(pos=cam[1], diffuse=(0.7, 0.7, 0.7), specular=(0.3, 0.3, 0.3), attenuation=(1, 0, 0.5)),       # Demo.cpp:141-147
+              dict(pos=(0.45, 0.4, 0.55), diffuse=(1, 0.8, 0.6), specular=(0.3, 0.3, 0.3), attenuation=(1, 10, 400))]   # Demo.cpp:160-165
+    for i, lt in enumerate(lights):
+        renderer.SetLigth(i, yv.LightParams(True, lt["pos"], lt["diffuse"], lt["specular"], lt["attenuation"]))
+    img, node, child, t = _render_gpu(renderer, cam, 480, 320)
+    o = yvo.render(svo.nodes(), svo.GetRoot(), yvo.camera(cam[1], cam[2], cam[3], cam[4], 480, 320, lights=lights), threads=8)
+    _check(o, img, node, child, t, "phong")
+    lambert = _render_cpu(svo, cam, 480, 320)
+    assert (o["rgba"] != lambert["rgba"]).any()
+    renderer.SetShowNormals(True)
+    assert renderer.GetShowNormals()
+    img, node, child, t = _render_gpu(renderer, cam, 480, 320)
+    o = yvo.render(svo.nodes(), svo.GetRoot(), yvo.camera(cam[1], cam[2], cam[3], cam[4], 480, 320, show_normals=True), threads=8)
+    _check(o, img, node, child, t, "normals")
+    renderer.SetShowNormals(False)
+    for i in range(2):
+        renderer.SetLigth(i, yv.LightParams(False))
+    renderer.SetOption("schedule", 0)
+    img, *_ = _render_gpu(renderer, cam, 480, 320)
+    assert (img == lambert["rgba"]).all()

@@ -10,9 +10,15 @@ NODE_DTYPE = np.dtype([("flags", "<u4"), ("data", "<u4"), ("child", "<u4", (8,))
 MISS_NODE = 0x80000000
 
 
+class Light(C.Structure):
+    _fields_ = [("enabled", C.c_int32), ("pos", C.c_float * 3), ("diffuse", C.c_float * 3),
+                ("specular", C.c_float * 3), ("attenuation", C.c_float * 3)]
+
+
 class Camera(C.Structure):
     _fields_ = [("pos", C.c_float * 3), ("dir", C.c_float * 3), ("up", C.c_float * 3),
-                ("fov_deg", C.c_float), ("width", C.c_int32), ("height", C.c_int32), ("detail_coef", C.c_float)]
+                ("fov_deg", C.c_float), ("width", C.c_int32), ("height", C.c_int32), ("detail_coef", C.c_float),
+                ("show_normals", C.c_int32), ("lights", Light * 4)]
 
 
 class RayDir(C.Structure):
@@ -62,7 +68,7 @@ def lib():
     return _lib
 
 
-def camera(pos, dir, up=(0, 0, 1), fov=70.0, width=64, height=64, detail_coef=0.0):
+def camera(pos, dir, up=(0, 0, 1), fov=70.0, width=64, height=64, detail_coef=0.0, lights=None, show_normals=False):
     c = Camera()
     c.pos[:] = [float(v) for v in pos]
     c.dir[:] = [float(v) for v in dir]
@@ -71,6 +77,13 @@ def camera(pos, dir, up=(0, 0, 1), fov=70.0, width=64, height=64, detail_coef=0.
     c.width = int(width)
     c.height = int(height)
     c.detail_coef = float(detail_coef)
+    c.show_normals = 1 if show_normals else 0
+    for i, lt in enumerate(lights or []):       # dicts: pos, diffuse, specular, attenuation (enabled implied)
+        c.lights[i].enabled = 1 if lt.get("enabled", True) else 0
+        c.lights[i].pos[:] = [float(v) for v in lt["pos"]]
+        c.lights[i].diffuse[:] = [float(v) for v in lt.get("diffuse", (0.7, 0.7, 0.7))]
+        c.lights[i].specular[:] = [float(v) for v in lt.get("specular", (0.3, 0.3, 0.3))]
+        c.lights[i].attenuation[:] = [float(v) for v in lt.get("attenuation", (1, 0, 0.5))]
     return c
 
 

@@ -15,7 +15,7 @@ import numpy as np
 __all__ = [
     "YVError", "lib", "lib_path", "SVOData", "SVORenderer", "CreateB200Renderer",
     "pack_voxdata", "device_count", "init_ray_dir", "BuildMode", "VoxelSource",
-    "MakeSphereSource", "MakeRawSource", "MakeIsoSource", "DynamicSVO", "NODE_DTYPE", "EMPTY_NODE", "FULL_NODE",
+    "MakeSphereSource", "MakeRawSource", "MakeIsoSource", "DynamicSVO", "LightParams", "NODE_DTYPE", "EMPTY_NODE", "FULL_NODE",
 ]
 
 EMPTY_NODE = 0x80000000
@@ -24,6 +24,21 @@ FULL_NODE = 0x80000001
 # VoxNode (reaction/report/main.tex:46-51): 40 bytes
 NODE_DTYPE = np.dtype([("flags", "<u4"), ("data", "<u4"), ("child", "<u4", (8,))])
 assert NODE_DTYPE.itemsize == 40
+
+
+class LightParams(C.Structure):
+    """LightParams (demo/Demo.cpp:141-147) == yv_light."""
+    _fields_ = [("enabled", C.c_int32), ("pos", C.c_float * 3), ("diffuse", C.c_float * 3),
+                ("specular", C.c_float * 3), ("attenuationCoefs", C.c_float * 3)]
+
+    def __init__(self, enabled=True, pos=(0, 0, 0), diffuse=(0.7, 0.7, 0.7), specular=(0.3, 0.3, 0.3),
+                 attenuationCoefs=(1, 0, 0.5)):
+        super().__init__()
+        self.enabled = 1 if enabled else 0
+        self.pos[:] = [float(v) for v in pos]
+        self.diffuse[:] = [float(v) for v in diffuse]
+        self.specular[:] = [float(v) for v in specular]
+        self.attenuationCoefs[:] = [float(v) for v in attenuationCoefs]
 
 
 class YVError(RuntimeError):
@@ -97,6 +112,9 @@ def lib():
         "yv_get_resolution": (i32, [vp, P(i32), P(i32)]),
         "yv_set_fov": (i32, [vp, f32]),
         "yv_get_fov": (i32, [vp, P(f32)]),
+        "yv_set_light": (i32, [vp, i32, vp]),
+        "yv_set_show_normals": (i32, [vp, i32]),
+        "yv_get_show_normals": (i32, [vp, P(i32)]),
         "yv_set_detail_coef": (i32, [vp, f32]),
         "yv_get_detail_coef": (i32, [vp, P(f32)]),
         "yv_render_frame": (i32, [vp, P(vp)]),
@@ -390,6 +408,19 @@ class SVORenderer:
         f = C.c_float()
         _check(lib().yv_get_fov(self._h, C.byref(f)))
         return f.value
+
+    def SetLigth(self, i, lp):                            # demo/SVORenderer.h:34 (the reference's spelling)
+        _check(lib().yv_set_light(self._h, int(i), C.byref(lp)))
+
+    SetLight = SetLigth
+
+    def SetShowNormals(self, enable):                     # demo/SVORenderer.h:31
+        _check(lib().yv_set_show_normals(self._h, 1 if enable else 0))
+
+    def GetShowNormals(self):                             # demo/SVORenderer.h:32
+        v = C.c_int()
+        _check(lib().yv_get_show_normals(self._h, C.byref(v)))
+        return bool(v.value)
 
     def SetDetailCoef(self, coef):                        # demo/SVORenderer.h:25
         _check(lib().yv_set_detail_coef(self._h, float(coef)))

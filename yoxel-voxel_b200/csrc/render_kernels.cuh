@@ -51,6 +51,9 @@ struct RenderParams {
   unsigned int *tile_counter;  // persistent schedule: next tile to hand out
   int tiles_x, num_tiles;      // 8x8 tiles covering [0,width) x [y0,y1)
   int refill_threshold;        // persistent schedule: refill once <= this many lanes are still traversing
+  int shade_mode;              // 0 = head-light Lambert (SimpleShader), 1 = Phong point lights (ShadeSimple), 2 = normals
+  yv_light lights[YV_MAX_LIGHTS];   // SetLigth(i, LightParams) (demo/SVORenderer.h:34)
+  uint2 *shade_rec;            // shade_mode != 0: (VoxData, t) of every hit pixel for the ShadeSimple pass; else NULL
   int shadow, ao_samples;      // secondary rays
   uint32_t seed;
   float voxel_size, ao_max_t;
@@ -305,6 +308,7 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_frame(const 
           }
         }
         if (p.hit_node) { p.hit_node[pixel] = hn; p.hit_child[pixel] = hc; p.hit_t[pixel] = ht; }
+        if (!SEC && p.shade_rec && hit) p.shade_rec[pixel] = make_uint2(sdata, __float_as_uint(ht));
       } else {
         // a secondary ray came back
         const float ts = max3f(s.t1x, s.t1y, s.t1z);
@@ -494,11 +498,41 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_queue(const 
       const float Pz = YV_FADD(p.pos[2], YV_FMUL(dz, ht));
       const float dl = lambert(nx, ny, nz, Px, Py, Pz, p.light[0], p.light[1], p.light[2]);
       rgba = shade_rgba(data, YV_FADD(YV_SHADE_AMBIENT, YV_FMUL(YV_SHADE_DIFFUSE, YV_FMUL(dl, 1.0f))));
+      if (p.shade_rec) p.shade_rec[pixel] = make_uint2(data, __float_as_uint(ht));
     }
     p.out_rgba[pixel] = rgba;
     if (p.hit_node) { p.hit_node[pixel] = hn; p.hit_child[pixel] = hc; p.hit_t[pixel] = ht; }
     if (COUNT) p.counters[pixel] = slots[7 * kQueueRays + slot];
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ShadeSimple pass (demo/SVORenderer.cpp:147): the CUDA renderer's second kernel. Used only for the shading
+// models the CPU tracer does not have (point-light Phong, show-normals): the trace kernel leaves (VoxData, t)
+// per hit pixel, this pass re-derives the ray and overwrites the pixel. Keeping it out of the trace kernel
+// costs that kernel no registers.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) shade_pass(const __grid_constant__ RenderParams p) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = tile_row_y(p, blockIdx.y) + (threadIdx.x >> 5);      // the rows of this launch's band / blocks
+  if (x >= p.width || y >= p.y1) return;
+  const uint32_t pixel = (uint32_t)y * (uint32_t)p.width + (uint32_t)x;
+  if (p.out_rgba[pixel] == 0u) return;                    // miss (hit pixels carry alpha 255)
+  const uint2 rec = p.shade_rec[pixel];
+  const float t = __uint_as_float(rec.y);
+  float nx, ny, nz, dx, dy, dz;
+  unpack_normal(rec.x, nx, ny, nz);
+  uint32_t rgba;
+  if (p.shade_mode == 2) rgba = shade_normal(nx, ny, nz);
+  else {
+    primary_dir(p.dir0, p.du, p.dv, x, y, dx, dy, dz);
+    dx = adjust_dir1(dx); dy = adjust_dir1(dy); dz = adjust_dir1(dz);
+    const float Px = YV_FADD(p.pos[0], YV_FMUL(dx, t));
+    const float Py = YV_FADD(p.pos[1], YV_FMUL(dy, t));
+    const float Pz = YV_FADD(p.pos[2], YV_FMUL(dz, t));
+    rgba = shade_phong(rec.x, nx, ny, nz, Px, Py, Pz, p.pos, p.lights);
+  }
+  p.out_rgba[pixel] = rgba;
 }
 
 // ---------------------------------------------------------------------------------------------

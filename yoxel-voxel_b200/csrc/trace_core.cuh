@@ -380,6 +380,52 @@ YV_HD uint32_t shade_rgba(uint32_t data, float k) {
   return o0 | (o1 << 8) | (o2 << 16) | 0xff000000u;
 }
 
+// ShadeSimple with point lights / SetShowNormals (spec: include/yv_format.h)
+YV_HD uint32_t shade_phong(uint32_t data, float nx, float ny, float nz, float Px, float Py, float Pz,
+                           const float viewer[3], const yv_light *lights) {
+  const uint32_t r5 = (data >> 11) & 31u, g6 = (data >> 5) & 63u, b5 = data & 31u;
+  const float c[3] = { (float)((r5 << 3) | (r5 >> 2)), (float)((g6 << 2) | (g6 >> 4)), (float)((b5 << 3) | (b5 >> 2)) };
+  float acc[3] = { YV_FMUL(YV_SHADE_AMBIENT, c[0]), YV_FMUL(YV_SHADE_AMBIENT, c[1]), YV_FMUL(YV_SHADE_AMBIENT, c[2]) };
+  float Vx = YV_FSUB(viewer[0], Px), Vy = YV_FSUB(viewer[1], Py), Vz = YV_FSUB(viewer[2], Pz);
+  const float vl = YV_FSQRT(YV_FADD(YV_FADD(YV_FMUL(Vx, Vx), YV_FMUL(Vy, Vy)), YV_FMUL(Vz, Vz)));
+  if (vl > 0) { Vx = YV_FDIV(Vx, vl); Vy = YV_FDIV(Vy, vl); Vz = YV_FDIV(Vz, vl); } else { Vx = Vy = Vz = 0.0f; }
+  for (int i = 0; i < YV_MAX_LIGHTS; ++i) {
+    if (!lights[i].enabled) continue;
+    const float lx = YV_FSUB(lights[i].pos[0], Px), ly = YV_FSUB(lights[i].pos[1], Py), lz = YV_FSUB(lights[i].pos[2], Pz);
+    const float d = YV_FSQRT(YV_FADD(YV_FADD(YV_FMUL(lx, lx), YV_FMUL(ly, ly)), YV_FMUL(lz, lz)));
+    if (!(d > 0)) continue;
+    const float Lx = YV_FDIV(lx, d), Ly = YV_FDIV(ly, d), Lz = YV_FDIV(lz, d);
+    const float att = YV_FDIV(1.0f, YV_FADD(YV_FADD(lights[i].attenuation[0], YV_FMUL(lights[i].attenuation[1], d)),
+                                             YV_FMUL(YV_FMUL(lights[i].attenuation[2], d), d)));
+    const float nl = YV_FADD(YV_FADD(YV_FMUL(nx, Lx), YV_FMUL(ny, Ly)), YV_FMUL(nz, Lz));
+    const float ndl = nl > 0 ? nl : 0.0f;
+    const float k2 = YV_FMUL(2.0f, nl);
+    const float Rx = YV_FSUB(YV_FMUL(k2, nx), Lx), Ry = YV_FSUB(YV_FMUL(k2, ny), Ly), Rz = YV_FSUB(YV_FMUL(k2, nz), Lz);
+    float rv = YV_FADD(YV_FADD(YV_FMUL(Rx, Vx), YV_FMUL(Ry, Vy)), YV_FMUL(Rz, Vz));
+    rv = (nl > 0 && rv > 0) ? rv : 0.0f;
+    const float s2 = YV_FMUL(rv, rv), s4 = YV_FMUL(s2, s2), s8 = YV_FMUL(s4, s4), spec = YV_FMUL(s8, s2);
+    for (int ch = 0; ch < 3; ++ch)
+      acc[ch] = YV_FADD(acc[ch], YV_FMUL(att, YV_FADD(YV_FMUL(YV_FMUL(lights[i].diffuse[ch], ndl), c[ch]),
+                                                       YV_FMUL(YV_FMUL(lights[i].specular[ch], spec), 255.0f))));
+  }
+  uint32_t out = 0xff000000u;
+  for (int ch = 0; ch < 3; ++ch) {
+    const float v = floorf(YV_FADD(acc[ch], 0.5f));
+    out |= (uint32_t)(v < 255.0f ? (v > 0.0f ? v : 0.0f) : 255.0f) << (8 * ch);
+  }
+  return out;
+}
+
+YV_HD uint32_t shade_normal(float nx, float ny, float nz) {
+  const float n[3] = { nx, ny, nz };
+  uint32_t out = 0xff000000u;
+  for (int ch = 0; ch < 3; ++ch) {
+    const float v = floorf(YV_FADD(YV_FMUL(YV_FADD(YV_FMUL(n[ch], 0.5f), 0.5f), 255.0f), 0.5f));
+    out |= (uint32_t)(v < 255.0f ? (v > 0.0f ? v : 0.0f) : 255.0f) << (8 * ch);
+  }
+  return out;
+}
+
 // ---- secondary-ray helpers (BASELINE config 4; spec: include/yv_b200.h YV secondary rays) -----
 
 YV_HD uint32_t hash_u32(uint32_t x) {

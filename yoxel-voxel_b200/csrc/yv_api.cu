@@ -63,6 +63,8 @@ struct yv_renderer {
   // RendererBase state (renderer_base.h:10-18,25)
   float pos[3] = { 0, 0, 0 }, dir[3] = { 1, 0, 0 }, up[3] = { 0, 0, 1 };
   float fov = 70.0f;
+  yv_light lights[YV_MAX_LIGHTS] = {};   // SetLigth (demo/SVORenderer.h:34); any enabled light switches to Phong
+  bool show_normals = false;          // SetShowNormals (demo/SVORenderer.h:31)
   float detail_coef = 0.0f;           // SVORenderer::m_detailCoef (demo/SVORenderer.h:56); 0 = off
   int width = 0, height = 0;
   int y0 = 0, y1 = 0;
@@ -78,6 +80,7 @@ struct yv_renderer {
   size_t fb_pixels = 0;
   uint32_t *d_hit_node = nullptr; int32_t *d_hit_child = nullptr; float *d_hit_t = nullptr;
   uint32_t *d_counters = nullptr;
+  uint2 *d_shade_rec = nullptr;       // (VoxData, t) per pixel for the ShadeSimple pass
   unsigned int *d_tile_counter = nullptr;
   bool hits = false, counters = false;
   // launch
@@ -91,6 +94,7 @@ struct yv_renderer {
   int opt_pipeline = 4;               // row chunks per RenderFrame (0/1 = no pipelining); 4 measured best at 1080p
   bool timed = false;
   int launches = 0;
+  int last_launches = 1;              // kernels launched by the most recent launch_frame call
   // options
   int opt_smem_nodes = 0;             // records staged in shared memory (585 = four levels)
   int opt_persistent = 0;
@@ -182,6 +186,7 @@ void free_frame_buffers(yv_renderer *r) {
   cudaFree(r->d_fb); r->d_fb = nullptr;
   cudaFreeHost(r->h_fb); r->h_fb = nullptr;
   cudaFree(r->d_hit_node); cudaFree(r->d_hit_child); cudaFree(r->d_hit_t); cudaFree(r->d_counters);
+  cudaFree(r->d_shade_rec); r->d_shade_rec = nullptr;
   r->d_hit_node = nullptr; r->d_hit_child = nullptr; r->d_hit_t = nullptr; r->d_counters = nullptr;
   r->fb_pixels = 0;
 }
@@ -352,6 +357,13 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
   p.tiles_x = (p.width + 7) / 8;
   p.num_tiles = p.tiles_x * tile_rows;
   p.refill_threshold = r->opt_refill;
+  bool any_light = false;
+  for (int i = 0; i < YV_MAX_LIGHTS; ++i) { p.lights[i] = r->lights[i]; any_light = any_light || r->lights[i].enabled; }
+  p.shade_mode = sec ? 0 : (r->show_normals ? 2 : (any_light ? 1 : 0));
+  if (p.shade_mode != 0) {
+    if (!r->d_shade_rec) YV_CUDA(cudaMalloc(&r->d_shade_rec, std::max<size_t>(1, r->fb_pixels) * sizeof(uint2)));
+    p.shade_rec = r->d_shade_rec;
+  }
   p.shadow = r->shadow; p.ao_samples = r->ao_samples; p.seed = r->seed;
   p.voxel_size = r->voxel_size; p.ao_max_t = r->ao_max_t;
   const bool lod = r->detail_coef > 0.0f;
@@ -401,10 +413,18 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
     default: rc = launch_stack<true, true>(r, p, smem); break;
   }
   if (rc) return rc;
+  int launches = 1;
+  if (p.shade_mode != 0 && p.num_tiles > 0) {       // ShadeSimple pass over the rows this launch rendered
+    dim3 grid((p.width + 31) / 32, p.num_tiles / p.tiles_x);
+    yv::shade_pass<<<grid, 256, 0, r->stream>>>(p);
+    YV_CUDA(cudaGetLastError());
+    ++launches;
+  }
+  r->last_launches = launches;
   if (!r->suppress_events) {
     YV_CUDA(cudaEventRecord(r->ev1, r->stream));
     r->timed = true;
-    r->launches = 1;
+    r->launches = launches;
   }
   return YV_OK;
 }
@@ -432,7 +452,7 @@ int render_frame_pipelined(yv_renderer *r) {
       cudaStreamWaitEvent(r->copy_stream, r->ev_chunk[k], 0);
       const size_t off = (size_t)y0 * W * 4, bytes = (size_t)(y1 - y0) * W * 4;
       cudaMemcpyAsync(r->h_fb + off, (const uint8_t *)r->d_fb + off, bytes, cudaMemcpyDeviceToHost, r->copy_stream);
-      ++launched;
+      launched += r->last_launches;
     }
   }
   r->suppress_events = false;
@@ -676,6 +696,22 @@ int yv_get_resolution(const yv_renderer *r, int *width, int *height) {
 int yv_set_fov(yv_renderer *r, float fov_deg) {
   if (!r) return fail(YV_ERR_ARG, "null renderer");
   r->fov = fov_deg;
+  return YV_OK;
+}
+int yv_set_light(yv_renderer *r, int index, const yv_light *light) {
+  if (!r || !light) return fail(YV_ERR_ARG, "null argument");
+  if (index < 0 || index >= YV_MAX_LIGHTS) return fail(YV_ERR_ARG, "light index out of range");
+  r->lights[index] = *light;
+  return YV_OK;
+}
+int yv_set_show_normals(yv_renderer *r, int enable) {
+  if (!r) return fail(YV_ERR_ARG, "null renderer");
+  r->show_normals = enable != 0;
+  return YV_OK;
+}
+int yv_get_show_normals(const yv_renderer *r, int *enable) {
+  if (!r || !enable) return fail(YV_ERR_ARG, "null argument");
+  *enable = r->show_normals ? 1 : 0;
   return YV_OK;
 }
 int yv_set_detail_coef(yv_renderer *r, float coef) {
