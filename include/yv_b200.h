@@ -177,6 +177,11 @@ int yv_set_stream(yv_renderer *r, void *cuda_stream);
  *                 16x8 tile over its lanes; primary rays). "persistent" is an alias.
  *                 (with warp-level lane refill: ballot + popc compaction of finished rays)
  *   "refill"      persistent schedule: refill a warp once <= this many lanes are still traversing
+ *   "sec_queue"   secondary rays: 0 (default) = every lane traces its own pixel's rays as stages
+ *                 (render_frame<SEC>); 1 = primary and shadow rays in lock-step, AO rays pooled per warp and pulled
+ *                 by whichever lane is free (render_sec_queue; fills more lanes but loses lock-step fetches: slower)
+ *   "sec_threshold" secondary rays (stage machine): lanes whose ray has ended are handed their pixel's next ray once <= this many
+ *                 lanes of the warp are still traversing (-1 = only when the whole warp has drained)
  *   "pipeline"    number of row chunks (2..8, default 4) yv_render_frame cuts the frame into: chunks render on
  *                 two alternating streams and each chunk's device->host copy overlaps the next chunk's kernel;
  *                 0 or 1 = one launch, then one copy

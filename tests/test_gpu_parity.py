@@ -117,14 +117,21 @@ def test_ragged_resolutions(renderer, size, persistent):
     dict(shadow=1, ao_samples=16, seed=99, light_pos=(0.1, 0.9, 0.2), voxel_size=2.0 / 1024, ao_max_t=0.2),
 ], ids=["shadow", "ao4", "shadow+ao4", "shadow+ao16"])
 def test_secondary_rays(renderer, sec, persistent):
-    """BASELINE config 4 (at depth 10): primary + shadow + AO rays."""
+    """BASELINE config 4 (at depth 10): primary + shadow + AO rays; stage machine and pooled-AO kernel."""
     svo = scenes.fractal(10)
     renderer.SetOption("persistent", persistent)
     renderer.SetScene(svo)
+    renderer.EnableCounters(True)
     for cam in (scenes.CAMERAS[1], scenes.CAMERAS[4]):
-        img, node, child, t = _render_gpu(renderer, cam, 400, 300, sec)
-        o = _render_cpu(svo, cam, 400, 300, sec)
-        _check(o, img, node, child, t, "sec")
+        o = _render_cpu(svo, cam, 397, 301, sec, visits=True)
+        for sec_queue in (0, 1):
+            renderer.SetOption("sec_queue", sec_queue)
+            img, node, child, t = _render_gpu(renderer, cam, 397, 301, sec)
+            _check(o, img, node, child, t, "sec/q%d" % sec_queue)
+            visits, pops = renderer.GetCounters()
+            assert (visits == o["visits"]).all(), "node visits differ (sec_queue=%d)" % sec_queue
+    renderer.EnableCounters(False)
+    renderer.SetOption("sec_queue", 0)
     renderer.SetSecondary(0, 0)
 
 

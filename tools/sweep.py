@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--smem", default="0")
     ap.add_argument("--refill", default="20")
     ap.add_argument("--layout", default="0")
+    ap.add_argument("--sec-threshold", default="16")
+    ap.add_argument("--sec-queue", default="1")
     ap.add_argument("--detail", type=float, default=0.0)
     ap.add_argument("--secondary", action="store_true")
     ap.add_argument("--scene", default="fractal", choices=["fractal", "iso"])
@@ -52,11 +54,14 @@ def main():
                                                      [int(v) for v in a.smem.split(",")]):
         for refill in ([int(v) for v in a.refill.split(",")] if persistent == 1 else [20]):
             for layout in [int(v) for v in a.layout.split(",")]:
-                combos.append((persistent, stack, smem, refill, layout))
+                for sect in [int(v) for v in a.sec_threshold.split(",")]:
+                    for secq in [int(v) for v in a.sec_queue.split(",")]:
+                        combos.append((persistent, stack, smem, refill, layout, sect, secq))
     with torch.cuda.stream(st):
-        for persistent, stack, smem, refill, layout in combos:
+        for persistent, stack, smem, refill, layout, sect, secq in combos:
             r.SetOption("persistent", persistent); r.SetOption("stack", stack); r.SetOption("smem_nodes", smem)
             r.SetOption("refill", refill); r.SetOption("layout", layout); r.SetDetailCoef(a.detail)
+            r.SetOption("sec_threshold", sect); r.SetOption("sec_queue", secq)
             try:
                 times = []
                 for i in range(a.frames + 3):
@@ -78,7 +83,7 @@ def main():
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record(st); r.Render(buf.data_ptr(), sync=False); e1.record(st); st.synchronize()
                     warm.append(e0.elapsed_time(e1))
-                res = dict(lib=os.environ.get("YV_B200_LIB", "default"), persistent=persistent, stack=stack, smem=smem, refill=refill, layout=layout, ms_median=float(np.median(times)),
+                res = dict(lib=os.environ.get("YV_B200_LIB", "default"), persistent=persistent, stack=stack, smem=smem, refill=refill, layout=layout, sec_threshold=sect, sec_queue=secq, ms_median=float(np.median(times)),
                            ms_min=float(min(times)), ms_warm_l2=float(np.median(warm[2:])), same_image=same)
             except yv.YVError as e:
                 res = dict(persistent=persistent, stack=stack, smem=smem, refill=refill, error=str(e))

@@ -51,6 +51,7 @@ struct RenderParams {
   unsigned int *tile_counter;  // persistent schedule: next tile to hand out
   int tiles_x, num_tiles;      // 8x8 tiles covering [0,width) x [y0,y1)
   int refill_threshold;        // persistent schedule: refill once <= this many lanes are still traversing
+  int sec_threshold;           // secondary rays: hand waiting lanes their next ray once <= this many lanes traverse
   int shade_mode;              // 0 = head-light Lambert (SimpleShader), 1 = Phong point lights (ShadeSimple), 2 = normals
   yv_light lights[YV_MAX_LIGHTS];   // SetLigth(i, LightParams) (demo/SVORenderer.h:34)
   uint2 *shade_rec;            // shade_mode != 0: (VoxData, t) of every hit pixel for the ShadeSimple pass; else NULL
@@ -264,6 +265,10 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_frame(const 
       const unsigned am = __ballot_sync(kFullMask, state == kLaneActive);
       if (am == 0u) break;
       if (PERSISTENT && !pool_empty && __popc(am) <= p.refill_threshold) break;
+      // secondary stages: lanes whose ray has ended wait for their next ray; serve them once few lanes
+      // are still traversing instead of only when the whole warp has drained
+      if (SEC && __popc(am) <= p.sec_threshold &&
+          __ballot_sync(kFullMask, state == kLaneHit || state == kLaneMiss || state == kLaneLodHit) != 0u) break;
 #pragma unroll
       for (int u = 0; u < kStepsPerVote; ++u) {
         if (state == kLaneActive) {
@@ -503,6 +508,200 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_queue(const 
     p.out_rgba[pixel] = rgba;
     if (p.hit_node) { p.hit_node[pixel] = hn; p.hit_child[pixel] = hc; p.hit_t[pixel] = ht; }
     if (COUNT) p.counters[pixel] = slots[7 * kQueueRays + slot];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// secondary rays with a per-warp AO-ray queue (BASELINE config 4)
+// ---------------------------------------------------------------------------------------------
+// In the stage machine of render_frame a lane traces its pixel's shadow and AO rays one after the other,
+// so a warp runs as long as its slowest pixel: ncu shows 11 of 32 lanes busy in the child test on config 4
+// (42 % of the pixels miss and have no secondary rays; AO rays differ wildly in length). AO rays are
+// incoherent by construction, so unlike primary rays they lose nothing by being handed to whichever lane
+// is free. This kernel therefore keeps the coherent rays in lock-step and pools the incoherent ones:
+//   A  primary rays, one per lane, lock-step (as render_frame's tile schedule);
+//   B  shadow rays of the hit pixels, one per lane, lock-step (they all aim at the light);
+//   C  AO rays: every hit lane sets up its pixel's next (up to 4) AO rays and parks them in shared memory;
+//      the warp's lanes then pull rays from that queue until it is dry, adding an occlusion to the pixel's
+//      shared-memory counter when a ray ends occluded; repeated while samples remain;
+//   D  every hit lane shades and stores its pixel.
+// Results are order-independent sums, so the frame is bit-identical to the stage machine's and the oracle's.
+constexpr int kAoBatch = 4;                               // AO rays queued per pixel and pass
+constexpr int kAoQueueRays = 32 * kAoBatch;               // per warp
+constexpr size_t kAoSmemPerWarp = kAoQueueRays * 8 * 4 + 32 * 4 + 32 * 4;
+
+template <bool COUNT, bool LOD>
+__global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_sec_queue(const __grid_constant__ RenderParams p) {
+  extern __shared__ uint4 smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  uint32_t *slots = reinterpret_cast<uint32_t *>(smem) + warp * (kAoSmemPerWarp / 4);     // [word][slot], 8 words
+  uint32_t *occ_cnt = slots + kAoQueueRays * 8;                                             // per pixel (lane)
+  uint32_t *vis_cnt = occ_cnt + 32;                                                          // per pixel: extra node visits (COUNT)
+
+  const int tiles_x16 = (p.width + 15) >> 4;
+  const int tx = blockIdx.x % tiles_x16, ty = blockIdx.x / tiles_x16;
+  const int x = tx * 16 + (warp & 1) * 8 + (lane & 7);
+  const int y = tile_row_y(p, ty) + (warp >> 1) * 4 + (lane >> 3);
+  const bool in_frame = x < p.width && y < p.y1;
+  const uint32_t pixel = (uint32_t)y * (uint32_t)p.width + (uint32_t)x;
+
+  NodeFetch<COUNT, false> fetch = { p.recs, nullptr, 0u, 0u, 0u, 0u };
+  LocalStack stk(nullptr);
+  LeanState s;
+  const bool root_valid = p.root_valid != 0u;
+  uint32_t root_masks = 0u, root_child_base = 0u;
+  if (root_valid) { const Rec r = fetch.load(0u); root_masks = r.masks; root_child_base = r.child_base; }
+
+  // ---- A: primary ray, lock-step ------------------------------------------------------------------
+  int state = kLaneIdle;
+  if (in_frame) {
+    float dx, dy, dz;
+    primary_dir(p.dir0, p.du, p.dv, x, y, dx, dy, dz);
+    dx = adjust_dir1(dx); dy = adjust_dir1(dy); dz = adjust_dir1(dz);
+    state = lean_begin(s, fetch, root_valid, p.pos[0], p.pos[1], p.pos[2], dx, dy, dz) ? kLaneActive : kLaneMiss;
+  }
+  auto run_lockstep = [&](bool front_only) {
+    for (;;) {
+      if (__ballot_sync(kFullMask, state == kLaneActive) == 0u) break;
+#pragma unroll
+      for (int u = 0; u < kStepsPerVote; ++u) {
+        if (state == kLaneActive) {
+          const int r = lean_step<LOD>(s, fetch, stk, front_only, p.detail);
+          if (r == kStepHit) state = kLaneHit;
+          else if (r == kStepMiss) state = kLaneMiss;
+          else if (LOD && r == kStepLodHit) state = kLaneLodHit;
+        }
+      }
+    }
+  };
+  run_lockstep(false);
+
+  // ---- primary result; hit point, normal, secondary origin ---------------------------------------------
+  const bool lod_hit = LOD && state == kLaneLodHit;
+  const bool hit = state == kLaneHit || lod_hit;
+  uint32_t sdata = 0u, hn = YV_MISS_NODE; int32_t hc = YV_MISS_CHILD; float ht = 0.0f;
+  float nx = 0.f, ny = 0.f, nz = 0.f, Ox = 0.f, Oy = 0.f, Oz = 0.f, dl = 0.f, vis = 1.0f;
+  if (hit) {
+    const uint32_t c = s.ch ^ s.flags;
+    fetch.hit_info(p.leaves, p.node_data, s.idx, c, lod_hit, hn, sdata);
+    hc = lod_hit ? -1 : (int32_t)c; ht = max3f(s.t1x, s.t1y, s.t1z);
+    unpack_normal(sdata, nx, ny, nz);
+    float dx, dy, dz;
+    primary_dir(p.dir0, p.du, p.dv, x, y, dx, dy, dz);
+    dx = adjust_dir1(dx); dy = adjust_dir1(dy); dz = adjust_dir1(dz);
+    const float Px = YV_FADD(p.pos[0], YV_FMUL(dx, ht));
+    const float Py = YV_FADD(p.pos[1], YV_FMUL(dy, ht));
+    const float Pz = YV_FADD(p.pos[2], YV_FMUL(dz, ht));
+    dl = lambert(nx, ny, nz, Px, Py, Pz, p.light[0], p.light[1], p.light[2]);
+    Ox = YV_FADD(Px, YV_FMUL(nx, p.voxel_size));
+    Oy = YV_FADD(Py, YV_FMUL(ny, p.voxel_size));
+    Oz = YV_FADD(Pz, YV_FMUL(nz, p.voxel_size));
+  }
+  if (in_frame && p.hit_node) { p.hit_node[pixel] = hn; p.hit_child[pixel] = hc; p.hit_t[pixel] = ht; }
+
+  // ---- B: shadow rays, lock-step -------------------------------------------------------------------------
+  state = kLaneIdle;
+  float slen = 0.0f;
+  if (hit && p.shadow) {
+    const float vx = YV_FSUB(p.light[0], Ox), vy = YV_FSUB(p.light[1], Oy), vz = YV_FSUB(p.light[2], Oz);
+    slen = YV_FSQRT(YV_FADD(YV_FADD(YV_FMUL(vx, vx), YV_FMUL(vy, vy)), YV_FMUL(vz, vz)));
+    if (slen > 0) {
+      const float rx = adjust_dir1(YV_FDIV(vx, slen)), ry = adjust_dir1(YV_FDIV(vy, slen)), rz = adjust_dir1(YV_FDIV(vz, slen));
+      if (lean_begin(s, fetch, root_valid, Ox, Oy, Oz, rx, ry, rz)) state = kLaneActive;
+    }
+  }
+  run_lockstep(true);
+  if (state == kLaneHit || (LOD && state == kLaneLodHit)) {
+    const float ts = max3f(s.t1x, s.t1y, s.t1z);
+    if (ts > 0 && ts < slen) vis = 0.0f;
+  }
+
+  // ---- C: AO rays through the warp's queue ------------------------------------------------------------------
+  const uint32_t own_visits = fetch.visits, own_revisits = fetch.revisits;   // this pixel's primary + shadow rays
+  occ_cnt[lane] = 0u;
+  if (COUNT) vis_cnt[lane] = 0u;
+  __syncwarp();
+  for (int k0 = 0; k0 < p.ao_samples; k0 += kAoBatch) {
+    const int nb = min(kAoBatch, p.ao_samples - k0);
+    // set-up: hit lanes park their pixel's next nb rays
+    const unsigned hm = __ballot_sync(kFullMask, hit);
+    const int my_rank = __popc(hm & lt_mask);
+    int qcount = __popc(hm) * nb;
+    if (hit) {
+      for (int k = 0; k < nb; ++k) {
+        float rx, ry, rz;
+        ao_direction(nx, ny, nz, pixel, (uint32_t)(k0 + k), p.seed, rx, ry, rz);
+        rx = adjust_dir1(rx); ry = adjust_dir1(ry); rz = adjust_dir1(rz);
+        const int slot = my_rank * nb + k;
+        LeanState q;
+        if (lean_setup_root(q, root_valid, Ox, Oy, Oz, rx, ry, rz)) {
+          slots[0 * kAoQueueRays + slot] = __float_as_uint(q.t1x); slots[1 * kAoQueueRays + slot] = __float_as_uint(q.t1y);
+          slots[2 * kAoQueueRays + slot] = __float_as_uint(q.t1z); slots[3 * kAoQueueRays + slot] = __float_as_uint(q.Tx);
+          slots[4 * kAoQueueRays + slot] = __float_as_uint(q.Ty);  slots[5 * kAoQueueRays + slot] = __float_as_uint(q.Tz);
+          slots[6 * kAoQueueRays + slot] = q.ch | (q.flags << 3) | ((uint32_t)lane << 6);
+        } else {
+          slots[6 * kAoQueueRays + slot] = 0xffffffffu;        // misses the cube outright: unoccluded, nothing to trace
+        }
+      }
+    }
+    __syncwarp();
+    // lanes pull rays
+    int qnext = 0, cur = -1, owner = 0;
+    for (;;) {
+      const unsigned idle = __ballot_sync(kFullMask, cur < 0);
+      if (idle != 0u && qnext < qcount) {
+        const int take = min(__popc(idle), qcount - qnext);
+        const int rank = __popc(idle & lt_mask);
+        if (cur < 0 && rank < take) {
+          const int slot = qnext + rank;
+          const uint32_t w = slots[6 * kAoQueueRays + slot];
+          if (w != 0xffffffffu) {
+            cur = slot; owner = (int)((w >> 6) & 31u);
+            s.t1x = __uint_as_float(slots[0 * kAoQueueRays + slot]); s.t1y = __uint_as_float(slots[1 * kAoQueueRays + slot]);
+            s.t1z = __uint_as_float(slots[2 * kAoQueueRays + slot]); s.Tx = __uint_as_float(slots[3 * kAoQueueRays + slot]);
+            s.Ty = __uint_as_float(slots[4 * kAoQueueRays + slot]);  s.Tz = __uint_as_float(slots[5 * kAoQueueRays + slot]);
+            s.ch = w & 7u; s.flags = (w >> 3) & 7u; s.idx = 0u; s.sp = 0; s.pend = 0u; s.level = 0u;
+            s.masks = root_masks; s.child_base = root_child_base;
+            lean_eval_next(s);
+            if (COUNT) { atomicAdd(&vis_cnt[owner], 1u); }
+          }
+        }
+        qnext += take;
+      }
+      if (__ballot_sync(kFullMask, cur >= 0) == 0u) { if (qnext >= qcount) break; else continue; }
+#pragma unroll
+      for (int u = 0; u < kStepsPerVote; ++u) {
+        if (cur >= 0) {
+          const uint32_t v0 = COUNT ? fetch.visits : 0u, r0 = COUNT ? fetch.revisits : 0u;
+          const int r = lean_step<LOD>(s, fetch, stk, true, p.detail);
+          if (COUNT) { const uint32_t dv = fetch.visits - v0, dr = fetch.revisits - r0; if (dv | dr) atomicAdd(&vis_cnt[owner], dv | (dr << 16)); }
+          if (r != kStepContinue) {
+            if (r != kStepMiss) {
+              const float ts = max3f(s.t1x, s.t1y, s.t1z);
+              if (ts > 0 && ts < p.ao_max_t) atomicAdd(&occ_cnt[owner], 1u);
+            }
+            cur = -1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- D: shade + store ------------------------------------------------------------------------------------
+  if (!in_frame) return;
+  uint32_t rgba = 0u;
+  if (hit) {
+    float ao = 1.0f;
+    if (p.ao_samples > 0) ao = YV_FSUB(1.0f, YV_FDIV((float)occ_cnt[lane], (float)p.ao_samples));
+    const float k = YV_FMUL(YV_FADD(YV_SHADE_AMBIENT, YV_FMUL(YV_SHADE_DIFFUSE, YV_FMUL(dl, vis))), ao);
+    rgba = shade_rgba(sdata, k);
+  }
+  p.out_rgba[pixel] = rgba;
+  if (COUNT) {
+    const uint32_t extra = vis_cnt[lane];
+    p.counters[pixel] = ((own_visits + (extra & 0xffffu)) & 0xffffu) | ((own_revisits + (extra >> 16)) << 16);
   }
 }
 

@@ -99,6 +99,8 @@ struct yv_renderer {
   int opt_smem_nodes = 0;             // records staged in shared memory (585 = four levels)
   int opt_persistent = 0;
   int opt_refill = 20;                // persistent schedule: refill when <= this many lanes are live
+  int opt_sec_threshold = 16;         // secondary rays: serve waiting lanes when <= this many lanes are traversing (-1 = only when drained)
+  int opt_sec_queue = 0;              // 1 = AO rays pooled per warp (render_sec_queue); measured slower than the per-lane stage machine (6.31 vs 5.60 ms on config 4)
   int opt_layout = 0;                 // 0 = packed records (static scenes), 1 = raw reference pool (scenes under edit)
   int opt_stack = 0;                  // yv::kStackLocal / kStackRing4
 };
@@ -277,6 +279,16 @@ int launch_queue(yv_renderer *r, const yv::RenderParams &p) {
   return YV_OK;
 }
 
+template <bool COUNT, bool LOD>
+int launch_sec_queue(yv_renderer *r, const yv::RenderParams &p) {
+  auto kern = yv::render_sec_queue<COUNT, LOD>;
+  const size_t smem = yv::kAoSmemPerWarp * (yv::kCtaThreads / 32);
+  const long grid = (long)((p.width + 15) / 16) * (p.num_tiles / p.tiles_x);
+  if (grid > 0) kern<<<(unsigned)grid, yv::kCtaThreads, smem, r->stream>>>(p);
+  YV_CUDA(cudaGetLastError());
+  return YV_OK;
+}
+
 template <bool SEC, bool COUNT, int STACK, bool PERSISTENT>
 int launch_staged(yv_renderer *r, const yv::RenderParams &p, size_t smem) {
   return p.smem_nodes > 0 ? launch_kernel<SEC, COUNT, STACK, PERSISTENT, true>(r, p, smem)
@@ -357,6 +369,7 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
   p.tiles_x = (p.width + 7) / 8;
   p.num_tiles = p.tiles_x * tile_rows;
   p.refill_threshold = r->opt_refill;
+  p.sec_threshold = r->opt_sec_threshold;
   bool any_light = false;
   for (int i = 0; i < YV_MAX_LIGHTS; ++i) { p.lights[i] = r->lights[i]; any_light = any_light || r->lights[i].enabled; }
   p.shade_mode = sec ? 0 : (r->show_normals ? 2 : (any_light ? 1 : 0));
@@ -384,7 +397,10 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
 
   if (!r->suppress_events) YV_CUDA(cudaEventRecord(r->ev0, r->stream));
   const int key = (sec ? 2 : 0) | (r->counters ? 1 : 0);
-  if (raw) {
+  if (sec && !raw && r->opt_sec_queue && r->opt_persistent != 1) {      // pooled AO rays (config 4)
+    if (lod) rc = r->counters ? launch_sec_queue<true, true>(r, p) : launch_sec_queue<false, true>(r, p);
+    else rc = r->counters ? launch_sec_queue<true, false>(r, p) : launch_sec_queue<false, false>(r, p);
+  } else if (raw) {
     switch (key | (lod ? 4 : 0)) {
       case 0: rc = launch_raw<false, false, false>(r, p); break;
       case 1: rc = launch_raw<false, true, false>(r, p); break;
@@ -903,6 +919,8 @@ int yv_set_option(yv_renderer *r, const char *name, int value) {
     if (value < 0 || value > 2) return fail(YV_ERR_ARG, "schedule must be 0 (tiles), 1 (persistent) or 2 (queue)");
     r->opt_persistent = value;
   }
+  else if (n == "sec_queue") r->opt_sec_queue = value ? 1 : 0;
+  else if (n == "sec_threshold") { if (value < -1 || value > 31) return fail(YV_ERR_ARG, "sec_threshold must be -1..31"); r->opt_sec_threshold = value; }
   else if (n == "pipeline") { if (value < 0 || value > yv_renderer::kChunks) return fail(YV_ERR_ARG, "pipeline must be 0..8 chunks"); r->opt_pipeline = value; }
   else if (n == "layout") { if (value != 0 && value != 1) return fail(YV_ERR_ARG, "layout must be 0 (packed) or 1 (raw)"); r->opt_layout = value; }
   else if (n == "refill") { if (value < 0 || value > 31) return fail(YV_ERR_ARG, "refill must be 0..31"); r->opt_refill = value; }
@@ -920,6 +938,8 @@ int yv_get_option(const yv_renderer *r, const char *name, int *value) {
   std::string n(name);
   if (n == "smem_nodes") *value = r->opt_smem_nodes;
   else if (n == "persistent" || n == "schedule") *value = r->opt_persistent;
+  else if (n == "sec_queue") *value = r->opt_sec_queue;
+  else if (n == "sec_threshold") *value = r->opt_sec_threshold;
   else if (n == "pipeline") *value = r->opt_pipeline;
   else if (n == "layout") *value = r->opt_layout;
   else if (n == "refill") *value = r->opt_refill;
