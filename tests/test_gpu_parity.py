@@ -386,3 +386,32 @@ def test_phong_lights_and_show_normals(renderer, schedule):
     renderer.SetOption("schedule", 0)
     img, *_ = _render_gpu(renderer, cam, 480, 320)
     assert (img == lambert["rgba"]).all()
+
+
+def test_8k_frame_sampled_bands():
+    """BASELINE config 5 resolution (7680x4320): the whole frame is rendered on the GPU, the oracle checks
+    bands of rows spread over the image (an exhaustive 33 M-ray CPU frame is not needed to catch an
+    addressing or partition bug at this size)."""
+    svo = scenes.fractal(10)
+    r = yv.SVORenderer(0)
+    r.EnableHits(True)
+    r.SetScene(svo)
+    cam = scenes.CAMERAS[1]
+    W, H = 7680, 4320
+    img, node, child, t = _render_gpu(r, cam, W, H)
+    name, pos, d, up, fov = cam
+    for y0 in (0, 1077, 2160, 3333, H - 24):
+        o = yvo.render(svo.nodes(), svo.GetRoot(), yvo.camera(pos, d, up, fov, W, H), threads=8, rows=(y0, y0 + 24))
+        sl = slice(y0, y0 + 24)
+        assert (node[sl] == o["node"][sl]).all() and (child[sl] == o["child"][sl]).all()
+        assert t[sl].tobytes() == o["t"][sl].tobytes() and (img[sl] == o["rgba"][sl]).all()
+    # interleaved 8-way partition of the same frame reproduces it
+    from yoxel_voxel_b200 import multigpu
+    out = np.zeros_like(img)
+    for rank in range(8):
+        r.SetInterleave(32, 8, rank)
+        part = r.RenderFrame()
+        rows = multigpu.interleaved_rows(rank, 8, H, 32)
+        out[rows] = part[rows]
+    assert (out == img).all()
+    r.close()
