@@ -82,13 +82,17 @@ int yv_svo_count_changed_pages(const yv_svo *svo, uint32_t since_version);      
  * "layout" = 1 read that mirror (and call this implicitly before every frame). */
 int yv_svo_update(yv_svo *svo, int device, uint64_t *bytes_transferred);
 
-/* CudaSVO::Update (demo/SVORenderer.cpp:33-53): repack the pool into the 16-byte GPU record
- * form and copy it to `device`. Implicit at the first render if not called. */
+/* CudaSVO::Update (demo/SVORenderer.cpp:33-53): bring the packed 16-byte record form of the pool onto `device`:
+ * the raw pool is copied page-wise and re-laid-out breadth-first by GPU kernels (environment YV_HOST_PACK=1, or a
+ * pool with shared sub-trees, uses the host repack instead). Implicit at the first render if not called. */
 int yv_svo_upload(yv_svo *svo, int device);
 /* bytes resident on `device` for this scene (0 if not uploaded) */
 uint64_t yv_svo_device_bytes(const yv_svo *svo, int device);
 /* repacked record / leaf counts, for roofline arithmetic and tests */
 int yv_svo_packed_counts(yv_svo *svo, uint32_t *records, uint32_t *leaves);
+/* the device's packed arrays copied back (tests: the GPU repack equals the host repack); any pointer may be NULL */
+int yv_svo_device_packed_copy(yv_svo *svo, int device, uint32_t *n_records, uint32_t *n_leaves,
+                              uint32_t *records_out, uint32_t *leaves_out, uint32_t *node_data_out);
 /* copy of the repacked host arrays (tests): records = 4 u32 each, leaves = 1 u32 each */
 int yv_svo_packed_copy(yv_svo *svo, uint32_t *records_out, uint32_t *leaves_out);
 

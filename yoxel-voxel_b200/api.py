@@ -100,6 +100,7 @@ def lib():
         "yv_svo_update": (i32, [vp, i32, P(C.c_uint64)]),
         "yv_svo_upload": (i32, [vp, i32]),
         "yv_svo_device_bytes": (C.c_uint64, [vp, i32]),
+        "yv_svo_device_packed_copy": (i32, [vp, i32, P(u32), P(u32), vp, vp, vp]),
         "yv_svo_packed_counts": (i32, [vp, P(u32), P(u32)]),
         "yv_svo_packed_copy": (i32, [vp, vp, vp]),
         "yv_renderer_create": (i32, [i32, P(vp)]),
@@ -352,6 +353,15 @@ class SVOData:
         leaves = np.zeros(nl.value, dtype=np.uint32)
         _check(lib().yv_svo_packed_copy(self._h, recs.ctypes.data_as(C.c_void_p), leaves.ctypes.data_as(C.c_void_p)))
         return recs, leaves
+
+    def device_packed(self, device=0):
+        """The packed arrays as they sit on the device (records (n,4) u32, leaves, node_data)."""
+        nr, nl = C.c_uint32(), C.c_uint32()
+        _check(lib().yv_svo_device_packed_copy(self._h, int(device), C.byref(nr), C.byref(nl), None, None, None))
+        recs = np.zeros((nr.value, 4), np.uint32); leaves = np.zeros(nl.value, np.uint32); nd = np.zeros(nr.value, np.uint32)
+        _check(lib().yv_svo_device_packed_copy(self._h, int(device), None, None, recs.ctypes.data_as(C.c_void_p),
+                                               leaves.ctypes.data_as(C.c_void_p), nd.ctypes.data_as(C.c_void_p)))
+        return recs, leaves, nd
 
     def Upload(self, device=0):                           # CudaSVO::Update
         _check(lib().yv_svo_upload(self._h, int(device)))

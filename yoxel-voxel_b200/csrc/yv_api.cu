@@ -7,6 +7,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -18,6 +19,7 @@
 #include "dynamic_svo.h"
 #include "svo_host.h"
 #include "svo_pack.h"
+#include "svo_pack_gpu.h"
 
 namespace {
 
@@ -37,6 +39,8 @@ struct DeviceSVO {
   uint32_t *leaves = nullptr;
   uint32_t *node_data = nullptr;      // uploaded on first use of the LOD cut-off
   size_t n_recs = 0, n_leaves = 0;
+  bool root_null = true;
+  int levels = 0;
   uint32_t packed_version = 0;        // scene edit version the packed copy was made from
   // raw mirror of the reference-layout pool, kept in step page by page (CudaSVO::Update)
   yv_vox_node *raw = nullptr;
@@ -125,8 +129,14 @@ void free_packed_device(DeviceSVO &d) {
 
 // CudaSVO::Update (demo/SVORenderer.cpp:33-53; paging: reaction/report/main.tex:71): bring the device's raw
 // mirror of the pool up to date by copying only the 256-node pages written since the last call.
+int sync_raw_locked(yv_svo *svo, int device, DeviceSVO **out, uint64_t *bytes_out);
+
 int sync_raw(yv_svo *svo, int device, DeviceSVO **out, uint64_t *bytes_out) {
   std::lock_guard<std::mutex> lock(svo->mu);
+  return sync_raw_locked(svo, device, out, bytes_out);
+}
+
+int sync_raw_locked(yv_svo *svo, int device, DeviceSVO **out, uint64_t *bytes_out) {
   YV_CUDA(cudaSetDevice(device));
   DeviceSVO &d = svo->dev[device];
   if (svo->dyn.page_versions().empty() && !svo->host.nodes.empty()) svo->dyn.adopt_existing();
@@ -157,26 +167,57 @@ int sync_raw(yv_svo *svo, int device, DeviceSVO **out, uint64_t *bytes_out) {
   return YV_OK;
 }
 
+// The device copy of the packed pool. Default: ship the raw pool (page-wise, sync_raw) and re-lay it out on the
+// GPU (svo_pack_gpu.cu); YV_HOST_PACK=1, or a pool that is not a tree, uses the host BFS of svo_pack.cpp.
 int ensure_uploaded(yv_svo *svo, int device, DeviceSVO **out) {
   std::lock_guard<std::mutex> lock(svo->mu);
-  int rc = ensure_packed(svo);
-  if (rc) return rc;
+  const uint32_t want = svo->dyn.version();
   auto it = svo->dev.find(device);
-  if (it != svo->dev.end() && it->second.recs && it->second.packed_version != svo->packed_version)
+  if (it != svo->dev.end() && it->second.recs && it->second.packed_version != want)
     free_packed_device(it->second);               // the scene was edited since this copy was made
   if (it == svo->dev.end() || !it->second.recs) {
     YV_CUDA(cudaSetDevice(device));
-    DeviceSVO d = it == svo->dev.end() ? DeviceSVO() : it->second;
-    d.packed_version = svo->packed_version;
-    d.n_recs = svo->packed.records.size();
-    d.n_leaves = svo->packed.leaves.size();
-    YV_CUDA(cudaMalloc(&d.recs, std::max<size_t>(1, d.n_recs) * sizeof(uint4)));
-    YV_CUDA(cudaMalloc(&d.leaves, std::max<size_t>(1, d.n_leaves) * sizeof(uint32_t)));
-    if (d.n_recs)
-      YV_CUDA(cudaMemcpy(d.recs, svo->packed.records.data(), d.n_recs * sizeof(uint4), cudaMemcpyHostToDevice));
-    if (d.n_leaves)
-      YV_CUDA(cudaMemcpy(d.leaves, svo->packed.leaves.data(), d.n_leaves * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    svo->dev[device] = d;
+    const char *host_env = std::getenv("YV_HOST_PACK");
+    bool done = false;
+    if (!(host_env && host_env[0] == '1') && !svo->host.nodes.empty()) {
+      DeviceSVO *d = nullptr;
+      const bool had_raw = it != svo->dev.end() && it->second.raw != nullptr;
+      int rc = sync_raw_locked(svo, device, &d, nullptr);
+      if (rc) return rc;
+      yv::DevicePacked dp; std::string err;
+      if (yv::pack_svo_on_device(d->raw, svo->host.nodes.size(), svo->host.root, dp, err) == 0) {
+        if (dp.levels > yv::kMaxStack + 1) {
+          cudaFree(dp.recs); cudaFree(dp.leaves); cudaFree(dp.node_data);
+          return fail(YV_ERR_FORMAT, "tree deeper than the traversal stack supports");
+        }
+        d->recs = (uint4 *)dp.recs; d->leaves = dp.leaves; d->node_data = dp.node_data;
+        d->n_recs = dp.n_recs; d->n_leaves = dp.n_leaves; d->levels = dp.levels;
+        d->root_null = YV_IS_NULL(svo->host.root);
+        if (!d->recs) {                            // null root: keep valid (dummy) pointers
+          YV_CUDA(cudaMalloc(&d->recs, sizeof(uint4))); YV_CUDA(cudaMalloc(&d->leaves, sizeof(uint32_t)));
+        }
+        d->packed_version = want;
+        done = true;
+      }
+      if (!had_raw) { cudaFree(d->raw); d->raw = nullptr; d->raw_capacity = 0; d->raw_version = 0; }   // only needed for the repack
+      if (!done && err.find("not a tree") == std::string::npos) return fail(YV_ERR_FORMAT, err);
+    }
+    if (!done) {
+      int rc = ensure_packed(svo);
+      if (rc) return rc;
+      DeviceSVO &d = svo->dev[device];
+      d.n_recs = svo->packed.records.size();
+      d.n_leaves = svo->packed.leaves.size();
+      d.root_null = svo->packed.root_null;
+      d.levels = (int)svo->packed.level_start.size() - 1;
+      YV_CUDA(cudaMalloc(&d.recs, std::max<size_t>(1, d.n_recs) * sizeof(uint4)));
+      YV_CUDA(cudaMalloc(&d.leaves, std::max<size_t>(1, d.n_leaves) * sizeof(uint32_t)));
+      if (d.n_recs)
+        YV_CUDA(cudaMemcpy(d.recs, svo->packed.records.data(), d.n_recs * sizeof(uint4), cudaMemcpyHostToDevice));
+      if (d.n_leaves)
+        YV_CUDA(cudaMemcpy(d.leaves, svo->packed.leaves.data(), d.n_leaves * sizeof(uint32_t), cudaMemcpyHostToDevice));
+      d.packed_version = want;
+    }
     it = svo->dev.find(device);
   }
   if (out) *out = &it->second;
@@ -339,7 +380,7 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
     p.root_index = p.root_valid ? r->svo->host.root : 0u;
   } else {
     p.recs = ds->recs; p.leaves = ds->leaves;
-    p.root_valid = r->svo->packed.root_null ? 0u : 1u;
+    p.root_valid = ds->root_null ? 0u : 1u;
   }
   p.smem_nodes = raw ? 0u : (uint32_t)std::min<size_t>((size_t)std::max(0, r->opt_smem_nodes), ds->n_recs);
   for (int i = 0; i < 3; ++i) p.pos[i] = r->pos[i];
@@ -382,6 +423,7 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
   const bool lod = r->detail_coef > 0.0f;
   if (lod) {
     if (!raw && !ds->node_data) {
+      { std::lock_guard<std::mutex> lock(r->svo->mu); int prc = ensure_packed(r->svo); if (prc) return prc; }
       const std::vector<uint32_t> &nd = r->svo->packed.node_data;
       YV_CUDA(cudaMalloc(&ds->node_data, std::max<size_t>(1, nd.size()) * sizeof(uint32_t)));
       if (!nd.empty()) YV_CUDA(cudaMemcpy(ds->node_data, nd.data(), nd.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -580,6 +622,22 @@ uint64_t yv_svo_device_bytes(const yv_svo *svo, int device) {
   if (it == svo->dev.end()) return 0;
   return (uint64_t)it->second.n_recs * 16u + (uint64_t)it->second.n_leaves * 4u +
          (it->second.node_data ? (uint64_t)it->second.n_recs * 4u : 0u);
+}
+
+// device-side packed arrays copied back (tests: the GPU repack must equal the host repack bit for bit)
+int yv_svo_device_packed_copy(yv_svo *svo, int device, uint32_t *n_records, uint32_t *n_leaves,
+                              uint32_t *records_out, uint32_t *leaves_out, uint32_t *node_data_out) {
+  if (!svo) return fail(YV_ERR_ARG, "null scene");
+  DeviceSVO *d = nullptr;
+  int rc = ensure_uploaded(svo, device, &d);
+  if (rc) return rc;
+  if (n_records) *n_records = (uint32_t)d->n_recs;
+  if (n_leaves) *n_leaves = (uint32_t)d->n_leaves;
+  YV_CUDA(cudaSetDevice(device));
+  if (records_out && d->n_recs) YV_CUDA(cudaMemcpy(records_out, d->recs, d->n_recs * 16, cudaMemcpyDeviceToHost));
+  if (leaves_out && d->n_leaves) YV_CUDA(cudaMemcpy(leaves_out, d->leaves, d->n_leaves * 4, cudaMemcpyDeviceToHost));
+  if (node_data_out && d->n_recs && d->node_data) YV_CUDA(cudaMemcpy(node_data_out, d->node_data, d->n_recs * 4, cudaMemcpyDeviceToHost));
+  return YV_OK;
 }
 
 int yv_svo_packed_counts(yv_svo *svo, uint32_t *records, uint32_t *leaves) {
@@ -974,7 +1032,7 @@ int yv_trace_rays(yv_renderer *r, const float *pos, const float *dir, uint32_t c
       yv::trace_rays_kernel<true><<<grid, 128, 0, r->stream>>>(reinterpret_cast<const uint4 *>(ds->raw), nullptr, valid,
                                                                valid ? r->svo->host.root : 0u, d_pos, d_dir, count, d_node, d_child, d_t);
     } else {
-      yv::trace_rays_kernel<false><<<grid, 128, 0, r->stream>>>(ds->recs, ds->leaves, r->svo->packed.root_null ? 0u : 1u, 0u,
+      yv::trace_rays_kernel<false><<<grid, 128, 0, r->stream>>>(ds->recs, ds->leaves, ds->root_null ? 0u : 1u, 0u,
                                                                 d_pos, d_dir, count, d_node, d_child, d_t);
     }
     e = cudaGetLastError();
