@@ -111,6 +111,16 @@ def test_small_edit_touches_few_pages_of_a_large_scene():
     assert svo.livenodes >= svo.nodecount - 1000
 
 
+def test_null_flags_are_recomputed_on_import():
+    """A pool whose derived null flags are missing (e.g. written by another tool) is normalised on import, so the
+    raw-layout kernel, which trusts them, cannot chase a null child id."""
+    nodes, root, leaf = scenes.two_level_tree()
+    nodes["flags"] &= 0xFF                       # drop every null flag
+    svo = yv.SVOData.FromNodes(root, nodes)
+    fixed = svo.nodes()
+    assert (fixed["flags"] >> 8 & 0xFF).tolist() == [0x7F, 0xFE]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("sec", [None, dict(shadow=1, ao_samples=2, seed=5, light_pos=(0.6, 0.4, 1.2), voxel_size=1.0 / 1024, ao_max_t=0.05)],
                          ids=["primary", "secondary"])

@@ -37,6 +37,7 @@ int load_vox(const char *path, HostSVO &out, std::string &err) {
   size_t got = count ? std::fread(out.nodes.data(), sizeof(yv_vox_node), count, f) : 0;
   std::fclose(f);
   if (got != count) { err = "truncated .vox node array"; out.nodes.clear(); return -3; }
+  normalize_flags(out);
   return validate(out, err);
 }
 
@@ -50,6 +51,17 @@ int save_vox(const char *path, const HostSVO &svo, std::string &err) {
   ok = (std::fclose(f) == 0) && ok;
   if (!ok) { err = "write failed"; return -2; }
   return 0;
+}
+
+// The null flags (bits 8..15) are derived data; the raw-layout kernel trusts them, so pools that come from a file or
+// from the caller get them recomputed from the child words (top bit set and not a leaf = null, main.tex:40-42,62).
+void normalize_flags(HostSVO &svo) {
+  for (yv_vox_node &nd : svo.nodes) {
+    uint32_t nulls = 0;
+    for (int c = 0; c < 8; ++c)
+      if (!YV_LEAF_FLAG(nd.flags, c) && YV_IS_NULL(nd.child[c])) nulls |= 1u << (8 + c);
+    nd.flags = (nd.flags & ~0xff00u) | nulls;
+  }
 }
 
 int validate(const HostSVO &svo, std::string &err) {

@@ -24,6 +24,9 @@ struct HostSVO {
 int load_vox(const char *path, HostSVO &out, std::string &err);
 int save_vox(const char *path, const HostSVO &svo, std::string &err);
 
+// Recompute the derived null flags (bits 8..15) from the child words.
+void normalize_flags(HostSVO &svo);
+
 // Structural validation: root and every non-leaf, non-null child id must index the pool.
 int validate(const HostSVO &svo, std::string &err);
 

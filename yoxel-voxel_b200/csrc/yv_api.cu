@@ -581,6 +581,7 @@ int yv_svo_from_memory(yv_node_id root, const yv_vox_node *nodes, uint32_t count
   yv_svo *s = new yv_svo;
   s->host.root = root;
   s->host.nodes.assign(nodes, nodes + count);
+  yv::normalize_flags(s->host);
   std::string err;
   if (yv::validate(s->host, err)) { delete s; return fail(YV_ERR_FORMAT, err); }
   *out = s;
