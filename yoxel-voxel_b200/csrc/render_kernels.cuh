@@ -65,6 +65,9 @@ constexpr int kCtaThreads = 128;
 #ifndef YV_MINBLOCKS
 #define YV_MINBLOCKS 8                 // __launch_bounds__ residency target (register cap = 65536 / (128 * this))
 #endif
+#ifndef YV_WARP_W
+#define YV_WARP_W 8                    // pixels per warp: 8x4 (4 = 4x8, 16 = 16x2); 8x4 measured best (profiles/README.md)
+#endif
 #ifndef YV_STEPS_PER_VOTE
 #define YV_STEPS_PER_VOTE 4            // lean_steps between two warp votes on "anyone still traversing?"
 #endif
@@ -217,8 +220,10 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_frame(const 
     const int warp = threadIdx.x >> 5;
     const int tiles_x16 = (p.width + 15) >> 4;
     const int tx = blockIdx.x % tiles_x16, ty = blockIdx.x / tiles_x16;
-    x = tx * 16 + (warp & 1) * 8 + (lane & 7);
-    y = tile_row_y(p, ty) + (warp >> 1) * 4 + (lane >> 3);
+    // warp footprint YV_WARP_W x (32 / YV_WARP_W) pixels inside the CTA's 16x8 tile
+    constexpr int kWW = YV_WARP_W, kWH = 32 / YV_WARP_W, kWarpsX = 16 / YV_WARP_W;
+    x = tx * 16 + (warp % kWarpsX) * kWW + (lane % kWW);
+    y = tile_row_y(p, ty) + (warp / kWarpsX) * kWH + (lane / kWW);
     if (x < p.width && y < p.y1) state = kLaneNew;
   }
 
