@@ -25,8 +25,10 @@
 
 #if defined(__CUDACC__)
 #define YV_HD __host__ __device__ __forceinline__
+#elif defined(YV_TEST_HOST_BUILD)
+#define YV_HD inline          // tests/emu only: checks the state machine against the oracle without a GPU
 #else
-#define YV_HD inline
+#error "trace_core.cuh is device code; a host build exists only for tests/emu (define YV_TEST_HOST_BUILD there)"
 #endif
 
 #if defined(__CUDA_ARCH__)
