@@ -5,12 +5,18 @@
 // RGBA8 store (:54,:67) — the reference CUDA path's InitEyeRays / Trace / ShadeSimple sequence
 // (demo/SVORenderer.cpp:95-149, trace_cuda.py:20-23) collapsed into one launch.
 //
-// render_frame<SEC, COUNT, STACK, PERSISTENT, STAGED> is one warp-synchronous state machine:
+// Kernels in this file:
+//   render_frame<SEC, COUNT, STACK, PERSISTENT, STAGED, LOD, RAW>   the renderer (default: all false / local stack)
+//   render_queue, render_sec_queue                                   measured alternatives (see below), off by default
+//   shade_pass                                                       ShadeSimple pass for Phong lights / show-normals
+//   trace_rays_kernel<RAW>                                           DynamicSVO::TraceRay, batched
+//
+// render_frame is one warp-synchronous state machine:
 //   * every lane owns one pixel at a time; a pixel's rays (primary, then shadow and AO samples when
 //     SEC) are stages of the lane's state, so secondary rays re-enter the same traversal loop
 //     instead of running as divergent tails, and ray set-up / shading run batched over many lanes;
-//   * the traversal loop is flat: each iteration every live lane performs one lean_step
-//     (trace_core.cuh) — test the current child, then one sibling step or one (descend | pop);
+//   * the traversal loop is flat: each trip every live lane performs one lean_step (trace_core.cuh) —
+//     up to two sibling steps, then one (descend | pop); the warp votes every kStepsPerVote trips;
 //   * PERSISTENT = false: one CTA per 16x8 pixel tile, one pixel per lane (8x4 pixels per warp);
 //     PERSISTENT = true : resident CTAs; each warp pulls 8x8-pixel tiles from an atomic counter and
 //     re-fills idle lanes (ballot + popc prefix) once <= refill_threshold lanes are still traversing;
@@ -19,7 +25,11 @@
 //     126 MB L2 + L1 already serve these records (L1 hit rate 94 % without staging) and the extra
 //     branch costs issue slots, so the default is smem_nodes = 0; the knob stays for ablation;
 //   * STACK selects where the explicit traversal stack lives: local memory, or a 4-entry
-//     shared-memory ring for the hot top of the stack that spills to local memory.
+//     shared-memory ring for the hot top of the stack that spills to local memory;
+//   * LOD: SetDetailCoef cut-off; RAW: traverse the reference's 40-byte pool (scenes under edit).
+// What the measurements say (profiles/README.md): the kernel is instruction-issue bound, and lanes of a warp
+// that descend in lock-step share their node fetches. Every schedule that fills idle lanes by de-synchronising
+// them (PERSISTENT refill, render_queue, render_sec_queue) executes fewer instructions and still loses.
 #pragma once
 
 #include <cuda_runtime.h>
