@@ -111,6 +111,34 @@ def test_small_edit_touches_few_pages_of_a_large_scene():
     assert svo.livenodes >= svo.nodecount - 1000
 
 
+def test_scene_scripts(tmp_path):
+    """tools/gen_spheres.py and tools/gen_largevol.py (the reference's scene scripts on this library)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "spheres.vox")
+    subprocess.check_call([sys.executable, os.path.join(root, "tools", "gen_spheres.py"), "8", out], stdout=subprocess.DEVNULL)
+    a, b = yv.SVOData().Load(out), yv.SVOData.SphereFractal(8)
+    assert a.nodecount == b.nodecount
+    assert (_img(a, 96, 96, scenes.CAMERAS[1][1:])["rgba"] == _img(b, 96, 96, scenes.CAMERAS[1][1:])["rgba"]).all()
+    out2 = str(tmp_path / "vol.vox")
+    subprocess.check_call([sys.executable, os.path.join(root, "tools", "gen_largevol.py"), "--level", "7", "--out", out2],
+                          stdout=subprocess.DEVNULL)
+    assert yv.SVOData().Load(out2).nodecount == yv.SVOData.IsoVolume(7).nodecount
+    # and through MakeIsoSource bricks, as the original does
+    bricks = tmp_path / "bricks"
+    bricks.mkdir()
+    z, y, x = np.mgrid[0:128, 0:256, 0:256]
+    vol = np.clip(260 - 3 * np.sqrt((x - 128.0) ** 2 + (y - 128.0) ** 2 + (z - 64.0) ** 2), 0, 255).astype(np.uint8)
+    vol.tofile(str(bricks / ("d_0219_%04d" % (3 * 64))))
+    out3 = str(tmp_path / "ct.vox")
+    subprocess.check_call([sys.executable, os.path.join(root, "tools", "gen_largevol.py"), "--bricks", str(bricks), "--out", out3],
+                          stdout=subprocess.DEVNULL)
+    ct = yv.SVOData().Load(out3)
+    assert ct.nodecount > 100
+
+
 def test_null_flags_are_recomputed_on_import():
     """A pool whose derived null flags are missing (e.g. written by another tool) is normalised on import, so the
     raw-layout kernel, which trusts them, cannot chase a null child id."""

@@ -415,3 +415,17 @@ def test_8k_frame_sampled_bands():
         out[rows] = part[rows]
     assert (out == img).all()
     r.close()
+
+
+def test_cuda_renderer_mirror_of_trace_cuda_py():
+    """CudaRenderer (trace_cuda.py:16-118): constructor, updateScene, setLightPos, render -> stats, getImage."""
+    cr = yv.CudaRenderer(res=(320, 240))
+    cr.updateScene(scenes.fractal(9))
+    assert cr.getViewSize() == (320, 240) and cr.detailCoef == 10.0
+    stat = cr.render((0.5, 0.5, 0.3), (-1, -1, 1.5))
+    assert "gpu time:" in stat and "eye trace time:" in stat and "detailCoef: 10.0" in stat
+    img = cr.getImage()
+    assert img.shape == (240, 320, 3) and img.any()
+    cr.detailCoef = 1.0                         # coarser LOD -> a different picture
+    cr.render((0.5, 0.5, 0.3), (-1, -1, 1.5))
+    assert (cr.getImage() != img).any()

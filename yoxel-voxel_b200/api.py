@@ -15,7 +15,7 @@ import numpy as np
 __all__ = [
     "YVError", "lib", "lib_path", "SVOData", "SVORenderer", "CreateB200Renderer",
     "pack_voxdata", "device_count", "init_ray_dir", "BuildMode", "VoxelSource",
-    "MakeSphereSource", "MakeRawSource", "MakeIsoSource", "DynamicSVO", "LightParams", "NODE_DTYPE", "EMPTY_NODE", "FULL_NODE",
+    "MakeSphereSource", "MakeRawSource", "MakeIsoSource", "DynamicSVO", "LightParams", "CudaRenderer", "NODE_DTYPE", "EMPTY_NODE", "FULL_NODE",
 ]
 
 EMPTY_NODE = 0x80000000
@@ -541,6 +541,52 @@ class SVORenderer:
 
 
 DynamicSVO = SVOData     # the scripts' name for the editable scene (ore/src/main.cpp:119)
+
+
+class CudaRenderer:
+    """The pycuda host class of the reference (trace_cuda.py:16-118) over this library: same constructor, methods
+    and `detailCoef` / `lightPos` attributes, so qtview.py-style callers keep working. `render` returns the same kind
+    of statistics string; the three kernels it used to launch (InitEyeRays, Trace, ShadeSimple) are one fused launch."""
+
+    FOV = 70.0
+
+    def __init__(self, res=(640, 480), device=0):
+        self._r = SVORenderer(device)
+        self.resx, self.resy = int(res[0]), int(res[1])          # (trace_cuda.py rounds to its block size; not needed here)
+        self._r.SetResolution(self.resx, self.resy)
+        self._r.SetFOV(self.FOV)
+        self.setLightPos((0.5, 0.5, 1))                         # trace_cuda.py:48
+        self.detailCoef = 10.0                                   # trace_cuda.py:49
+        self._img = None
+
+    def updateScene(self, scene):                                # trace_cuda.py:51
+        self._scene = scene
+        self._r.SetScene(scene)
+
+    def setLightPos(self, pos):                                  # trace_cuda.py:63
+        self.lightPos = tuple(float(v) for v in pos)
+
+    def getViewSize(self):                                       # trace_cuda.py:66
+        return (self.resx, self.resy)
+
+    def render(self, eyePos, viewDir, first=False):              # trace_cuda.py:69
+        import time
+        self._r.SetViewPos(eyePos); self._r.SetViewDir(viewDir); self._r.SetViewUp((0, 0, 1))
+        # trace_cuda.py:93 passes an angular threshold of (1 degree / detailCoef) per node; the same angle in
+        # SetDetailCoef's unit (rad(fov/2)/width per unit coefficient):
+        ang = np.radians(1.0) / max(self.detailCoef, 1e-6)
+        self._r.SetDetailCoef(float(ang * self.resx / np.radians(self.FOV / 2)))
+        self._r.SetLigth(0, LightParams(True, self.lightPos, (0.9, 0.9, 0.9), (0.0, 0.0, 0.0), (1, 0, 0)))
+        t = time.perf_counter()
+        self._img = self._r.RenderFrame()
+        gpu = time.perf_counter() - t
+        stat = "gpu time: %.2f ms\n" % (gpu * 1000)
+        stat += "eye trace time: %.2f ms\n" % self._r.LastFrameMs()
+        stat += "detailCoef: %f\n" % (self.detailCoef)
+        return stat
+
+    def getImage(self):                                          # trace_cuda.py:117
+        return None if self._img is None else self._img[..., :3]
 
 
 def CreateB200Renderer(device=0):
