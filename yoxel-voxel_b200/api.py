@@ -586,7 +586,7 @@ class CudaRenderer:
         return stat
 
     def getImage(self):                                          # trace_cuda.py:117
-        return None if self._img is None else self._img[..., :3]
+        return None if self._img is None else self._img[..., :3].copy()      # (d_img.get() copies as well)
 
 
 def CreateB200Renderer(device=0):
