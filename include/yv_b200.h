@@ -149,7 +149,10 @@ int yv_set_rows(yv_renderer *r, int y0, int y1);
 int yv_set_interleave(yv_renderer *r, int band_rows, int stride, int phase);
 
 /* Secondary rays (BASELINE config 4). shadow: 0/1; ao_samples: 0..16. light_pos is used for
- * the Lambert term and the shadow ray when shadow != 0 (otherwise the light rides on the eye). */
+ * the Lambert term and the shadow ray when shadow != 0 (otherwise the light rides on the eye).
+ * A shadow ray is occluded by a hit closer than the light, an AO ray by a hit closer than ao_max_t; both are
+ * traced with that range limit (the traversal meets cells front to back, so it stops at the first cell entered
+ * beyond the limit — same outcome as tracing to the end, far fewer node visits). */
 int yv_set_secondary(yv_renderer *r, int shadow, int ao_samples, uint32_t seed,
                      const float light_pos[3], float voxel_size, float ao_max_t);
 

@@ -129,6 +129,10 @@ typedef struct {
   uint32_t dir_flags;
   int front_only;        /* 0 = reference behaviour; 1 = secondary rays: a leaf counts only
                             if its own min(t2) > 0 (no hits behind the origin)              */
+  float tlimit;          /* secondary rays: range limit (shadow: distance to the light, AO: ao_max_t). Cells are
+                            met in non-decreasing entry parameter, so the ray ends as a miss at the first child
+                            entered at t >= tlimit; the outcome (occluded within the limit or not) is unchanged */
+  int abort;
   float detail;          /* rp.detailCoef (demo/SVORenderer.cpp:104); 0 = off. A child node whose
                             cube is smaller than detail * entry distance is not entered: it is the
                             hit, child = -1, shaded with VoxNode::data (SVORenderer.cpp:176-179)  */
@@ -149,6 +153,7 @@ static int rec_trace(trace_ctx *c, yv_node_id id, v3 t1, v3 t2, int level) {
   int ch = find_first_child(&t1, &t2);                      /* :24 */
   for (;;) {
     int cc = ch ^ (int)c->dir_flags;
+    if (c->front_only && max3(t1) >= c->tlimit) { c->abort = 1; return 0; }
     c->iters++;
     if (YV_LEAF_FLAG(node->flags, cc) && (!c->front_only || min3(t2) > 0)) {   /* :27 */
       c->node = id; c->child = cc; c->t = max3(t1);         /* :29-31 */
@@ -165,6 +170,7 @@ static int rec_trace(trace_ctx *c, yv_node_id id, v3 t1, v3 t2, int level) {
         }
       }
       if (rec_trace(c, kid, t1, t2, level + 1)) return 1;                /* :35 */
+      if (c->abort) return 0;
     }
     if (!go_next(&ch, &t1, &t2)) return 0;                  /* :38 */
   }
@@ -172,6 +178,7 @@ static int rec_trace(trace_ctx *c, yv_node_id id, v3 t1, v3 t2, int level) {
 
 static int trace_ray(trace_ctx *c, yv_node_id root, v3 pos, v3 dir) {
   v3 t1, t2;
+  c->abort = 0;
   dir = adjust_dir(dir);
   if (!setup_trace(pos, dir, &t1, &t2, &c->dir_flags)) return 0;
   return rec_trace(c, root, t1, t2, 0);
@@ -365,6 +372,7 @@ static void *render_strip(void *arg) {
             if (len > 0) {
               v3 sd = { Lv.x / len, Lv.y / len, Lv.z / len };
               j->stats.rays++;
+              c.tlimit = len;
               if (trace_ray(&c, j->root, O, sd) && c.t > 0 && c.t < len) vis = 0.0f;
             }
           }
@@ -379,6 +387,7 @@ static void *render_strip(void *arg) {
               if (l2 < 1e-6f) { D.x = n[0]; D.y = n[1]; D.z = n[2]; }
               else { float l = sqrtf(l2); D.x /= l; D.y /= l; D.z /= l; }
               j->stats.rays++;
+              c.tlimit = sec->ao_max_t;
               if (trace_ray(&c, j->root, O, D) && c.t > 0 && c.t < sec->ao_max_t) occ++;
             }
             ao = 1.0f - (float)occ / (float)sec->ao_samples;

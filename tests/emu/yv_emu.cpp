@@ -44,11 +44,13 @@ struct HostFetch {
 };
 
 bool trace(const HostFetch &fetch, bool root_valid, HostStack &stk, float ox, float oy, float oz,
-           float dx, float dy, float dz, bool front_only, RayState &s, Rec &rec, uint64_t &steps) {
+           float dx, float dy, float dz, bool front_only, RayState &s, Rec &rec, uint64_t &steps,
+           float tlimit = __builtin_huge_valf()) {
   dx = adjust_dir1(dx); dy = adjust_dir1(dy); dz = adjust_dir1(dz);
   if (g_mode == 2) {
     LeanState ls;
     if (!lean_begin(ls, fetch, root_valid, ox, oy, oz, dx, dy, dz)) return false;
+    ls.tlimit = tlimit;
     for (;;) {
       ++steps;
       const int r = g_detail > 0.0f ? lean_step<true>(ls, fetch, g_lean_stack, front_only, g_detail)
@@ -114,7 +116,7 @@ extern "C" int yve_render(const uint32_t *records, const uint32_t *leaves, int r
           if (shadow) {
             const float vx = YV_FSUB(light[0], Ox), vy = YV_FSUB(light[1], Oy), vz = YV_FSUB(light[2], Oz);
             const float len = YV_FSQRT(YV_FADD(YV_FADD(YV_FMUL(vx, vx), YV_FMUL(vy, vy)), YV_FMUL(vz, vz)));
-            if (len > 0 && trace(fetch, root_valid != 0, stk, Ox, Oy, Oz, YV_FDIV(vx, len), YV_FDIV(vy, len), YV_FDIV(vz, len), true, s2, r2, steps)) {
+            if (len > 0 && trace(fetch, root_valid != 0, stk, Ox, Oy, Oz, YV_FDIV(vx, len), YV_FDIV(vy, len), YV_FDIV(vz, len), true, s2, r2, steps, len)) {
               const float ts = max3f(s2.t1x, s2.t1y, s2.t1z);
               if (ts > 0 && ts < len) vis = 0.0f;
             }
@@ -124,7 +126,7 @@ extern "C" int yve_render(const uint32_t *records, const uint32_t *leaves, int r
             for (int k = 0; k < ao_samples; ++k) {
               float ax, ay, az;
               ao_direction(nx, ny, nz, pixel, (uint32_t)k, seed, ax, ay, az);
-              if (trace(fetch, root_valid != 0, stk, Ox, Oy, Oz, ax, ay, az, true, s2, r2, steps)) {
+              if (trace(fetch, root_valid != 0, stk, Ox, Oy, Oz, ax, ay, az, true, s2, r2, steps, ao_max_t)) {
                 const float ts = max3f(s2.t1x, s2.t1y, s2.t1z);
                 if (ts > 0 && ts < ao_max_t) ++occ;
               }

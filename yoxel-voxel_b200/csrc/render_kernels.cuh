@@ -355,8 +355,10 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_frame(const 
           }
           rx = adjust_dir1(rx); ry = adjust_dir1(ry); rz = adjust_dir1(rz);
           stk.reset();
-          if (lean_begin(s, fetch, p.root_valid != 0u, Ox, Oy, Oz, rx, ry, rz))
+          if (lean_begin(s, fetch, p.root_valid != 0u, Ox, Oy, Oz, rx, ry, rz)) {
+            s.tlimit = stage == 1 ? slen : p.ao_max_t;
             launched = true;          // otherwise this secondary ray misses outright: unoccluded
+          }
         }
         if (launched) state = kLaneActive;
         else {
@@ -467,7 +469,7 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_queue(const 
         s.t1z = __uint_as_float(slots[2 * kQueueRays + cur]); s.Tx = __uint_as_float(slots[3 * kQueueRays + cur]);
         s.Ty = __uint_as_float(slots[4 * kQueueRays + cur]);  s.Tz = __uint_as_float(slots[5 * kQueueRays + cur]);
         const uint32_t w = slots[6 * kQueueRays + cur];
-        s.ch = w & 7u; s.flags = w >> 3; s.idx = 0u; s.sp = 0; s.pend = 0u;
+        s.ch = w & 7u; s.flags = w >> 3; s.idx = 0u; s.sp = 0; s.pend = 0u; s.tlimit = __builtin_huge_valf();
         s.masks = root_masks; s.child_base = root_child_base;
         stk.reset();
         lean_eval_next(s);
@@ -623,7 +625,7 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_sec_queue(co
     slen = YV_FSQRT(YV_FADD(YV_FADD(YV_FMUL(vx, vx), YV_FMUL(vy, vy)), YV_FMUL(vz, vz)));
     if (slen > 0) {
       const float rx = adjust_dir1(YV_FDIV(vx, slen)), ry = adjust_dir1(YV_FDIV(vy, slen)), rz = adjust_dir1(YV_FDIV(vz, slen));
-      if (lean_begin(s, fetch, root_valid, Ox, Oy, Oz, rx, ry, rz)) state = kLaneActive;
+      if (lean_begin(s, fetch, root_valid, Ox, Oy, Oz, rx, ry, rz)) { s.tlimit = slen; state = kLaneActive; }
     }
   }
   run_lockstep(true);
@@ -676,7 +678,7 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_sec_queue(co
             s.t1x = __uint_as_float(slots[0 * kAoQueueRays + slot]); s.t1y = __uint_as_float(slots[1 * kAoQueueRays + slot]);
             s.t1z = __uint_as_float(slots[2 * kAoQueueRays + slot]); s.Tx = __uint_as_float(slots[3 * kAoQueueRays + slot]);
             s.Ty = __uint_as_float(slots[4 * kAoQueueRays + slot]);  s.Tz = __uint_as_float(slots[5 * kAoQueueRays + slot]);
-            s.ch = w & 7u; s.flags = (w >> 3) & 7u; s.idx = 0u; s.sp = 0; s.pend = 0u; s.level = 0u;
+            s.ch = w & 7u; s.flags = (w >> 3) & 7u; s.idx = 0u; s.sp = 0; s.pend = 0u; s.level = 0u; s.tlimit = p.ao_max_t;
             s.masks = root_masks; s.child_base = root_child_base;
             lean_eval_next(s);
             if (COUNT) { atomicAdd(&vis_cnt[owner], 1u); }

@@ -180,6 +180,9 @@ struct LeanState {
   uint32_t masks, child_base;
   uint32_t pend;         // exit axis (one-hot) of a sibling step chosen but not yet applied; 0 = none
   uint32_t level;        // depth of the current node (root = 0); only maintained when LOD is on
+  float tlimit;          // secondary rays: nothing at or beyond this ray parameter matters (shadow: distance to
+                         // the light, AO: ao_max_t); cells are met in non-decreasing entry parameter, so the ray
+                         // ends as a miss at the first child entered at t >= tlimit. +inf for primary rays.
   int sp;
 };
 
@@ -244,7 +247,7 @@ YV_HD bool lean_setup_root(LeanState &s, const bool root_valid,
   if (!setup_trace(px, py, pz, dx, dy, dz, r)) return false;
   if (!root_valid || fminf(fminf(r.t2x, r.t2y), r.t2z) <= 0.0f) return false;
   s.t1x = r.t1x; s.t1y = r.t1y; s.t1z = r.t1z; s.Tx = r.t2x; s.Ty = r.t2y; s.Tz = r.t2z;
-  s.flags = r.flags; s.sp = 0; s.idx = 0u; s.pend = 0u; s.level = 0u;
+  s.flags = r.flags; s.sp = 0; s.idx = 0u; s.pend = 0u; s.level = 0u; s.tlimit = __builtin_huge_valf();
   lean_first_child(s);
   return true;
 }
@@ -284,6 +287,7 @@ YV_HD int lean_step(LeanState &s, const Fetch &fetch, Stack &stk, const bool fro
   for (int k = 0;; ++k) {
     lean_apply_step(s, s.pend);                                    // deferred GoNext (no-op when pend == 0)
     s.pend = 0u;
+    if (front_only && fmaxf(fmaxf(s.t1x, s.t1y), s.t1z) >= s.tlimit) return kStepMiss;      // secondary rays: range limit
     bit = 1u << (s.ch ^ s.flags);
     const bool xy = s.Tx > s.Ty;
     const bool nz = xy ? (s.Ty < s.Tz) : (s.Tx < s.Tz);
