@@ -103,7 +103,7 @@ struct yv_renderer {
   int opt_smem_nodes = 0;             // records staged in shared memory (585 = four levels)
   int opt_persistent = 0;
   int opt_refill = 20;                // persistent schedule: refill when <= this many lanes are live
-  int opt_sec_threshold = 16;         // secondary rays: serve waiting lanes when <= this many lanes are traversing (-1 = only when drained)
+  int opt_sec_threshold = -1;         // secondary rays: serve waiting lanes when <= this many lanes are traversing (-1 = only when the warp has drained: best once the rays are range-limited)
   int opt_sec_queue = 0;              // 1 = AO rays pooled per warp (render_sec_queue); measured slower than the per-lane stage machine (6.31 vs 5.60 ms on config 4)
   int opt_layout = 0;                 // 0 = packed records (static scenes), 1 = raw reference pool (scenes under edit)
   int opt_stack = 0;                  // yv::kStackLocal / kStackRing4
