@@ -26,7 +26,7 @@ def main():
     ap.add_argument("--refill", default="20")
     ap.add_argument("--layout", default="0")
     ap.add_argument("--sec-threshold", default="-1")
-    ap.add_argument("--sec-queue", default="1")
+    ap.add_argument("--sec-queue", default="0")
     ap.add_argument("--detail", type=float, default=0.0)
     ap.add_argument("--secondary", action="store_true")
     ap.add_argument("--scene", default="fractal", choices=["fractal", "iso"])
