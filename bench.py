@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--detail", type=float, default=0.0,
                     help="SVORenderer::SetDetailCoef LOD cut-off (0 = off, the CPU tracer's behaviour; the CUDA demo used 1.0)")
+    ap.add_argument("--ssna", action="store_true",
+                    help="SetSSNA: BlurZ x5 + normals from the z-buffer (demo/SVORenderer.cpp:126-147); one GPU")
     ap.add_argument("--flythrough", action="store_true",
                     help="tiles partition: move the camera every step (BASELINE config 5: 64-frame flythrough)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -161,14 +163,15 @@ def workload_name(a):
     scene = "gen_spheres sphere-fractal SVO" if a.scene == "fractal" else "gen_largevol-style synthetic iso-volume SVO (seed 219, iso 200)"
     return ("%s depth %d, %dx%d primary rays + Lambert%s%s" %
             (scene, a.depth, a.width, a.height, " + shadow + 4 AO" if a.secondary else "",
-             ", LOD detailCoef %g" % a.detail if a.detail > 0 else ""))
+             ", LOD detailCoef %g" % a.detail if a.detail > 0 else "") + (" + SSNA (z-buffer BlurZ x5)" if a.ssna else ""))
 
 
 def oracle_frame(svo_nodes, root, a, frame, threads, want_visits=False):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import yvo
     pos, d = camera_for(frame)
-    cam = yvo.camera(pos, d, UP, FOV, a.width, a.height, detail_coef=a.detail)
+    cam = yvo.camera(pos, d, UP, FOV, a.width, a.height, detail_coef=a.detail, ssna=a.ssna,
+                     ssna_voxel_size=1.0 / (1 << a.depth))
     sec = None
     if a.secondary:
         sec = yvo.secondary(shadow=1, ao_samples=4, seed=1, light_pos=(0.6, 0.4, 1.2),
@@ -262,6 +265,8 @@ def main():
     r.SetResolution(a.width, a.height)
     r.SetViewUp(UP); r.SetFOV(FOV)
     r.SetDetailCoef(a.detail)
+    if a.ssna:
+        r.SetSSNA(True, 1.0 / (1 << a.depth))
     if a.secondary:
         r.SetSecondary(shadow=1, ao_samples=4, seed=1, light_pos=(0.6, 0.4, 1.2),
                        voxel_size=1.0 / (1 << a.depth), ao_max_t=0.05)
@@ -384,6 +389,7 @@ def main():
             dist.barrier()                          # the batch on GPU 0 is complete once every rank has stored
     sync_all()
     wall1 = time.time()
+    launches_per_step = r.LastFrameLaunches()       # 1 (trace); 8 with SSNA (z, 5 x BlurZ, ShadeSimple)
     clocks = sampler.stop(wall0, wall1) if sampler else None
     step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
@@ -485,7 +491,7 @@ def main():
                    "gather": gather, "flythrough": bool(a.flythrough), "hit_fraction": round(hit_frac, 4)},
         "frame_ms": 1e3 * total_s / a.steps, "rays_per_step": rays_step,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
-        "gpu_launches": a.steps * world, "e2e_gpu_launches_per_step": r.LastFrameLaunches(), "parity": parity,
+        "gpu_launches": a.steps * world * launches_per_step, "e2e_gpu_launches_per_step": r.LastFrameLaunches(), "parity": parity,
     }
     print(json.dumps(line))
     if world > 1:

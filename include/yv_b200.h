@@ -124,6 +124,16 @@ int yv_set_light(yv_renderer *r, int index, const yv_light *light);
 /* SetShowNormals / GetShowNormals (demo/SVORenderer.h:31-32): write the unpacked normal as the colour */
 int yv_set_show_normals(yv_renderer *r, int enable);
 int yv_get_show_normals(const yv_renderer *r, int *enable);
+/* SetSSNA / GetSSNA (demo/SVORenderer.h:28-29; Demo.cpp:204): screen-space normal approximation. The frame's
+ * view-space z-buffer is blurred five times (SVORenderer::Render, demo/SVORenderer.cpp:126-141) and every hit pixel is
+ * shaded (Lambert, Phong or show-normals as selected above) with the normal rebuilt from it instead of the voxel's
+ * stored normal; arithmetic in yv_format.h "SSNA". Primary-ray frames only, whole frame on one device: a frame call
+ * with a row band or an interleaved partition set returns YV_ERR_ARG. The reference constructs with SSNA on
+ * (demo/SVORenderer.cpp:15); this handle starts with it off so that the default frame is ISVORenderer's.
+ * yv_set_ssna_voxel_size replaces the hard-coded voxSize = 1/2048 of demo/SVORenderer.cpp:129 (0 restores it). */
+int yv_set_ssna(yv_renderer *r, int enable);
+int yv_get_ssna(const yv_renderer *r, int *enable);
+int yv_set_ssna_voxel_size(yv_renderer *r, float voxel_size);
 int yv_get_detail_coef(const yv_renderer *r, float *coef);
 
 /* const Color32* RenderFrame()  (cell/svorenderer.h:23): synchronous; *rgba aliases

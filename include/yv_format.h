@@ -114,6 +114,31 @@ typedef struct yv_vox_node {
  *   acc_ch += att * ((diffuse_i.ch * ndl) * c_ch + (specular_i.ch * spec) * 255)
  * starting from acc_ch = YV_SHADE_AMBIENT * c_ch; out_ch = (uint8) min(255, floorf(acc_ch + 0.5f)); alpha 255.
  * SetShowNormals (demo/SVORenderer.h:31): out_ch = (uint8) floorf((n_ch * 0.5f + 0.5f) * 255.0f + 0.5f).      */
+/* SSNA — screen-space normal approximation (SetSSNA / GetSSNA, demo/SVORenderer.h:28-29). The host sequence is
+ * demo/SVORenderer.cpp:55-79 (Gaussian taps) and :126-147 (Trace, BlurZ x5 on ping-pong z-buffers, ShadeSimple);
+ * the BlurZ / ShadeSimple kernel bodies and BlurZKernSize are absent. Restated (float32, no FMA, in this order)
+ * from that sequence and from the prototype's normal reconstruction (demo/dumps/ztools.py:23-44):
+ *   z-buffer  z0[p] = hit ? t * ((d.x*f.x + d.y*f.y) + d.z*f.z) : 0     d = the pixel's adjusted unit ray,
+ *             f = normalized(viewDir). A pixel is "valid" iff its z != 0.
+ *   taps      K = YV_BLURZ_KERN, h = (float)(K/2), scale = 2; rows y then columns x:
+ *             tx = scale*((float)x - h)/h ; ty likewise ; tx = tx*tx ; ty = ty*ty ;
+ *             v[y][x] = (float)exp(-(double)(tx + ty)) ; sum += v[y][x] ; afterwards w[y][x] = v[y][x] / sum.
+ *   pass i    (i = 0..4) blurSize = 3 + 3*i ; pixelAng = (fov * (float)(pi/180)) / W ;
+ *             zlimit = (5*voxSize) / (pixelAng * blurSize) ; voxSize = 1/2048 in the reference (:129), settable here.
+ *             dst[p] = 0 if src[p] is invalid, else acc / wacc, where, over the taps q = p + (kx - K/2, ky - K/2)
+ *             in row-major (ky, kx) order that lie inside the frame, are valid and have |src[q] - src[p]| < zlimit:
+ *             acc = acc + w*src[q] ; wacc = wacc + w.
+ *   normal    z = blurred value at p ; d2 = 2*da (da from InitRayDir) ;
+ *             fx = z[x+1,y] - z ; bx = z - z[x-1,y], each defined only if that neighbour is inside the frame and valid;
+ *             dx = both defined ? (|fx| < |bx| ? fx : bx) : the defined one, else 0 ; dy likewise with rows y+1 / y-1 ;
+ *             nvx = (d2*dx)*z ; nvy = (d2*dy)*z ; nvz = -((d2*d2)*(z*z)) ; len = sqrt((nvx*nvx + nvy*nvy) + nvz*nvz) ;
+ *             len > 0: n_c = ((right_c*nvx + down_c*nvy) + fwd_c*nvz) / len with right = normalized(fwd x up),
+ *             down = -(right x fwd) ; otherwise (or z invalid) n = the voxel's stored normal.
+ *   shading   the Lambert / Phong / show-normals formulas above with this n ; P still uses the unblurred t.
+ * SSNA needs the whole frame on one device (the taps reach 15 rows beyond any band).                            */
+#define YV_BLURZ_KERN 7
+#define YV_BLURZ_PASSES 5
+#define YV_SSNA_VOXEL_SIZE (1.0f / 2048.0f)
 #define YV_MAX_LIGHTS 4
 #define YV_SPECULAR_EXP 10
 typedef struct yv_light {            /* LightParams (demo/Demo.cpp:141-147) */

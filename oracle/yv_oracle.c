@@ -304,9 +304,123 @@ static v3 hash_unit_vector(uint32_t key) {
   return up;
 }
 
+/* ---- SSNA (spec: include/yv_format.h "SSNA") ------------------------------------------------ */
+
+/* SVORenderer::InitBlur (demo/SVORenderer.cpp:55-79) */
+void yvo_blur_taps(float *taps) {
+  const int K = YV_BLURZ_KERN;
+  float h = (float)(K / 2);
+  float scale = 2.0f;
+  float sum = 0;
+  for (int y = 0; y < K; ++y)
+    for (int x = 0; x < K; ++x) {
+      float tx = scale * ((float)x - h) / h;
+      float ty = scale * ((float)y - h) / h;
+      tx = tx * tx;
+      ty = ty * ty;
+      float v = (float)exp(-(double)(tx + ty));
+      taps[y * K + x] = v;
+      sum += v;
+    }
+  for (int i = 0; i < K * K; ++i) taps[i] /= sum;
+}
+
+static void blur_pass(const float *taps, const float *src, float *dst, int W, int H, float zlimit) {
+  const int K = YV_BLURZ_KERN, h = K / 2;
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      float zc = src[(size_t)y * W + x];
+      float out = 0.0f;
+      if (zc != 0.0f) {
+        float acc = 0.0f, wacc = 0.0f;
+        for (int ky = 0; ky < K; ++ky) {
+          int qy = y + ky - h;
+          if (qy < 0 || qy >= H) continue;
+          for (int kx = 0; kx < K; ++kx) {
+            int qx = x + kx - h;
+            if (qx < 0 || qx >= W) continue;
+            float zq = src[(size_t)qy * W + qx];
+            if (zq == 0.0f || !(fabsf(zq - zc) < zlimit)) continue;
+            float w = taps[ky * K + kx];
+            acc = acc + w * zq;
+            wacc = wacc + w;
+          }
+        }
+        out = wacc > 0 ? acc / wacc : zc;
+      }
+      dst[(size_t)y * W + x] = out;
+    }
+}
+
+/* the BlurZ loop of SVORenderer::Render (demo/SVORenderer.cpp:126-141) */
+int yvo_blur_z(const yvo_camera *cam, const float *z0, float *out) {
+  const int W = cam->width, H = cam->height;
+  float taps[YV_BLURZ_KERN * YV_BLURZ_KERN];
+  yvo_blur_taps(taps);
+  float *buf[2];
+  buf[0] = (float *)malloc((size_t)W * H * sizeof(float));
+  buf[1] = (float *)malloc((size_t)W * H * sizeof(float));
+  if (!buf[0] || !buf[1]) { free(buf[0]); free(buf[1]); return -1; }
+  memcpy(buf[0], z0, (size_t)W * H * sizeof(float));
+  const float vox = cam->ssna_voxel_size > 0 ? cam->ssna_voxel_size : YV_SSNA_VOXEL_SIZE;
+  const float pixel_ang = (cam->fov_deg * (float)(3.14159265358979323846 / 180.0)) / (float)W;   /* :105 */
+  int src = 0;
+  float blur_size = 3;
+  for (int i = 0; i < YV_BLURZ_PASSES; ++i) {
+    float zlimit = (5.0f * vox) / (pixel_ang * blur_size);
+    blur_pass(taps, buf[src], buf[1 - src], W, H, zlimit);
+    src = 1 - src;
+    blur_size += 3;
+  }
+  memcpy(out, buf[src], (size_t)W * H * sizeof(float));
+  free(buf[0]); free(buf[1]);
+  return 0;
+}
+
+/* camera basis as InitRayDir builds it (cell/renderer_base.h:52-54) */
+static void view_basis(const yvo_camera *cam, v3 *fwd, v3 *right, v3 *down, float *d2) {
+  *fwd = v3_normalized(v3_from(cam->dir));
+  *right = v3_normalized(v3_cross(*fwd, v3_from(cam->up)));
+  v3 up = v3_cross(*right, *fwd);
+  down->x = -up.x; down->y = -up.y; down->z = -up.z;
+  float half_rad = (cam->fov_deg / 2) * (float)(3.14159265358979323846 / 180.0);
+  float da = (float)(tan((double)half_rad) / (double)cam->width);
+  *d2 = 2.0f * da;
+}
+
+static inline float abs_min_diff(int has_f, float f, int has_b, float b) {      /* ztools.py:21-22,33-34 */
+  if (has_f && has_b) return fabsf(f) < fabsf(b) ? f : b;
+  if (has_f) return f;
+  if (has_b) return b;
+  return 0.0f;
+}
+
+/* normal from the z-buffer (demo/dumps/ztools.py:23-44), turned to face the camera, in world space */
+int yvo_ssna_normal(const yvo_camera *cam, const float *zb, int32_t x, int32_t y, float n[3]) {
+  const int W = cam->width, H = cam->height;
+  const float z = zb[(size_t)y * W + x];
+  if (z == 0.0f) return 0;
+  v3 fwd, right, down; float d2;
+  view_basis(cam, &fwd, &right, &down, &d2);
+  float zr = x + 1 < W ? zb[(size_t)y * W + x + 1] : 0.0f, zl = x > 0 ? zb[(size_t)y * W + x - 1] : 0.0f;
+  float zd = y + 1 < H ? zb[(size_t)(y + 1) * W + x] : 0.0f, zu = y > 0 ? zb[(size_t)(y - 1) * W + x] : 0.0f;
+  float dx = abs_min_diff(zr != 0.0f, zr - z, zl != 0.0f, z - zl);
+  float dy = abs_min_diff(zd != 0.0f, zd - z, zu != 0.0f, z - zu);
+  float nvx = (d2 * dx) * z;
+  float nvy = (d2 * dy) * z;
+  float nvz = -((d2 * d2) * (z * z));
+  float len = sqrtf((nvx * nvx + nvy * nvy) + nvz * nvz);
+  if (!(len > 0)) return 0;
+  n[0] = ((right.x * nvx + down.x * nvy) + fwd.x * nvz) / len;
+  n[1] = ((right.y * nvx + down.y * nvy) + fwd.y * nvz) / len;
+  n[2] = ((right.z * nvx + down.z * nvy) + fwd.z * nvz) / len;
+  return 1;
+}
+
 typedef struct {
   const yv_vox_node *nodes; uint32_t count; yv_node_id root;
   const yvo_camera *cam; const yvo_secondary *sec; yvo_raydir rdd;
+  uint32_t *ssna_data; float *ssna_t, *ssna_z;     /* SSNA: per-pixel VoxData, t and view-space z of the hit */
   int32_t y0, y1;
   uint32_t *hit_node; int32_t *hit_child; float *hit_t; uint8_t *rgba; uint32_t *visits;
   yvo_stats stats;
@@ -346,6 +460,11 @@ static void *render_strip(void *arg) {
         j->stats.hits++;
         yv_vox_data data = hc < 0 ? j->nodes[hn].data : j->nodes[hn].child[hc];   /* :67; LOD: node.data */
         float dd[3] = { d.x, d.y, d.z };
+        if (j->ssna_z) {                                   /* Trace leaves RayData + z (demo/SVORenderer.cpp:118-126) */
+          v3 f = v3_normalized(v3_from(j->cam->dir));
+          j->ssna_data[offs] = data; j->ssna_t[offs] = ht;
+          j->ssna_z[offs] = ht * ((d.x * f.x + d.y * f.y) + d.z * f.z);
+        }
         int any_light = 0;
         for (int li = 0; li < YV_MAX_LIGHTS; ++li) any_light |= j->cam->lights[li].enabled;
         if (!want_sec && (j->cam->show_normals || any_light)) {
@@ -423,6 +542,17 @@ int yvo_render(const yv_vox_node *nodes, uint32_t node_count, yv_node_id root,
   if (rows <= 0) { if (stats) memset(stats, 0, sizeof *stats); return 0; }
   if (threads > rows) threads = rows;
 
+  const int want_sec = sec && (sec->shadow || sec->ao_samples > 0);
+  const int ssna = cam->ssna && !want_sec && rgba;
+  uint32_t *ssna_data = NULL; float *ssna_t = NULL, *ssna_z = NULL, *ssna_zb = NULL;
+  if (ssna) {
+    if (y0 != 0 || y1 != cam->height) return -2;                 /* SSNA needs the whole frame */
+    size_t n = (size_t)cam->width * (size_t)cam->height;
+    ssna_data = (uint32_t *)calloc(n, 4); ssna_t = (float *)calloc(n, 4);
+    ssna_z = (float *)calloc(n, 4); ssna_zb = (float *)calloc(n, 4);
+    if (!ssna_data || !ssna_t || !ssna_z || !ssna_zb) { free(ssna_data); free(ssna_t); free(ssna_z); free(ssna_zb); return -1; }
+  }
+
   strip_job *jobs = (strip_job *)calloc((size_t)threads, sizeof(strip_job));
   pthread_t *tids = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
   yvo_raydir rdd;
@@ -435,6 +565,7 @@ int yvo_render(const yv_vox_node *nodes, uint32_t node_count, yv_node_id root,
     j->y1 = (i == threads - 1) ? y1 : y0 + ystep * (i + 1);
     j->hit_node = hit_node; j->hit_child = hit_child; j->hit_t = hit_t; j->rgba = rgba;
     j->visits = visits_per_ray;
+    j->ssna_data = ssna_data; j->ssna_t = ssna_t; j->ssna_z = ssna_z;
   }
   if (threads == 1) render_strip(&jobs[0]);
   else {
@@ -449,6 +580,31 @@ int yvo_render(const yv_vox_node *nodes, uint32_t node_count, yv_node_id root,
     }
   }
   free(jobs); free(tids);
+  if (ssna) {                       /* BlurZ x5, then ShadeSimple with the z-buffer (demo/SVORenderer.cpp:126-147) */
+    const int W = cam->width, H = cam->height;
+    int rc = yvo_blur_z(cam, ssna_z, ssna_zb);
+    const v3 pos = v3_from(cam->pos);
+    const v3 dir0 = v3_from(rdd.dir0), du = v3_from(rdd.du), dv = v3_from(rdd.dv);
+    int any_light = 0;
+    for (int li = 0; li < YV_MAX_LIGHTS; ++li) any_light |= cam->lights[li].enabled;
+    for (int y = 0; y < H && rc == 0; ++y)
+      for (int x = 0; x < W; ++x) {
+        size_t offs = (size_t)y * (size_t)W + (size_t)x;
+        if (rgba[4 * offs + 3] == 0) continue;                   /* miss */
+        yv_vox_data data = ssna_data[offs];
+        float ht = ssna_t[offs], n[3];
+        if (!yvo_ssna_normal(cam, ssna_zb, x, y, n)) yvo_unpack_normal(data, n);
+        v3 d = v3_add(v3_add(dir0, v3_scale(du, (float)x)), v3_scale(dv, (float)y));
+        d = adjust_dir(v3_normalized(d));
+        v3 P = { pos.x + d.x * ht, pos.y + d.y * ht, pos.z + d.z * ht };
+        uint8_t *px = rgba + 4 * offs;
+        if (cam->show_normals) shade_normal(n, px);
+        else if (any_light) shade_phong(data, n, P, pos, cam->lights, px);
+        else write_color(data, YV_SHADE_AMBIENT + YV_SHADE_DIFFUSE * (lambert(n, P, pos) * 1.0f), px);
+      }
+    free(ssna_data); free(ssna_t); free(ssna_z); free(ssna_zb);
+    if (rc) return rc;
+  }
   return 0;
 }
 

@@ -30,6 +30,8 @@ typedef struct yvo_camera {
   float detail_coef;  /* SVORenderer::SetDetailCoef (demo/SVORenderer.h:25); 0 = no LOD cut-off   */
   int32_t show_normals;             /* SetShowNormals (demo/SVORenderer.h:31)                     */
   yv_light lights[YV_MAX_LIGHTS];   /* SetLigth (demo/SVORenderer.h:34): any enabled light -> Phong */
+  int32_t ssna;                     /* SetSSNA (demo/SVORenderer.h:28): normals from the blurred z-buffer */
+  float ssna_voxel_size;            /* voxSize of demo/SVORenderer.cpp:129; 0 = the reference's 1/2048    */
 } yvo_camera;
 
 /* RayDirData{dir0,du,dv} (cell/renderer_base.h:50-61) */
@@ -83,6 +85,14 @@ int yvo_trace_ray(const yv_vox_node *nodes, uint32_t node_count, yv_node_id root
 void yvo_shade(yv_vox_data data, const float dir[3], float t,
                const float viewer[3], const float light[3], float visibility, uint8_t out_rgba[4]);
 void yvo_unpack_normal(yv_vox_data data, float n[3]);
+
+/* SSNA building blocks (spec: include/yv_format.h "SSNA"), exposed for unit tests.
+ * yvo_blur_taps: the K*K normalised Gaussian taps (demo/SVORenderer.cpp:55-79), row-major.
+ * yvo_blur_z: the five BlurZ passes (:126-141) from z0 into out (both width*height floats).
+ * yvo_ssna_normal: world-space normal at pixel (x,y) of a blurred z-buffer; returns 0 if undefined. */
+void yvo_blur_taps(float *taps);
+int yvo_blur_z(const yvo_camera *cam, const float *z0, float *out);
+int yvo_ssna_normal(const yvo_camera *cam, const float *z, int32_t x, int32_t y, float n[3]);
 
 /* SVOData::Load (cell/svodata.h:31-50). Caller frees *nodes with yvo_free. */
 int yvo_load_vox(const char *path, yv_node_id *root, uint32_t *count, yv_vox_node **nodes);

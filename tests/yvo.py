@@ -18,7 +18,8 @@ class Light(C.Structure):
 class Camera(C.Structure):
     _fields_ = [("pos", C.c_float * 3), ("dir", C.c_float * 3), ("up", C.c_float * 3),
                 ("fov_deg", C.c_float), ("width", C.c_int32), ("height", C.c_int32), ("detail_coef", C.c_float),
-                ("show_normals", C.c_int32), ("lights", Light * 4)]
+                ("show_normals", C.c_int32), ("lights", Light * 4),
+                ("ssna", C.c_int32), ("ssna_voxel_size", C.c_float)]
 
 
 class RayDir(C.Structure):
@@ -60,6 +61,12 @@ def lib():
         L.yvo_shade.restype = None
         L.yvo_unpack_normal.argtypes = [C.c_uint32, C.POINTER(C.c_float)]
         L.yvo_unpack_normal.restype = None
+        L.yvo_blur_taps.argtypes = [C.POINTER(C.c_float)]
+        L.yvo_blur_taps.restype = None
+        L.yvo_blur_z.argtypes = [C.POINTER(Camera), vp, vp]
+        L.yvo_blur_z.restype = C.c_int
+        L.yvo_ssna_normal.argtypes = [C.POINTER(Camera), vp, C.c_int32, C.c_int32, C.POINTER(C.c_float)]
+        L.yvo_ssna_normal.restype = C.c_int
         L.yvo_load_vox.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(vp)]
         L.yvo_load_vox.restype = C.c_int
         L.yvo_free.argtypes = [vp]
@@ -68,7 +75,8 @@ def lib():
     return _lib
 
 
-def camera(pos, dir, up=(0, 0, 1), fov=70.0, width=64, height=64, detail_coef=0.0, lights=None, show_normals=False):
+def camera(pos, dir, up=(0, 0, 1), fov=70.0, width=64, height=64, detail_coef=0.0, lights=None, show_normals=False,
+           ssna=False, ssna_voxel_size=0.0):
     c = Camera()
     c.pos[:] = [float(v) for v in pos]
     c.dir[:] = [float(v) for v in dir]
@@ -78,6 +86,8 @@ def camera(pos, dir, up=(0, 0, 1), fov=70.0, width=64, height=64, detail_coef=0.
     c.height = int(height)
     c.detail_coef = float(detail_coef)
     c.show_normals = 1 if show_normals else 0
+    c.ssna = 1 if ssna else 0
+    c.ssna_voxel_size = float(ssna_voxel_size)
     for i, lt in enumerate(lights or []):       # dicts: pos, diffuse, specular, attenuation (enabled implied)
         c.lights[i].enabled = 1 if lt.get("enabled", True) else 0
         c.lights[i].pos[:] = [float(v) for v in lt["pos"]]
@@ -156,6 +166,28 @@ def unpack_normal(data):
     n = (C.c_float * 3)()
     lib().yvo_unpack_normal(int(data), n)
     return np.array(n[:], np.float32)
+
+
+def blur_taps():
+    k = (C.c_float * 49)()
+    lib().yvo_blur_taps(k)
+    return np.array(k[:], np.float32).reshape(7, 7)
+
+
+def blur_z(cam, z0):
+    z0 = np.ascontiguousarray(z0, np.float32)
+    out = np.zeros_like(z0)
+    rc = lib().yvo_blur_z(C.byref(cam), z0.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return out
+
+
+def ssna_normal(cam, z, x, y):
+    """World-space SSNA normal at (x, y) of a blurred z-buffer, or None where it is undefined."""
+    z = np.ascontiguousarray(z, np.float32)
+    n = (C.c_float * 3)()
+    ok = lib().yvo_ssna_normal(C.byref(cam), z.ctypes.data_as(C.c_void_p), int(x), int(y), n)
+    return np.array(n[:], np.float32) if ok else None
 
 
 def load_vox(path):

@@ -116,6 +116,9 @@ def lib():
         "yv_set_light": (i32, [vp, i32, vp]),
         "yv_set_show_normals": (i32, [vp, i32]),
         "yv_get_show_normals": (i32, [vp, P(i32)]),
+        "yv_set_ssna": (i32, [vp, i32]),
+        "yv_get_ssna": (i32, [vp, P(i32)]),
+        "yv_set_ssna_voxel_size": (i32, [vp, f32]),
         "yv_set_detail_coef": (i32, [vp, f32]),
         "yv_get_detail_coef": (i32, [vp, P(f32)]),
         "yv_render_frame": (i32, [vp, P(vp)]),
@@ -430,6 +433,16 @@ class SVORenderer:
     def GetShowNormals(self):                             # demo/SVORenderer.h:32
         v = C.c_int()
         _check(lib().yv_get_show_normals(self._h, C.byref(v)))
+        return bool(v.value)
+
+    def SetSSNA(self, enable, voxel_size=None):           # demo/SVORenderer.h:28 (voxSize: SVORenderer.cpp:129)
+        _check(lib().yv_set_ssna(self._h, 1 if enable else 0))
+        if voxel_size is not None:
+            _check(lib().yv_set_ssna_voxel_size(self._h, float(voxel_size)))
+
+    def GetSSNA(self):                                    # demo/SVORenderer.h:29
+        v = C.c_int()
+        _check(lib().yv_get_ssna(self._h, C.byref(v)))
         return bool(v.value)
 
     def SetDetailCoef(self, coef):                        # demo/SVORenderer.h:25

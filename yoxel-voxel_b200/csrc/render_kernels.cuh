@@ -68,6 +68,19 @@ struct RenderParams {
   int shadow, ao_samples;      // secondary rays
   uint32_t seed;
   float voxel_size, ao_max_t;
+  // SSNA (SetSSNA, demo/SVORenderer.h:28): view-space z-buffer + the camera basis InitRayDir builds
+  int ssna;
+  float *zbuf;                 // ssna_z_pass: z0 out; shade_pass: the blurred z in; full-frame
+  float fwd[3], right[3], down[3], d2;   // down = -(right x fwd); d2 = 2*da
+};
+
+// BlurZ launch parameters (demo/SVORenderer.cpp:55-79,137): ping-pong buffers, zlimit, K*K Gaussian taps
+struct BlurParams {
+  const float *src;
+  float *dst;
+  int width, height;
+  float zlimit;
+  float taps[YV_BLURZ_KERN * YV_BLURZ_KERN];
 };
 
 constexpr unsigned kFullMask = 0xffffffffu;
@@ -738,6 +751,24 @@ __global__ void __launch_bounds__(256) shade_pass(const __grid_constant__ Render
   const float t = __uint_as_float(rec.y);
   float nx, ny, nz, dx, dy, dz;
   unpack_normal(rec.x, nx, ny, nz);
+  if (p.ssna) {                                           // normal from the blurred z-buffer (yv_format.h "SSNA")
+    const float z = p.zbuf[pixel];
+    if (z != 0.0f) {
+      const float zr = x + 1 < p.width ? p.zbuf[pixel + 1] : 0.0f, zl = x > 0 ? p.zbuf[pixel - 1] : 0.0f;
+      const float zd = y + 1 < p.height ? p.zbuf[pixel + p.width] : 0.0f, zu = y > 0 ? p.zbuf[pixel - p.width] : 0.0f;
+      const float ddx = abs_min_diff(zr != 0.0f, YV_FSUB(zr, z), zl != 0.0f, YV_FSUB(z, zl));
+      const float ddy = abs_min_diff(zd != 0.0f, YV_FSUB(zd, z), zu != 0.0f, YV_FSUB(z, zu));
+      const float nvx = YV_FMUL(YV_FMUL(p.d2, ddx), z);
+      const float nvy = YV_FMUL(YV_FMUL(p.d2, ddy), z);
+      const float nvz = -YV_FMUL(YV_FMUL(p.d2, p.d2), YV_FMUL(z, z));
+      const float len = YV_FSQRT(YV_FADD(YV_FADD(YV_FMUL(nvx, nvx), YV_FMUL(nvy, nvy)), YV_FMUL(nvz, nvz)));
+      if (len > 0.0f) {
+        nx = YV_FDIV(YV_FADD(YV_FADD(YV_FMUL(p.right[0], nvx), YV_FMUL(p.down[0], nvy)), YV_FMUL(p.fwd[0], nvz)), len);
+        ny = YV_FDIV(YV_FADD(YV_FADD(YV_FMUL(p.right[1], nvx), YV_FMUL(p.down[1], nvy)), YV_FMUL(p.fwd[1], nvz)), len);
+        nz = YV_FDIV(YV_FADD(YV_FADD(YV_FMUL(p.right[2], nvx), YV_FMUL(p.down[2], nvy)), YV_FMUL(p.fwd[2], nvz)), len);
+      }
+    }
+  }
   uint32_t rgba;
   if (p.shade_mode == 2) rgba = shade_normal(nx, ny, nz);
   else {
@@ -746,9 +777,88 @@ __global__ void __launch_bounds__(256) shade_pass(const __grid_constant__ Render
     const float Px = YV_FADD(p.pos[0], YV_FMUL(dx, t));
     const float Py = YV_FADD(p.pos[1], YV_FMUL(dy, t));
     const float Pz = YV_FADD(p.pos[2], YV_FMUL(dz, t));
-    rgba = shade_phong(rec.x, nx, ny, nz, Px, Py, Pz, p.pos, p.lights);
+    if (p.shade_mode == 1) rgba = shade_phong(rec.x, nx, ny, nz, Px, Py, Pz, p.pos, p.lights);
+    else {                                                // head-light Lambert with the SSNA normal
+      const float dl = lambert(nx, ny, nz, Px, Py, Pz, p.pos[0], p.pos[1], p.pos[2]);
+      rgba = shade_rgba(rec.x, YV_FADD(YV_SHADE_AMBIENT, YV_FMUL(YV_SHADE_DIFFUSE, YV_FMUL(dl, 1.0f))));
+    }
   }
   p.out_rgba[pixel] = rgba;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SSNA passes (SVORenderer::Render, demo/SVORenderer.cpp:126-147): the trace kernel leaves (VoxData, t) per hit
+// pixel; ssna_z_pass turns t into the view-space z-buffer, blur_z_pass runs five times on ping-pong buffers,
+// shade_pass (above) rebuilds the normal from the result. All three are HBM/L2 streaming passes over 4 B/pixel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ssna_z_pass(const __grid_constant__ RenderParams p) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= p.width || y >= p.height) return;
+  const uint32_t pixel = (uint32_t)y * (uint32_t)p.width + (uint32_t)x;
+  float z = 0.0f;
+  if (p.out_rgba[pixel] != 0u) {
+    const float t = __uint_as_float(p.shade_rec[pixel].y);
+    float dx, dy, dz;
+    primary_dir(p.dir0, p.du, p.dv, x, y, dx, dy, dz);
+    dx = adjust_dir1(dx); dy = adjust_dir1(dy); dz = adjust_dir1(dz);
+    z = YV_FMUL(t, YV_FADD(YV_FADD(YV_FMUL(dx, p.fwd[0]), YV_FMUL(dy, p.fwd[1])), YV_FMUL(dz, p.fwd[2])));
+  }
+  p.zbuf[pixel] = z;
+}
+
+// One BlurZ pass: a 32x32 output tile per CTA with its 3-pixel apron staged in shared memory (row pitch 39 words: a
+// warp's 32 consecutive columns never share a bank). A thread owns four vertically adjacent outputs and walks the ten
+// tile rows they touch once, so each staged value is read once per column offset instead of once per tap (70 LDS
+// for 196 taps). Invalid pixels are staged as +inf: |inf - zc| < zlimit is false, which folds the validity test into
+// the depth test. Per output the taps still arrive in row-major (ky, kx) order with separate multiply and add, so the
+// result matches the CPU statement bit for bit. 5 ALU instructions per tap: the pass is issue-bound, not HBM-bound
+// (245 instructions against 8 bytes per pixel).
+constexpr int kBlurTile = 32, kBlurApron = YV_BLURZ_KERN / 2, kBlurSpan = kBlurTile + 2 * kBlurApron, kBlurRows = 4;
+__global__ void __launch_bounds__(256) blur_z_pass(const __grid_constant__ BlurParams b) {
+  __shared__ float tile[kBlurSpan][kBlurSpan + 1];
+  const float kInvalid = __int_as_float(0x7f800000);
+  const int bx = blockIdx.x * kBlurTile, by = blockIdx.y * kBlurTile;
+  for (int i = threadIdx.x; i < kBlurSpan * kBlurSpan; i += 256) {
+    const int ty = i / kBlurSpan, tx = i - ty * kBlurSpan;
+    const int gx = bx + tx - kBlurApron, gy = by + ty - kBlurApron;
+    float v = 0.0f;                                       // outside the frame = invalid
+    if (gx >= 0 && gx < b.width && gy >= 0 && gy < b.height) v = b.src[(size_t)gy * b.width + gx];
+    tile[ty][tx] = v != 0.0f ? v : kInvalid;
+  }
+  __syncthreads();
+  const int lx = threadIdx.x & 31, gx = bx + lx;
+  const int ly = (threadIdx.x >> 5) * kBlurRows;           // first of this thread's four output rows
+  if (gx >= b.width || by + ly >= b.height) return;
+  float zc[kBlurRows], acc[kBlurRows], wacc[kBlurRows];
+#pragma unroll
+  for (int j = 0; j < kBlurRows; ++j) { zc[j] = tile[ly + j + kBlurApron][lx + kBlurApron]; acc[j] = 0.0f; wacc[j] = 0.0f; }
+#pragma unroll
+  for (int r = 0; r < kBlurRows + YV_BLURZ_KERN - 1; ++r) {           // tile row ly + r feeds output j as tap row ky = r - j
+    float zq[YV_BLURZ_KERN];
+#pragma unroll
+    for (int kx = 0; kx < YV_BLURZ_KERN; ++kx) zq[kx] = tile[ly + r][lx + kx];
+#pragma unroll
+    for (int j = 0; j < kBlurRows; ++j) {
+      const int ky = r - j;
+      if (ky < 0 || ky >= YV_BLURZ_KERN) continue;
+#pragma unroll
+      for (int kx = 0; kx < YV_BLURZ_KERN; ++kx) {
+        const float w = b.taps[ky * YV_BLURZ_KERN + kx];
+        const bool ok = fabsf(YV_FSUB(zq[kx], zc[j])) < b.zlimit;
+        acc[j] = ok ? YV_FADD(acc[j], YV_FMUL(w, zq[kx])) : acc[j];
+        wacc[j] = ok ? YV_FADD(wacc[j], w) : wacc[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kBlurRows; ++j) {
+    const int gy = by + ly + j;
+    if (gy >= b.height) break;
+    float out = 0.0f;
+    if (zc[j] != kInvalid) out = wacc[j] > 0.0f ? YV_FDIV(acc[j], wacc[j]) : zc[j];
+    b.dst[(size_t)gy * b.width + gx] = out;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -374,6 +374,13 @@ YV_HD float lambert(float nx, float ny, float nz, float Px, float Py, float Pz,
 }
 
 // colour * k -> RGBA8 word in memory order R,G,B,A (little-endian: R in bits 0..7)
+// dx / dy of the SSNA normal: the smaller-magnitude one-sided difference among the defined ones
+// (demo/dumps/ztools.py:21-22,33-34; spec in include/yv_format.h)
+YV_HD float abs_min_diff(bool has_f, float f, bool has_b, float b) {
+  if (has_f && has_b) return fabsf(f) < fabsf(b) ? f : b;
+  return has_f ? f : (has_b ? b : 0.0f);
+}
+
 YV_HD uint32_t shade_rgba(uint32_t data, float k) {
   const uint32_t r5 = (data >> 11) & 31u, g6 = (data >> 5) & 63u, b5 = data & 31u;
   const uint32_t c0 = (r5 << 3) | (r5 >> 2), c1 = (g6 << 2) | (g6 >> 4), c2 = (b5 << 3) | (b5 >> 2);

@@ -69,6 +69,10 @@ struct yv_renderer {
   float fov = 70.0f;
   yv_light lights[YV_MAX_LIGHTS] = {};   // SetLigth (demo/SVORenderer.h:34); any enabled light switches to Phong
   bool show_normals = false;          // SetShowNormals (demo/SVORenderer.h:31)
+  bool ssna = false;                  // SetSSNA (demo/SVORenderer.h:28); the reference defaults to true, off here so that
+                                      // the default frame is the CPU tracer's (ISVORenderer) image
+  float ssna_voxel_size = YV_SSNA_VOXEL_SIZE;   // voxSize of demo/SVORenderer.cpp:129
+  float blur_taps[YV_BLURZ_KERN * YV_BLURZ_KERN] = {};
   float detail_coef = 0.0f;           // SVORenderer::m_detailCoef (demo/SVORenderer.h:56); 0 = off
   int width = 0, height = 0;
   int y0 = 0, y1 = 0;
@@ -85,6 +89,7 @@ struct yv_renderer {
   uint32_t *d_hit_node = nullptr; int32_t *d_hit_child = nullptr; float *d_hit_t = nullptr;
   uint32_t *d_counters = nullptr;
   uint2 *d_shade_rec = nullptr;       // (VoxData, t) per pixel for the ShadeSimple pass
+  float *d_zbuf[2] = { nullptr, nullptr };   // m_zbuf[2] (demo/SVORenderer.cpp:85-86): BlurZ ping-pong
   unsigned int *d_tile_counter = nullptr;
   bool hits = false, counters = false;
   // launch
@@ -260,6 +265,7 @@ void free_frame_buffers(yv_renderer *r) {
   cudaFreeHost(r->h_fb); r->h_fb = nullptr;
   cudaFree(r->d_hit_node); cudaFree(r->d_hit_child); cudaFree(r->d_hit_t); cudaFree(r->d_counters);
   cudaFree(r->d_shade_rec); r->d_shade_rec = nullptr;
+  cudaFree(r->d_zbuf[0]); cudaFree(r->d_zbuf[1]); r->d_zbuf[0] = r->d_zbuf[1] = nullptr;
   r->d_hit_node = nullptr; r->d_hit_child = nullptr; r->d_hit_t = nullptr; r->d_counters = nullptr;
   r->fb_pixels = 0;
 }
@@ -284,8 +290,10 @@ int ensure_frame_buffers(yv_renderer *r) {
 
 // RendererBase::InitRayDir (cell/renderer_base.h:50-61), float32 with the cg:: operator order
 // (nest/include/geometry/primitives/point.h:416-440,462-499); tan evaluated in double, rounded once.
+struct ViewBasis { float fwd[3], right[3], down[3], d2; };   // SSNA: the frame InitRayDir builds; down = -up', d2 = 2*da
+
 void init_ray_dir_raw(const float vdir[3], const float vup[3], float fov, int width, int height,
-                      float dir0[3], float du[3], float dv[3]) {
+                      float dir0[3], float du[3], float dv[3], ViewBasis *basis = nullptr) {
   auto norm3 = [](const float v[3], float o[3]) {
     float d = 0.0f;
     d += v[0] * v[0]; d += v[1] * v[1]; d += v[2] * v[2];
@@ -311,10 +319,30 @@ void init_ray_dir_raw(const float vdir[3], const float vup[3], float fov, int wi
     const float b = (dv[i] * h) / 2.0f;
     dir0[i] = (fwd[i] - a) - b;
   }
+  if (basis) {
+    for (int i = 0; i < 3; ++i) { basis->fwd[i] = fwd[i]; basis->right[i] = right[i]; basis->down[i] = -upv[i]; }
+    basis->d2 = 2.0f * da;
+  }
 }
 
-void init_ray_dir(const yv_renderer *r, float dir0[3], float du[3], float dv[3]) {
-  init_ray_dir_raw(r->dir, r->up, r->fov, r->width, r->height, dir0, du, dv);
+// SVORenderer::InitBlur (demo/SVORenderer.cpp:55-79) with K = YV_BLURZ_KERN (spec: include/yv_format.h "SSNA")
+void init_blur_taps(float *taps) {
+  const int K = YV_BLURZ_KERN;
+  const float h = (float)(K / 2), scale = 2.0f;
+  float sum = 0.0f;
+  for (int y = 0; y < K; ++y)
+    for (int x = 0; x < K; ++x) {
+      float tx = scale * ((float)x - h) / h, ty = scale * ((float)y - h) / h;
+      tx = tx * tx; ty = ty * ty;
+      const float v = (float)std::exp(-(double)(tx + ty));
+      taps[y * K + x] = v;
+      sum += v;
+    }
+  for (int i = 0; i < K * K; ++i) taps[i] /= sum;
+}
+
+void init_ray_dir(const yv_renderer *r, float dir0[3], float du[3], float dv[3], ViewBasis *basis = nullptr) {
+  init_ray_dir_raw(r->dir, r->up, r->fov, r->width, r->height, dir0, du, dv, basis);
 }
 
 template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED, bool LOD = false, bool RAW = false>
@@ -414,8 +442,10 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
   }
   p.smem_nodes = raw ? 0u : (uint32_t)std::min<size_t>((size_t)std::max(0, r->opt_smem_nodes), ds->n_recs);
   for (int i = 0; i < 3; ++i) p.pos[i] = r->pos[i];
-  init_ray_dir(r, p.dir0, p.du, p.dv);
+  ViewBasis basis;
+  init_ray_dir(r, p.dir0, p.du, p.dv, &basis);
   const bool sec = r->shadow || r->ao_samples > 0;
+  const bool ssna = r->ssna && !sec;
   for (int i = 0; i < 3; ++i) p.light[i] = (sec && r->shadow) ? r->light[i] : r->pos[i];
   p.width = r->width; p.height = r->height;
   p.y0 = r->rows_set ? std::max(0, r->y0) : 0;
@@ -444,7 +474,16 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
   bool any_light = false;
   for (int i = 0; i < YV_MAX_LIGHTS; ++i) { p.lights[i] = r->lights[i]; any_light = any_light || r->lights[i].enabled; }
   p.shade_mode = sec ? 0 : (r->show_normals ? 2 : (any_light ? 1 : 0));
-  if (p.shade_mode != 0) {
+  if (ssna) {
+    if (p.y0 != 0 || p.y1 != r->height || r->il_stride > 1)
+      return fail(YV_ERR_ARG, "SSNA needs the whole frame on one device (clear yv_set_rows / yv_set_interleave)");
+    for (int i = 0; i < 2; ++i)
+      if (!r->d_zbuf[i]) YV_CUDA(cudaMalloc(&r->d_zbuf[i], std::max<size_t>(1, r->fb_pixels) * sizeof(float)));
+    p.ssna = 1;
+    for (int i = 0; i < 3; ++i) { p.fwd[i] = basis.fwd[i]; p.right[i] = basis.right[i]; p.down[i] = basis.down[i]; }
+    p.d2 = basis.d2;
+  }
+  if (p.shade_mode != 0 || ssna) {
     if (!r->d_shade_rec) YV_CUDA(cudaMalloc(&r->d_shade_rec, std::max<size_t>(1, r->fb_pixels) * sizeof(uint2)));
     p.shade_rec = r->d_shade_rec;
   }
@@ -502,7 +541,30 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
   }
   if (rc) return rc;
   int launches = 1;
-  if (p.shade_mode != 0 && p.num_tiles > 0) {       // ShadeSimple pass over the rows this launch rendered
+  if (ssna && p.num_tiles > 0) {                    // z-buffer, then BlurZ x5 (demo/SVORenderer.cpp:126-141)
+    dim3 zgrid((p.width + 31) / 32, (p.height + 7) / 8);
+    p.zbuf = r->d_zbuf[0];
+    yv::ssna_z_pass<<<zgrid, 256, 0, r->stream>>>(p);
+    ++launches;
+    yv::BlurParams b;
+    std::memcpy(b.taps, r->blur_taps, sizeof b.taps);
+    b.width = p.width; b.height = p.height;
+    const float pixel_ang = (r->fov * (float)(3.14159265358979323846 / 180.0)) / (float)r->width;    // rp.pixelAng (:105)
+    float blur_size = 3;
+    int src = 0;
+    dim3 bgrid((p.width + yv::kBlurTile - 1) / yv::kBlurTile, (p.height + yv::kBlurTile - 1) / yv::kBlurTile);
+    for (int i = 0; i < YV_BLURZ_PASSES; ++i) {
+      b.zlimit = (5.0f * r->ssna_voxel_size) / (pixel_ang * blur_size);
+      b.src = r->d_zbuf[src]; b.dst = r->d_zbuf[1 - src];
+      yv::blur_z_pass<<<bgrid, 256, 0, r->stream>>>(b);
+      ++launches;
+      src = 1 - src;
+      blur_size += 3;
+    }
+    YV_CUDA(cudaGetLastError());
+    p.zbuf = r->d_zbuf[src];
+  }
+  if ((p.shade_mode != 0 || ssna) && p.num_tiles > 0) {       // ShadeSimple pass over the rows this launch rendered
     dim3 grid((p.width + 31) / 32, p.num_tiles / p.tiles_x);
     yv::shade_pass<<<grid, 256, 0, r->stream>>>(p);
     YV_CUDA(cudaGetLastError());
@@ -740,6 +802,7 @@ int yv_renderer_create(int device, yv_renderer **out) {
   if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); yv_renderer_destroy(r); return fail(YV_ERR_CUDA, m); }
   r->stream = r->own_stream;
   r->width = 640; r->height = 480;            // renderer_base.h:25
+  init_blur_taps(r->blur_taps);               // InitBlur in the constructor (demo/SVORenderer.cpp:22)
   *out = r;
   return YV_OK;
 }
@@ -817,6 +880,22 @@ int yv_set_show_normals(yv_renderer *r, int enable) {
 int yv_get_show_normals(const yv_renderer *r, int *enable) {
   if (!r || !enable) return fail(YV_ERR_ARG, "null argument");
   *enable = r->show_normals ? 1 : 0;
+  return YV_OK;
+}
+int yv_set_ssna(yv_renderer *r, int enable) {
+  if (!r) return fail(YV_ERR_ARG, "null renderer");
+  r->ssna = enable != 0;
+  return YV_OK;
+}
+int yv_get_ssna(const yv_renderer *r, int *enable) {
+  if (!r || !enable) return fail(YV_ERR_ARG, "null argument");
+  *enable = r->ssna ? 1 : 0;
+  return YV_OK;
+}
+int yv_set_ssna_voxel_size(yv_renderer *r, float voxel_size) {
+  if (!r) return fail(YV_ERR_ARG, "null renderer");
+  if (!(voxel_size >= 0.0f)) return fail(YV_ERR_ARG, "voxel size must be >= 0");
+  r->ssna_voxel_size = voxel_size > 0.0f ? voxel_size : YV_SSNA_VOXEL_SIZE;
   return YV_OK;
 }
 int yv_set_detail_coef(yv_renderer *r, float coef) {
@@ -906,7 +985,8 @@ int yv_render_frame(yv_renderer *r, const uint8_t **rgba) {
   if (!r->svo) return fail(YV_ERR_NOSCENE, "no scene set");
   int rc = ensure_frame_buffers(r);
   if (rc) return rc;
-  if (r->opt_pipeline > 1 && !r->rows_set && r->il_stride == 1 && r->opt_persistent != 1 && r->height >= 256) {
+  const bool ssna = r->ssna && !(r->shadow || r->ao_samples > 0);      // BlurZ reaches across row chunks: one launch
+  if (r->opt_pipeline > 1 && !r->rows_set && r->il_stride == 1 && r->opt_persistent != 1 && r->height >= 256 && !ssna) {
     rc = render_frame_pipelined(r);
     if (rc) return rc;
     *rgba = r->h_fb;
