@@ -134,6 +134,15 @@ int yv_get_show_normals(const yv_renderer *r, int *enable);
 int yv_set_ssna(yv_renderer *r, int enable);
 int yv_get_ssna(const yv_renderer *r, int *enable);
 int yv_set_ssna_voxel_size(yv_renderer *r, float voxel_size);
+/* Hiding voxelisation artefacts (reaction/report/main.tex:107-114 — report text only, no code in the snapshot):
+ * yv_set_jitter displaces every primary ray's origin by `amplitude` (scene units; a voxel is 2^-depth) along a
+ * per-pixel hashed unit vector (arithmetic in yv_format.h); 0 switches it off. Primary-ray frames with the default
+ * schedule, stack and layout only (anything else: YV_ERR_ARG at the frame call).
+ * yv_render_accumulated draws `frames` frames with seeds seed, seed+1, ... and returns their per-channel integer mean
+ * ((sum + frames/2) / frames), the report's "average of several consecutive frames"; *rgba as for yv_render_frame.
+ * Row bands / interleave apply to the traced frames; the mean always covers the whole frame buffer. */
+int yv_set_jitter(yv_renderer *r, float amplitude, uint32_t seed);
+int yv_render_accumulated(yv_renderer *r, int frames, const uint8_t **rgba);
 int yv_get_detail_coef(const yv_renderer *r, float *coef);
 
 /* const Color32* RenderFrame()  (cell/svorenderer.h:23): synchronous; *rgba aliases

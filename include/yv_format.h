@@ -139,6 +139,17 @@ typedef struct yv_vox_node {
 #define YV_BLURZ_KERN 7
 #define YV_BLURZ_PASSES 5
 #define YV_SSNA_VOXEL_SIZE (1.0f / 2048.0f)
+
+/* Hiding voxelisation artefacts (reaction/report/main.tex:107-114; described in the report only, no code in the
+ * snapshot): (1) every traced ray starts from a randomly displaced origin, the displacement comparable to a voxel;
+ * (2) while the view is unchanged, consecutive frames drawn with different displacements are averaged. Restated:
+ *   origin    key = hash(pixel) ^ hash(seed ^ YV_JITTER_SALT) with pixel = y*W + x and hash = the lowbias32 mix of
+ *             the AO rays; U = the lattice-rejection unit vector of `key` (same generator as the AO rays);
+ *             O_c = pos_c + amplitude * U_c (mul, then add). The ray direction is the pixel's usual direction; the
+ *             shaded point is P = O + d*t; viewer and head light stay at pos.
+ *   average   frame k of n is drawn with seed + k; per channel out = (sum_k c_k + n/2) / n in integers (alpha too, so
+ *             a pixel hit in some frames only gets fractional coverage).                                           */
+#define YV_JITTER_SALT 0x6a09e667u
 #define YV_MAX_LIGHTS 4
 #define YV_SPECULAR_EXP 10
 typedef struct yv_light {            /* LightParams (demo/Demo.cpp:141-147) */

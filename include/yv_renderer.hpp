@@ -16,6 +16,7 @@
 
 #include <cstdint>
 #include <memory>
+#include <string>
 
 #include "yv_b200.h"
 
@@ -89,6 +90,17 @@ class B200Renderer : public YV_NS ISVORenderer {
   }
   // SVORenderer::Render(void* d_dstBuf) (demo/SVORenderer.h:36)
   bool Render(void *d_dst) { return r_ && yv_render_frame_device(r_, d_dst) == 0; }
+  // the remaining setters of the CUDA demo's SVORenderer (demo/SVORenderer.h:20-38)
+  void SetViewSize(int w, int h) { SetResolution(w, h); }                                        // :20
+  float GetFOV() const { float f = 0; if (r_) yv_get_fov(r_, &f); return f; }                    // :23
+  void SetDetailCoef(float coef) { if (r_) yv_set_detail_coef(r_, coef); }                       // :25
+  float GetDetailCoef() const { float c = 0; if (r_) yv_get_detail_coef(r_, &c); return c; }     // :26
+  void SetSSNA(bool enable) { if (r_) yv_set_ssna(r_, enable ? 1 : 0); }                         // :28
+  bool GetSSNA() const { int v = 0; if (r_) yv_get_ssna(r_, &v); return v != 0; }                // :29
+  void SetShowNormals(bool enable) { if (r_) yv_set_show_normals(r_, enable ? 1 : 0); }          // :31
+  bool GetShowNormals() const { int v = 0; if (r_) yv_get_show_normals(r_, &v); return v != 0; } // :32
+  void SetLigth(int i, const yv_light &lp) { if (r_) yv_set_light(r_, i, &lp); }                 // :34 (reference spelling)
+  void DumpTraceData(const std::string &fnbase) { if (r_) yv_dump_trace_data(r_, fnbase.c_str()); }   // :38
   float LastFrameMs() const { return r_ ? yv_last_frame_ms(r_) : -1.0f; }
   yv_renderer *handle() const { return r_; }
 

@@ -304,6 +304,15 @@ static v3 hash_unit_vector(uint32_t key) {
   return up;
 }
 
+/* displaced ray origin (reaction/report/main.tex:107-114; spec: include/yv_format.h) */
+static v3 jitter_origin(const yvo_camera *cam, size_t offs) {
+  v3 pos = v3_from(cam->pos);
+  if (!(cam->jitter_amp > 0)) return pos;
+  v3 U = hash_unit_vector(hash_u32((uint32_t)offs) ^ hash_u32(cam->jitter_seed ^ YV_JITTER_SALT));
+  v3 o = { pos.x + cam->jitter_amp * U.x, pos.y + cam->jitter_amp * U.y, pos.z + cam->jitter_amp * U.z };
+  return o;
+}
+
 /* ---- SSNA (spec: include/yv_format.h "SSNA") ------------------------------------------------ */
 
 /* SVORenderer::InitBlur (demo/SVORenderer.cpp:55-79) */
@@ -455,7 +464,8 @@ static void *render_strip(void *arg) {
       d = adjust_dir(d);                                                     /* :57 */
       j->stats.rays++;
       c.front_only = 0;
-      if (trace_ray(&c, j->root, pos, d)) {                                  /* :60-65 */
+      const v3 org = want_sec ? pos : jitter_origin(j->cam, offs);           /* main.tex:109 */
+      if (trace_ray(&c, j->root, org, d)) {                                  /* :60-65 */
         hn = c.node; hc = c.child; ht = c.t;
         j->stats.hits++;
         yv_vox_data data = hc < 0 ? j->nodes[hn].data : j->nodes[hn].child[hc];   /* :67; LOD: node.data */
@@ -470,11 +480,12 @@ static void *render_strip(void *arg) {
         if (!want_sec && (j->cam->show_normals || any_light)) {
           float n[3];
           yvo_unpack_normal(data, n);
-          v3 P = { pos.x + d.x * ht, pos.y + d.y * ht, pos.z + d.z * ht };
+          v3 P = { org.x + d.x * ht, org.y + d.y * ht, org.z + d.z * ht };
           if (j->cam->show_normals) shade_normal(n, px);
           else shade_phong(data, n, P, pos, j->cam->lights, px);
         } else if (!want_sec) {
-          yvo_shade(data, dd, ht, j->cam->pos, j->cam->pos, 1.0f, px);       /* light = eye (:33-34) */
+          float oo[3] = { org.x, org.y, org.z };
+          yvo_shade(data, dd, ht, oo, j->cam->pos, 1.0f, px);                /* light = eye (:33-34) */
         } else {
           float n[3];
           yvo_unpack_normal(data, n);
@@ -596,7 +607,8 @@ int yvo_render(const yv_vox_node *nodes, uint32_t node_count, yv_node_id root,
         if (!yvo_ssna_normal(cam, ssna_zb, x, y, n)) yvo_unpack_normal(data, n);
         v3 d = v3_add(v3_add(dir0, v3_scale(du, (float)x)), v3_scale(dv, (float)y));
         d = adjust_dir(v3_normalized(d));
-        v3 P = { pos.x + d.x * ht, pos.y + d.y * ht, pos.z + d.z * ht };
+        v3 org = jitter_origin(cam, offs);
+        v3 P = { org.x + d.x * ht, org.y + d.y * ht, org.z + d.z * ht };
         uint8_t *px = rgba + 4 * offs;
         if (cam->show_normals) shade_normal(n, px);
         else if (any_light) shade_phong(data, n, P, pos, cam->lights, px);

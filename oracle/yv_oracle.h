@@ -32,6 +32,8 @@ typedef struct yvo_camera {
   yv_light lights[YV_MAX_LIGHTS];   /* SetLigth (demo/SVORenderer.h:34): any enabled light -> Phong */
   int32_t ssna;                     /* SetSSNA (demo/SVORenderer.h:28): normals from the blurred z-buffer */
   float ssna_voxel_size;            /* voxSize of demo/SVORenderer.cpp:129; 0 = the reference's 1/2048    */
+  float jitter_amp;                 /* displaced ray origins (reaction/report/main.tex:107-114); 0 = off  */
+  uint32_t jitter_seed;
 } yvo_camera;
 
 /* RayDirData{dir0,du,dv} (cell/renderer_base.h:50-61) */

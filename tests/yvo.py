@@ -19,7 +19,8 @@ class Camera(C.Structure):
     _fields_ = [("pos", C.c_float * 3), ("dir", C.c_float * 3), ("up", C.c_float * 3),
                 ("fov_deg", C.c_float), ("width", C.c_int32), ("height", C.c_int32), ("detail_coef", C.c_float),
                 ("show_normals", C.c_int32), ("lights", Light * 4),
-                ("ssna", C.c_int32), ("ssna_voxel_size", C.c_float)]
+                ("ssna", C.c_int32), ("ssna_voxel_size", C.c_float),
+                ("jitter_amp", C.c_float), ("jitter_seed", C.c_uint32)]
 
 
 class RayDir(C.Structure):
@@ -76,7 +77,7 @@ def lib():
 
 
 def camera(pos, dir, up=(0, 0, 1), fov=70.0, width=64, height=64, detail_coef=0.0, lights=None, show_normals=False,
-           ssna=False, ssna_voxel_size=0.0):
+           ssna=False, ssna_voxel_size=0.0, jitter_amp=0.0, jitter_seed=1):
     c = Camera()
     c.pos[:] = [float(v) for v in pos]
     c.dir[:] = [float(v) for v in dir]
@@ -88,6 +89,8 @@ def camera(pos, dir, up=(0, 0, 1), fov=70.0, width=64, height=64, detail_coef=0.
     c.show_normals = 1 if show_normals else 0
     c.ssna = 1 if ssna else 0
     c.ssna_voxel_size = float(ssna_voxel_size)
+    c.jitter_amp = float(jitter_amp)
+    c.jitter_seed = int(jitter_seed)
     for i, lt in enumerate(lights or []):       # dicts: pos, diffuse, specular, attenuation (enabled implied)
         c.lights[i].enabled = 1 if lt.get("enabled", True) else 0
         c.lights[i].pos[:] = [float(v) for v in lt["pos"]]

@@ -119,6 +119,8 @@ def lib():
         "yv_set_ssna": (i32, [vp, i32]),
         "yv_get_ssna": (i32, [vp, P(i32)]),
         "yv_set_ssna_voxel_size": (i32, [vp, f32]),
+        "yv_set_jitter": (i32, [vp, f32, u32]),
+        "yv_render_accumulated": (i32, [vp, i32, P(vp)]),
         "yv_set_detail_coef": (i32, [vp, f32]),
         "yv_get_detail_coef": (i32, [vp, P(f32)]),
         "yv_render_frame": (i32, [vp, P(vp)]),
@@ -444,6 +446,16 @@ class SVORenderer:
         v = C.c_int()
         _check(lib().yv_get_ssna(self._h, C.byref(v)))
         return bool(v.value)
+
+    def SetJitter(self, amplitude, seed=1):               # reaction/report/main.tex:109 (displaced ray origins)
+        _check(lib().yv_set_jitter(self._h, float(amplitude), int(seed)))
+
+    def RenderAccumulated(self, frames):                  # reaction/report/main.tex:111 (mean of jittered frames)
+        """HxWx4 uint8 mean of `frames` frames drawn with seeds seed, seed+1, ... (view of renderer-owned memory)."""
+        px = C.c_void_p()
+        _check(lib().yv_render_accumulated(self._h, int(frames), C.byref(px)))
+        w, h = self.GetResolution()
+        return np.ctypeslib.as_array(C.cast(px, C.POINTER(C.c_uint8)), shape=(h, w, 4))
 
     def SetDetailCoef(self, coef):                        # demo/SVORenderer.h:25
         _check(lib().yv_set_detail_coef(self._h, float(coef)))

@@ -72,6 +72,9 @@ struct RenderParams {
   int ssna;
   float *zbuf;                 // ssna_z_pass: z0 out; shade_pass: the blurred z in; full-frame
   float fwd[3], right[3], down[3], d2;   // down = -(right x fwd); d2 = 2*da
+  // displaced ray origins (reaction/report/main.tex:107-114): 0 = off
+  float jitter_amp;
+  uint32_t jitter_seed;
 };
 
 // BlurZ launch parameters (demo/SVORenderer.cpp:55-79,137): ping-pong buffers, zlimit, K*K Gaussian taps
@@ -209,7 +212,7 @@ __device__ __forceinline__ int tile_row_y(const RenderParams &p, int ty) {
 
 enum : int { kLaneIdle = 0, kLaneActive = 1, kLaneHit = 2, kLaneMiss = 3, kLaneNew = 4, kLaneLodHit = 5 };
 
-template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED, bool LOD, bool RAW>
+template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED, bool LOD, bool RAW, bool JIT = false>
 __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_frame(const __grid_constant__ RenderParams p) {
   extern __shared__ uint4 smem[];
   uint4 *staged = smem;
@@ -285,7 +288,9 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_frame(const 
       dx = adjust_dir1(dx); dy = adjust_dir1(dy); dz = adjust_dir1(dz);
       stage = 0;
       stk.reset();
-      state = lean_begin(s, fetch, p.root_valid != 0u, p.pos[0], p.pos[1], p.pos[2], dx, dy, dz) ? kLaneActive : kLaneMiss;
+      float ex = p.pos[0], ey = p.pos[1], ez = p.pos[2];
+      if (JIT) jitter_origin(p.pos, p.jitter_amp, p.jitter_seed, (uint32_t)y * (uint32_t)p.width + (uint32_t)x, ex, ey, ez);
+      state = lean_begin(s, fetch, p.root_valid != 0u, ex, ey, ez, dx, dy, dz) ? kLaneActive : kLaneMiss;
     }
 
     // ---- 3. traversal: one lean_step per live lane per iteration --------------------------------
@@ -326,9 +331,11 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_frame(const 
           float dx, dy, dz;                                       // the primary direction, recomputed
           primary_dir(p.dir0, p.du, p.dv, x, y, dx, dy, dz);
           dx = adjust_dir1(dx); dy = adjust_dir1(dy); dz = adjust_dir1(dz);
-          const float Px = YV_FADD(p.pos[0], YV_FMUL(dx, ht));
-          const float Py = YV_FADD(p.pos[1], YV_FMUL(dy, ht));
-          const float Pz = YV_FADD(p.pos[2], YV_FMUL(dz, ht));
+          float ex = p.pos[0], ey = p.pos[1], ez = p.pos[2];
+          if (JIT) jitter_origin(p.pos, p.jitter_amp, p.jitter_seed, pixel, ex, ey, ez);
+          const float Px = YV_FADD(ex, YV_FMUL(dx, ht));
+          const float Py = YV_FADD(ey, YV_FMUL(dy, ht));
+          const float Pz = YV_FADD(ez, YV_FMUL(dz, ht));
           dl = lambert(nx, ny, nz, Px, Py, Pz, p.light[0], p.light[1], p.light[2]);
           if (!SEC) {
             rgba = shade_rgba(sdata, YV_FADD(YV_SHADE_AMBIENT, YV_FMUL(YV_SHADE_DIFFUSE, YV_FMUL(dl, 1.0f))));
@@ -774,9 +781,11 @@ __global__ void __launch_bounds__(256) shade_pass(const __grid_constant__ Render
   else {
     primary_dir(p.dir0, p.du, p.dv, x, y, dx, dy, dz);
     dx = adjust_dir1(dx); dy = adjust_dir1(dy); dz = adjust_dir1(dz);
-    const float Px = YV_FADD(p.pos[0], YV_FMUL(dx, t));
-    const float Py = YV_FADD(p.pos[1], YV_FMUL(dy, t));
-    const float Pz = YV_FADD(p.pos[2], YV_FMUL(dz, t));
+    float ex = p.pos[0], ey = p.pos[1], ez = p.pos[2];
+    if (p.jitter_amp > 0.0f) jitter_origin(p.pos, p.jitter_amp, p.jitter_seed, pixel, ex, ey, ez);
+    const float Px = YV_FADD(ex, YV_FMUL(dx, t));
+    const float Py = YV_FADD(ey, YV_FMUL(dy, t));
+    const float Pz = YV_FADD(ez, YV_FMUL(dz, t));
     if (p.shade_mode == 1) rgba = shade_phong(rec.x, nx, ny, nz, Px, Py, Pz, p.pos, p.lights);
     else {                                                // head-light Lambert with the SSNA normal
       const float dl = lambert(nx, ny, nz, Px, Py, Pz, p.pos[0], p.pos[1], p.pos[2]);
@@ -859,6 +868,25 @@ __global__ void __launch_bounds__(256) blur_z_pass(const __grid_constant__ BlurP
     if (zc[j] != kInvalid) out = wacc[j] > 0.0f ? YV_FDIV(acc[j], wacc[j]) : zc[j];
     b.dst[(size_t)gy * b.width + gx] = out;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// frame averaging (reaction/report/main.tex:111): per-channel integer sums of n frames, then (sum + n/2) / n
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) accumulate_frame(const uint32_t *rgba, uint4 *sum, uint32_t pixels, int first) {
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= pixels) return;
+  const uint32_t c = rgba[i];
+  uint4 a = first ? make_uint4(0u, 0u, 0u, 0u) : sum[i];
+  a.x += c & 255u; a.y += (c >> 8) & 255u; a.z += (c >> 16) & 255u; a.w += c >> 24;
+  sum[i] = a;
+}
+__global__ void __launch_bounds__(256) resolve_frames(const uint4 *sum, uint32_t *rgba, uint32_t pixels, uint32_t n) {
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= pixels) return;
+  const uint4 a = sum[i];
+  const uint32_t h = n / 2u;
+  rgba[i] = ((a.x + h) / n) | (((a.y + h) / n) << 8) | (((a.z + h) / n) << 16) | (((a.w + h) / n) << 24);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -463,6 +463,15 @@ YV_HD void hash_unit_vector(uint32_t key, float &ux, float &uy, float &uz) {
   ux = 0.0f; uy = 0.0f; uz = 1.0f;
 }
 
+// displaced ray origin (reaction/report/main.tex:107-114; spec: include/yv_format.h "Hiding voxelisation artefacts")
+YV_HD void jitter_origin(const float pos[3], float amplitude, uint32_t seed, uint32_t pixel, float &ox, float &oy, float &oz) {
+  float ux, uy, uz;
+  hash_unit_vector(hash_u32(pixel) ^ hash_u32(seed ^ YV_JITTER_SALT), ux, uy, uz);
+  ox = YV_FADD(pos[0], YV_FMUL(amplitude, ux));
+  oy = YV_FADD(pos[1], YV_FMUL(amplitude, uy));
+  oz = YV_FADD(pos[2], YV_FMUL(amplitude, uz));
+}
+
 // cosine-weighted AO direction: normalize(n + U), falling back to n when the sum degenerates
 YV_HD void ao_direction(float nx, float ny, float nz, uint32_t pixel, uint32_t sample, uint32_t seed,
                         float &dx, float &dy, float &dz) {

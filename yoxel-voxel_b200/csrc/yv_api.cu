@@ -73,6 +73,9 @@ struct yv_renderer {
                                       // the default frame is the CPU tracer's (ISVORenderer) image
   float ssna_voxel_size = YV_SSNA_VOXEL_SIZE;   // voxSize of demo/SVORenderer.cpp:129
   float blur_taps[YV_BLURZ_KERN * YV_BLURZ_KERN] = {};
+  float jitter_amp = 0.0f;            // displaced ray origins (reaction/report/main.tex:107-114); 0 = off
+  uint32_t jitter_seed = 1;
+  uint4 *d_accum = nullptr;           // per-channel sums of yv_render_accumulated
   float detail_coef = 0.0f;           // SVORenderer::m_detailCoef (demo/SVORenderer.h:56); 0 = off
   int width = 0, height = 0;
   int y0 = 0, y1 = 0;
@@ -266,6 +269,7 @@ void free_frame_buffers(yv_renderer *r) {
   cudaFree(r->d_hit_node); cudaFree(r->d_hit_child); cudaFree(r->d_hit_t); cudaFree(r->d_counters);
   cudaFree(r->d_shade_rec); r->d_shade_rec = nullptr;
   cudaFree(r->d_zbuf[0]); cudaFree(r->d_zbuf[1]); r->d_zbuf[0] = r->d_zbuf[1] = nullptr;
+  cudaFree(r->d_accum); r->d_accum = nullptr;
   r->d_hit_node = nullptr; r->d_hit_child = nullptr; r->d_hit_t = nullptr; r->d_counters = nullptr;
   r->fb_pixels = 0;
 }
@@ -345,9 +349,9 @@ void init_ray_dir(const yv_renderer *r, float dir0[3], float du[3], float dv[3],
   init_ray_dir_raw(r->dir, r->up, r->fov, r->width, r->height, dir0, du, dv, basis);
 }
 
-template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED, bool LOD = false, bool RAW = false>
+template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED, bool LOD = false, bool RAW = false, bool JIT = false>
 int launch_kernel(yv_renderer *r, const yv::RenderParams &p, size_t smem) {
-  auto kern = yv::render_frame<SEC, COUNT, STACK, PERSISTENT, STAGED, LOD, RAW>;
+  auto kern = yv::render_frame<SEC, COUNT, STACK, PERSISTENT, STAGED, LOD, RAW, JIT>;
   if (smem > 48 * 1024) YV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long grid;
   if (PERSISTENT) {
@@ -411,6 +415,12 @@ template <bool SEC, bool COUNT>
 int launch_lod(yv_renderer *r, const yv::RenderParams &p) {
   return r->opt_persistent == 1 ? launch_kernel<SEC, COUNT, yv::kStackLocal, true, false, true>(r, p, 0)
                                 : launch_kernel<SEC, COUNT, yv::kStackLocal, false, false, true>(r, p, 0);
+}
+
+// displaced ray origins: primary rays, packed pool, tiles schedule, local-memory stack
+template <bool COUNT, bool LOD>
+int launch_jitter(yv_renderer *r, const yv::RenderParams &p) {
+  return launch_kernel<false, COUNT, yv::kStackLocal, false, false, LOD, false, true>(r, p, 0);
 }
 
 template <bool SEC, bool COUNT>
@@ -487,6 +497,12 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
     if (!r->d_shade_rec) YV_CUDA(cudaMalloc(&r->d_shade_rec, std::max<size_t>(1, r->fb_pixels) * sizeof(uint2)));
     p.shade_rec = r->d_shade_rec;
   }
+  const bool jitter = r->jitter_amp > 0.0f;
+  if (jitter) {
+    if (sec || raw || r->opt_persistent != 0 || r->opt_stack != yv::kStackLocal || r->opt_smem_nodes > 0)
+      return fail(YV_ERR_ARG, "displaced ray origins: primary rays with the default schedule, stack and layout only");
+    p.jitter_amp = r->jitter_amp; p.jitter_seed = r->jitter_seed;
+  }
   p.shadow = r->shadow; p.ao_samples = r->ao_samples; p.seed = r->seed;
   p.voxel_size = r->voxel_size; p.ao_max_t = r->ao_max_t;
   const bool lod = r->detail_coef > 0.0f;
@@ -508,7 +524,10 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
 
   if (!r->suppress_events) YV_CUDA(cudaEventRecord(r->ev0, r->stream));
   const int key = (sec ? 2 : 0) | (r->counters ? 1 : 0);
-  if (sec && !raw && r->opt_sec_queue && r->opt_persistent != 1) {      // pooled AO rays (config 4)
+  if (jitter) {
+    if (lod) rc = r->counters ? launch_jitter<true, true>(r, p) : launch_jitter<false, true>(r, p);
+    else rc = r->counters ? launch_jitter<true, false>(r, p) : launch_jitter<false, false>(r, p);
+  } else if (sec && !raw && r->opt_sec_queue && r->opt_persistent != 1) {      // pooled AO rays (config 4)
     if (lod) rc = r->counters ? launch_sec_queue<true, true>(r, p) : launch_sec_queue<false, true>(r, p);
     else rc = r->counters ? launch_sec_queue<true, false>(r, p) : launch_sec_queue<false, false>(r, p);
   } else if (raw) {
@@ -898,6 +917,12 @@ int yv_set_ssna_voxel_size(yv_renderer *r, float voxel_size) {
   r->ssna_voxel_size = voxel_size > 0.0f ? voxel_size : YV_SSNA_VOXEL_SIZE;
   return YV_OK;
 }
+int yv_set_jitter(yv_renderer *r, float amplitude, uint32_t seed) {
+  if (!r) return fail(YV_ERR_ARG, "null renderer");
+  if (!(amplitude >= 0.0f)) return fail(YV_ERR_ARG, "jitter amplitude must be >= 0");
+  r->jitter_amp = amplitude; r->jitter_seed = seed;
+  return YV_OK;
+}
 int yv_set_detail_coef(yv_renderer *r, float coef) {
   if (!r) return fail(YV_ERR_ARG, "null renderer");
   if (!(coef >= 0.0f)) return fail(YV_ERR_ARG, "detail coefficient must be >= 0");
@@ -1000,6 +1025,41 @@ int yv_render_frame(yv_renderer *r, const uint8_t **rgba) {
     const size_t off = (size_t)y0 * r->width * 4, bytes = (size_t)(y1 - y0) * r->width * 4;
     YV_CUDA(cudaMemcpyAsync(r->h_fb + off, (const uint8_t *)r->d_fb + off, bytes, cudaMemcpyDeviceToHost, r->stream));
   }
+  YV_CUDA(cudaStreamSynchronize(r->stream));
+  *rgba = r->h_fb;
+  return YV_OK;
+}
+
+int yv_render_accumulated(yv_renderer *r, int frames, const uint8_t **rgba) {
+  if (!r || !rgba) return fail(YV_ERR_ARG, "null argument");
+  *rgba = nullptr;
+  if (frames < 1 || frames > 4096) return fail(YV_ERR_ARG, "frames must be 1..4096");
+  if (!r->svo) return fail(YV_ERR_NOSCENE, "no scene set");
+  int rc = ensure_frame_buffers(r);
+  if (rc) return rc;
+  YV_CUDA(cudaSetDevice(r->device));
+  if (!r->d_accum) YV_CUDA(cudaMalloc(&r->d_accum, std::max<size_t>(1, r->fb_pixels) * sizeof(uint4)));
+  const uint32_t pixels = (uint32_t)r->fb_pixels, grid = (pixels + 255u) / 256u;
+  const uint32_t seed0 = r->jitter_seed;
+  YV_CUDA(cudaEventRecord(r->ev0, r->stream));
+  r->suppress_events = true;
+  int launches = 0;
+  for (int k = 0; k < frames && rc == YV_OK; ++k) {
+    r->jitter_seed = seed0 + (uint32_t)k;
+    rc = launch_frame(r, r->d_fb);
+    if (rc == YV_OK && grid) {
+      yv::accumulate_frame<<<grid, 256, 0, r->stream>>>(r->d_fb, r->d_accum, pixels, k == 0);
+      launches += r->last_launches + 1;
+    }
+  }
+  r->suppress_events = false;
+  r->jitter_seed = seed0;
+  if (rc) return rc;
+  if (grid) { yv::resolve_frames<<<grid, 256, 0, r->stream>>>(r->d_accum, r->d_fb, pixels, (uint32_t)frames); ++launches; }
+  YV_CUDA(cudaGetLastError());
+  YV_CUDA(cudaEventRecord(r->ev1, r->stream));
+  r->timed = true; r->launches = launches;
+  YV_CUDA(cudaMemcpyAsync(r->h_fb, r->d_fb, r->fb_pixels * 4, cudaMemcpyDeviceToHost, r->stream));
   YV_CUDA(cudaStreamSynchronize(r->stream));
   *rgba = r->h_fb;
   return YV_OK;
