@@ -208,9 +208,14 @@ int yv_set_stream(yv_renderer *r, void *cuda_stream);
  *                 by whichever lane is free (render_sec_queue; fills more lanes but loses lock-step fetches: slower)
  *   "sec_threshold" secondary rays (stage machine): lanes whose ray has ended are handed their pixel's next ray once <= this many
  *                 lanes of the warp are still traversing (-1 = only when the whole warp has drained)
- *   "pipeline"    number of row chunks (2..8, default 4) yv_render_frame cuts the frame into: chunks render on
- *                 two alternating streams and each chunk's device->host copy overlaps the next chunk's kernel;
- *                 0 or 1 = one launch, then one copy
+ *   "zero_copy"   1 (default) = yv_render_frame's kernel stores its pixels straight into the pinned host frame
+ *                 (device-addressable under UVA): the posted PCIe writes overlap the traversal, there is no copy and
+ *                 no second launch. Frames that need a second pass over the image (Phong / show-normals / SSNA)
+ *                 and 0 use the copy paths below
+ *   "pipeline"    with zero_copy 0: number of row chunks (2..8, default 4) yv_render_frame cuts the frame into:
+ *                 chunks render on two alternating streams and each chunk's device->host copy overlaps the next
+ *                 chunk's kernel; 0 or 1 = one launch, then one copy
+ *   "pipeline_taper" each chunk is this many percent (10..100, default 100) of the rows of the one before it
  *   "layout"      0 = packed 16-byte records (default; re-packed and re-uploaded in full after an edit),
  *                 1 = the raw reference pool mirrored page by page (yv_svo_update) — for scenes under edit
  *   "stack"       where the traversal stack lives: 0 local memory, 4 = four-entry

@@ -274,15 +274,24 @@ def test_device_pointer_render_and_timing(renderer):
     renderer.Render(buf.data_ptr())
     assert (buf.cpu().numpy() == img).all()
     assert 0 < renderer.LastFrameMs() < 1000 and renderer.LastFrameLaunches() == 1
-    # RenderFrame pipelines 8 row chunks with their D2H copies; the pixels are the same either way
+    # RenderFrame's three ways of getting the frame to the host: the kernel stores into the pinned host frame
+    # (default), 8 row chunks pipelined with their D2H copies, one launch + one copy; the pixels are the same
+    assert renderer.GetOption("zero_copy") == 1
+    z = renderer.RenderFrame().copy()
+    assert renderer.LastFrameLaunches() == 1 and 0 < renderer.LastFrameMs() < 1000
+    renderer.SetOption("zero_copy", 0)
     renderer.SetOption("pipeline", 8)
     a = renderer.RenderFrame().copy()
     assert renderer.LastFrameLaunches() == 8 and 0 < renderer.LastFrameMs() < 1000
     renderer.SetOption("pipeline", 0)
     b = renderer.RenderFrame().copy()
     assert renderer.LastFrameLaunches() == 1
-    renderer.SetOption("pipeline", 8)
-    assert (a == img).all() and (b == img).all()
+    renderer.SetOption("pipeline", 4)
+    renderer.SetOption("pipeline_taper", 60)
+    c = renderer.RenderFrame().copy()
+    renderer.SetOption("pipeline_taper", 100)
+    renderer.SetOption("zero_copy", 1)
+    assert (z == img).all() and (a == img).all() and (b == img).all() and (c == img).all()
     # on torch's current stream
     renderer.SetStream(torch.cuda.current_stream().cuda_stream)
     buf.zero_()

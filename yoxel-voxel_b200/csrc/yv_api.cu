@@ -104,6 +104,10 @@ struct yv_renderer {
   cudaEvent_t ev_fork = nullptr, ev_chunk[kChunks] = {}, ev_copy = nullptr;
   bool suppress_events = false;
   int opt_pipeline = 4;               // row chunks per RenderFrame (0/1 = no pipelining); 4 measured best at 1080p
+  int opt_zero_copy = 1;              // 1 = RenderFrame's kernel stores its pixels straight into the pinned host frame
+                                      // (posted PCIe writes overlap the traversal; no copy, one launch)
+  int opt_pipeline_taper = 100;       // each chunk is this many percent of the one before it (100 = equal chunks): the copy
+                                      // of the last chunk is the only one that is not hidden behind a kernel
   bool timed = false;
   int launches = 0;
   int last_launches = 1;              // kernels launched by the most recent launch_frame call
@@ -604,15 +608,29 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
 int render_frame_pipelined(yv_renderer *r) {
   const int H = r->height, W = r->width;
   const int chunks = std::min(std::max(r->opt_pipeline, 2), (int)yv_renderer::kChunks);
-  int rows = ((H + chunks - 1) / chunks + 7) / 8 * 8;
+  // chunk k starts at row bound[k]; sizes fall geometrically by opt_pipeline_taper percent, rounded to 8-row tiles
+  int bound[yv_renderer::kChunks + 1];
+  {
+    const double q = std::min(100, std::max(10, r->opt_pipeline_taper)) / 100.0;
+    double total = 0.0, w = 1.0;
+    for (int k = 0; k < chunks; ++k, w *= q) total += w;
+    double acc = 0.0; w = 1.0;
+    bound[0] = 0;
+    for (int k = 0; k < chunks; ++k, w *= q) {
+      acc += w;
+      int b = (int)(H * (acc / total) / 8.0 + 0.5) * 8;
+      bound[k + 1] = k == chunks - 1 ? H : std::min(H, std::max(b, bound[k]));
+    }
+  }
   cudaStream_t main_stream = r->stream;
   YV_CUDA(cudaEventRecord(r->ev0, main_stream));
   YV_CUDA(cudaEventRecord(r->ev_fork, main_stream));
   for (int i = 0; i < 2; ++i) YV_CUDA(cudaStreamWaitEvent(r->aux[i], r->ev_fork, 0));
   int rc = YV_OK, launched = 0;
   r->suppress_events = true;
-  for (int k = 0, y0 = 0; y0 < H && rc == YV_OK; ++k, y0 += rows) {
-    const int y1 = std::min(H, y0 + rows);
+  for (int k = 0; k < chunks && rc == YV_OK; ++k) {
+    const int y0 = bound[k], y1 = bound[k + 1];
+    if (y1 <= y0) continue;
     r->rows_set = true; r->y0 = y0; r->y1 = y1;
     r->stream = r->aux[k & 1];
     rc = launch_frame(r, r->d_fb);
@@ -1011,6 +1029,16 @@ int yv_render_frame(yv_renderer *r, const uint8_t **rgba) {
   int rc = ensure_frame_buffers(r);
   if (rc) return rc;
   const bool ssna = r->ssna && !(r->shadow || r->ao_samples > 0);      // BlurZ reaches across row chunks: one launch
+  bool any_light = false;
+  for (int i = 0; i < YV_MAX_LIGHTS; ++i) any_light = any_light || r->lights[i].enabled;
+  const bool second_pass = ssna || ((r->show_normals || any_light) && !(r->shadow || r->ao_samples > 0));
+  if (r->opt_zero_copy && !second_pass) {       // (the ShadeSimple / SSNA passes read the frame back: keep it in HBM)
+    rc = launch_frame(r, r->h_fb);              // pinned memory is device-addressable under UVA
+    if (rc) return rc;
+    YV_CUDA(cudaStreamSynchronize(r->stream));
+    *rgba = r->h_fb;
+    return YV_OK;
+  }
   if (r->opt_pipeline > 1 && !r->rows_set && r->il_stride == 1 && r->opt_persistent != 1 && r->height >= 256 && !ssna) {
     rc = render_frame_pipelined(r);
     if (rc) return rc;
@@ -1150,6 +1178,8 @@ int yv_set_option(yv_renderer *r, const char *name, int value) {
   }
   else if (n == "sec_queue") r->opt_sec_queue = value ? 1 : 0;
   else if (n == "sec_threshold") { if (value < -1 || value > 31) return fail(YV_ERR_ARG, "sec_threshold must be -1..31"); r->opt_sec_threshold = value; }
+  else if (n == "zero_copy") r->opt_zero_copy = value != 0;
+  else if (n == "pipeline_taper") { if (value < 10 || value > 100) return fail(YV_ERR_ARG, "pipeline_taper must be 10..100 percent"); r->opt_pipeline_taper = value; }
   else if (n == "pipeline") { if (value < 0 || value > yv_renderer::kChunks) return fail(YV_ERR_ARG, "pipeline must be 0..8 chunks"); r->opt_pipeline = value; }
   else if (n == "layout") { if (value != 0 && value != 1) return fail(YV_ERR_ARG, "layout must be 0 (packed) or 1 (raw)"); r->opt_layout = value; }
   else if (n == "refill") { if (value < 0 || value > 31) return fail(YV_ERR_ARG, "refill must be 0..31"); r->opt_refill = value; }
@@ -1170,6 +1200,8 @@ int yv_get_option(const yv_renderer *r, const char *name, int *value) {
   else if (n == "sec_queue") *value = r->opt_sec_queue;
   else if (n == "sec_threshold") *value = r->opt_sec_threshold;
   else if (n == "pipeline") *value = r->opt_pipeline;
+  else if (n == "pipeline_taper") *value = r->opt_pipeline_taper;
+  else if (n == "zero_copy") *value = r->opt_zero_copy;
   else if (n == "layout") *value = r->opt_layout;
   else if (n == "refill") *value = r->opt_refill;
   else if (n == "stack") *value = r->opt_stack;
