@@ -88,9 +88,14 @@ struct BlurParams {
 
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kCtaThreads = 128;
+#ifndef YV_FRAME_CTA
+#define YV_FRAME_CTA 128               // threads per render_frame CTA (a 16x8-pixel tile is always four warps: smaller CTAs take
+#endif                                 // a share of one tile's warps and free their SM slot without waiting for the others)
+constexpr int kFrameCta = YV_FRAME_CTA;
 #ifndef YV_MINBLOCKS
 #define YV_MINBLOCKS 8                 // __launch_bounds__ residency target (register cap = 65536 / (128 * this))
 #endif
+constexpr int kFrameMinBlocks = YV_MINBLOCKS * kCtaThreads / kFrameCta;      // same register cap whatever the CTA size
 #ifndef YV_WARP_W
 #define YV_WARP_W 8                    // pixels per warp: 8x4 (4 = 4x8, 16 = 16x2); 8x4 measured best (profiles/README.md)
 #endif
@@ -213,12 +218,12 @@ __device__ __forceinline__ int tile_row_y(const RenderParams &p, int ty) {
 enum : int { kLaneIdle = 0, kLaneActive = 1, kLaneHit = 2, kLaneMiss = 3, kLaneNew = 4, kLaneLodHit = 5 };
 
 template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED, bool LOD, bool RAW, bool JIT = false>
-__global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_frame(const __grid_constant__ RenderParams p) {
+__global__ void __launch_bounds__(kFrameCta, kFrameMinBlocks) render_frame(const __grid_constant__ RenderParams p) {
   extern __shared__ uint4 smem[];
   uint4 *staged = smem;
   uint4 *stack_area = smem + (STAGED ? p.smem_nodes : 0u);
   if (STAGED) {
-    for (uint32_t i = threadIdx.x; i < p.smem_nodes; i += kCtaThreads) staged[i] = __ldg(p.recs + i);
+    for (uint32_t i = threadIdx.x; i < p.smem_nodes; i += kFrameCta) staged[i] = __ldg(p.recs + i);
     __syncthreads();
   }
 
@@ -243,9 +248,10 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_frame(const 
 
   if (!PERSISTENT) {
     // one CTA per 16x8 tile: warp w covers an 8x4 block
-    const int warp = threadIdx.x >> 5;
+    const int vwarp = (int)blockIdx.x * (kFrameCta / 32) + (threadIdx.x >> 5);     // four consecutive warps share a 16x8 tile
+    const int warp = vwarp & 3, tile = vwarp >> 2;
     const int tiles_x16 = (p.width + 15) >> 4;
-    const int tx = blockIdx.x % tiles_x16, ty = blockIdx.x / tiles_x16;
+    const int tx = tile % tiles_x16, ty = tile / tiles_x16;
     // warp footprint YV_WARP_W x (32 / YV_WARP_W) pixels inside the CTA's 16x8 tile
     constexpr int kWW = YV_WARP_W, kWH = 32 / YV_WARP_W, kWarpsX = 16 / YV_WARP_W;
     x = tx * 16 + (warp % kWarpsX) * kWW + (lane % kWW);

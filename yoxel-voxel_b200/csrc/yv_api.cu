@@ -360,17 +360,18 @@ int launch_kernel(yv_renderer *r, const yv::RenderParams &p, size_t smem) {
   long grid;
   if (PERSISTENT) {
     int per_sm = 0;
-    YV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, yv::kCtaThreads, smem));
+    YV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, yv::kFrameCta, smem));
     if (per_sm < 1) per_sm = 1;
     grid = (long)r->sm_count * per_sm;
     const long warps_needed = ((long)p.num_tiles * 64 + 31) / 32;
-    const long max_useful = (warps_needed + yv::kCtaThreads / 32 - 1) / (yv::kCtaThreads / 32);
+    const long max_useful = (warps_needed + yv::kFrameCta / 32 - 1) / (yv::kFrameCta / 32);
     if (grid > max_useful) grid = std::max(1l, max_useful);
     YV_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(unsigned int), r->stream));
   } else {
-    grid = (long)((p.width + 15) / 16) * (p.num_tiles / p.tiles_x);
+    const long tiles16x8 = (long)((p.width + 15) / 16) * (p.num_tiles / p.tiles_x);      // four warps each
+    grid = (tiles16x8 * 4 + yv::kFrameCta / 32 - 1) / (yv::kFrameCta / 32);
   }
-  if (grid > 0) kern<<<(unsigned)grid, yv::kCtaThreads, smem, r->stream>>>(p);
+  if (grid > 0) kern<<<(unsigned)grid, yv::kFrameCta, smem, r->stream>>>(p);
   YV_CUDA(cudaGetLastError());
   return YV_OK;
 }
