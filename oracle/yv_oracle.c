@@ -1,7 +1,8 @@
 /* yv_oracle.c — CPU oracle for the SVO ray-caster path.  TEST INFRASTRUCTURE ONLY.
  *
- * Plain-C restatement of the reference CPU tracer. PARITY UNPINNED (see yv_oracle.h):
- * the reference holds no golden vectors for this path and its tracer does not build here.
+ * Plain-C restatement of the reference CPU tracer. PARITY UNPINNED by golden vectors (see yv_oracle.h):
+ * the reference holds none for this path and its tracer does not build here; the traversal is
+ * checked against the reference's scalar prototype compiled into oracle/_ref, the rest is unpinned.
  *
  * Every function cites the reference lines whose behaviour it restates (paths relative to
  * /root/reference). All ray arithmetic is IEEE-754 binary32, round-to-nearest, and this file
@@ -107,9 +108,20 @@ static inline int find_first_child(v3 *t1, v3 *t2) {
   return ch;
 }
 
+/* Test-only switch: 0 = the path's argmin tie order (cell/spu/trace_spu.cpp:75-78, the default and the only order
+ * the parity tests use); 1 = the tie order of the reference's scalar prototype (argMin, cell/spu/vector.h:45-59), so
+ * that tests/test_reference_prototype.py can compare the traversal with that compiled prototype on rays that cross
+ * cell edges exactly. The two differ only when two components of t2 are equal. */
+static int g_tie_order = 0;
+void yvo_set_tie_order(int order) { g_tie_order = order; }
+
 /* GoNext (scalar form of cell/spu/trace_spu.cpp:70-93) */
 static inline int go_next(int *ch, v3 *t1, v3 *t2) {
   int e;
+  if (g_tie_order == 1) {
+    if (t2->x < t2->y) e = (t2->x < t2->z) ? 0 : 2;
+    else               e = (t2->y < t2->z) ? 1 : 2;
+  } else
   if (t2->x > t2->y) e = (t2->y < t2->z) ? 1 : 2;
   else               e = (t2->x < t2->z) ? 0 : 2;
   int mask = 1 << e;

@@ -4,11 +4,17 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it;
  * the product (yoxel-voxel_b200/) never links, imports or calls anything in oracle/.
  *
- * PARITY UNPINNED: the reference snapshot ships no golden vectors, no scene files and no
- * test for this path, and its own tracer does not compile (the cpp/ directory with
- * trace_utils.h, vox_node.h, shader.h, rdd.h is absent — SURVEY.md §0.2, §8c). The oracle
- * is therefore validated independently (hand-computed rays, a brute-force voxel-grid
- * marcher, structural properties — see tests/test_oracle_*.py), not against reference output.
+ * PARITY UNPINNED by golden vectors: the reference snapshot ships no golden vectors, no scene files and no test for
+ * this path, and its tracer for the path does not compile (the cpp/ directory with trace_utils.h, vox_node.h,
+ * shader.h, rdd.h is absent — SURVEY.md §0.2, §8c). What pins the oracle instead:
+ *   - the traversal (ray set-up, FindFirstChild, GoNext, recursion order, which node is hit) against reference code
+ *     run here: the snapshot's scalar prototype of the same traversal, cell/spu/trace_spu.c_, compiled unmodified
+ *     into oracle/_ref (oracle/Makefile target `ref`, stand-in headers in oracle/ref_shim/) —
+ *     tests/test_reference_prototype.py: identical on every ray without an exact edge crossing;
+ *   - hand-computed rays, a brute-force voxel-grid marcher (a different algorithm), structural properties —
+ *     tests/test_oracle.py.
+ * Shading, VoxData packing, the AdjustDir epsilon, LOD, SSNA and the secondary rays have no reference code at all;
+ * they are builder decisions written down in include/yv_format.h and remain unpinned.
  */
 #ifndef YV_ORACLE_H
 #define YV_ORACLE_H
@@ -82,6 +88,11 @@ int yvo_render_threaded_ref(const yv_vox_node *nodes, uint32_t node_count, yv_no
 int yvo_trace_ray(const yv_vox_node *nodes, uint32_t node_count, yv_node_id root,
                   const float pos[3], const float dir[3],
                   uint32_t *hit_node, int32_t *hit_child, float *hit_t);
+
+/* Test-only: argmin tie order of GoNext. 0 (default) = cell/spu/trace_spu.cpp:75-78, the path's; 1 = argMin of the
+ * reference's scalar prototype (cell/spu/vector.h:45-59), used only to compare against that prototype compiled into
+ * oracle/_ref (tests/test_reference_prototype.py). Process-global; restore 0 after use. */
+void yvo_set_tie_order(int order);
 
 /* SimpleShader::Shade restatement, exposed for unit tests */
 void yvo_shade(yv_vox_data data, const float dir[3], float t,

@@ -62,6 +62,8 @@ def lib():
         L.yvo_shade.restype = None
         L.yvo_unpack_normal.argtypes = [C.c_uint32, C.POINTER(C.c_float)]
         L.yvo_unpack_normal.restype = None
+        L.yvo_set_tie_order.argtypes = [C.c_int]
+        L.yvo_set_tie_order.restype = None
         L.yvo_blur_taps.argtypes = [C.POINTER(C.c_float)]
         L.yvo_blur_taps.restype = None
         L.yvo_blur_z.argtypes = [C.POINTER(Camera), vp, vp]
@@ -156,6 +158,11 @@ def trace_ray(nodes, root, pos, d):
     hit = lib().yvo_trace_ray(nodes.ctypes.data_as(C.c_void_p), len(nodes), int(root), p, dd,
                               C.byref(n), C.byref(c), C.byref(t))
     return bool(hit), n.value, c.value, t.value
+
+
+def set_tie_order(order):
+    """Test-only: 0 = the path's GoNext tie order (default), 1 = the scalar prototype's (cell/spu/vector.h:45-59)."""
+    lib().yvo_set_tie_order(int(order))
 
 
 def shade(data, d, t, viewer, light, visibility=1.0):
