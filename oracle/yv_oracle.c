@@ -49,8 +49,9 @@ static inline float min3(v3 a) { float m = a.x < a.y ? a.x : a.y; return m < a.z
 
 /* RendererBase::InitRayDir (cell/renderer_base.h:50-61).
  * grad2rad(float) = grad * float(pi/180) (nest/include/geometry/xmath.h:47,57).
- * The one transcendental (tan) is evaluated in double and rounded once; the product's host
- * side does the same (see DESIGN.md "numeric contract"). */
+ * tan(cg::grad2rad(m_fov / 2)) / m_viewSize.x (:56): the argument is a float, so the C++ overload set gives the
+ * float tangent and a float division — confirmed against the reference's header compiled in oracle/_ref
+ * (tests/test_reference_renderer.py); the product's host side does the same. */
 void yvo_init_ray_dir(const yvo_camera *cam, yvo_raydir *out) {
   const double pi = 3.14159265358979323846;
   v3 vfwd = v3_normalized(v3_from(cam->dir));
@@ -59,7 +60,7 @@ void yvo_init_ray_dir(const yvo_camera *cam, yvo_raydir *out) {
 
   float half_deg = cam->fov_deg / 2;
   float half_rad = half_deg * (float)(pi / 180.0);
-  float da = (float)(tan((double)half_rad) / (double)cam->width);
+  float da = tanf(half_rad) / (float)cam->width;
 
   v3 du = v3_scale(v3_scale(vright, 2.0f), da);     /* 2 * vright * da   (:58) */
   v3 dv = v3_scale(v3_scale(vup, -2.0f), da);       /* -2 * vup * da     (:59) */
@@ -405,7 +406,7 @@ static void view_basis(const yvo_camera *cam, v3 *fwd, v3 *right, v3 *down, floa
   v3 up = v3_cross(*right, *fwd);
   down->x = -up.x; down->y = -up.y; down->z = -up.z;
   float half_rad = (cam->fov_deg / 2) * (float)(3.14159265358979323846 / 180.0);
-  float da = (float)(tan((double)half_rad) / (double)cam->width);
+  float da = tanf(half_rad) / (float)cam->width;
   *d2 = 2.0f * da;
 }
 

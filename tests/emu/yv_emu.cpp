@@ -14,6 +14,7 @@ namespace {
 float g_detail = 0.0f;   // rp.detailCoef; > 0 switches the LOD cut-off on (lean mode only)
 bool g_lod_hit = false;
 const uint32_t *g_node_data = nullptr;
+uint64_t g_trips = 0;   // lean_step / trace_step calls of the last yve_render
 int g_mode = 2;   // 0 = trace_step (classic form), 2 = lean_step (what render_frame runs)
 struct HostStack {
   StackEntry e[kMaxStack];
@@ -77,6 +78,7 @@ bool trace(const HostFetch &fetch, bool root_valid, HostStack &stk, float ox, fl
 }  // namespace
 
 extern "C" void yve_set_mode(int mode) { g_mode = mode; }
+extern "C" uint64_t yve_trips() { return g_trips; }      // lean_step / trace_step calls of the last yve_render
 extern "C" void yve_set_lod(float detail, const uint32_t *node_data) { g_detail = detail; g_node_data = node_data; }
 
 extern "C" int yve_render(const uint32_t *records, const uint32_t *leaves, int root_valid,
@@ -143,6 +145,7 @@ extern "C" int yve_render(const uint32_t *records, const uint32_t *leaves, int r
       if (hit_t) hit_t[pixel] = ht;
       if (rgba) rgba[pixel] = out;
     }
+  g_trips = steps;
   if (out_fetches) *out_fetches = fetch.fetches;
   if (out_visits) *out_visits = fetch.visits;
   if (out_max_sp) *out_max_sp = stk.max_sp;

@@ -1,0 +1,234 @@
+"""The oracle against the reference's own renderer, compiled here from the reference's sources.
+
+SURVEY §8c found that cell/ppu_renderer.cpp does not compile as shipped: six headers of a cpp/ directory, Boost.Thread
+and the Cell SDK are missing. oracle/Makefile (target `ref`) compiles it anyway — unmodified, from where it lies —
+against stand-ins for exactly those headers (oracle/ref_shim/, each stating what it replaces), and the SPU program
+cell/spu/trace_spu.cpp the same way. So everything of the path that IS in the snapshot runs here as the reference
+wrote it and pins the oracle bit for bit:
+
+  * SVOData::Load reading the .vox files this repo writes ............................ cell/svodata.h:31-50
+  * RendererBase defaults and setters, InitRayDir over the reference's cg::point_t ..... cell/renderer_base.h:25-61
+  * the per-pixel loop (ray generation, clear colour, frame layout) and RecTrace ....... cell/ppu_renderer.cpp:18-70
+  * SimpleRenderer / TreadedRenderer::RenderFrame (NULL without a scene, 4 strips) ..... cell/ppu_renderer.cpp:76-144
+  * the SPU program: FetchNode cache, FindFirstChildSPU, GoNextSPU, RecTrace,
+    RenderBlock (clear colour (0,0,0,255), 16x16 blocks) ............................... cell/spu/trace_spu.cpp:15-181
+
+What stays a builder decision (the stand-ins hold our statement of it, so agreement there proves nothing): the
+AdjustDir epsilon, the body of SetupTrace, the VoxData bit layout and the Shade formula; and, on the PPU build only,
+the scalar FindFirstChild / GoNext — the SPU build runs the reference's own SIMD bodies of those two, and both builds
+must agree with the oracle, which closes that gap.
+
+A frame's TraceResult leaves the reference's loop through the stand-in shader's probe modes (the 32 bits of t, the
+VoxData word); with every leaf word rewritten to node*8+child the VoxData IS the hit id.
+These tests need oracle/_ref (built only where /root/reference exists); elsewhere they skip and
+tests/test_reference_golden.py checks the committed output of the same builds."""
+import os
+
+import numpy as np
+import pytest
+
+import scenes
+import yvo
+import yvref
+import yoxel_voxel_b200 as yv
+from test_fuzz_scenes import POOLS, _cams, _random_pool
+
+pytestmark = pytest.mark.skipif(not yvref.available(), reason="oracle/_ref is built only where /root/reference exists")
+
+
+def tag_leaves(nodes):
+    """Copy of the pool whose every inline leaf word is node*8+child: the VoxData a hit returns names the hit."""
+    out = nodes.copy()
+    ids = (np.arange(len(nodes), dtype=np.uint32)[:, None] * 8 + np.arange(8, dtype=np.uint32)[None, :])
+    leaf = ((nodes["flags"][:, None] >> np.arange(8)[None, :]) & 1).astype(bool)
+    out["child"] = np.where(leaf, ids, nodes["child"])
+    return out
+
+
+def oracle_data(nodes, o):
+    hit = o["node"] != yvo.MISS_NODE
+    n = np.where(hit, o["node"], 0)
+    c = np.where(hit, o["child"], 0)
+    return np.where(hit, nodes["child"][n, c], 0).astype(np.uint32), hit
+
+
+def check_ppu_frame(scene, nodes, root, cam_spec, W, H, threaded=False):
+    name, pos, d, up, fov = cam_spec
+    o = yvo.render(nodes, root, yvo.camera(pos, d, up, fov, W, H), threads=4)
+    rgba, tbits, data = yvref.ppu_result(scene, pos, d, up, fov, W, H, threaded)
+    rows = slice(0, (H // 4) * 4) if threaded else slice(0, H)      # TreadedRenderer leaves H % 4 rows untouched (:130)
+    odata, hit = oracle_data(nodes, o)
+    assert (rgba[rows] == o["rgba"][rows]).all(), name                                   # misses are (0,0,0,0) (:54)
+    assert (tbits[rows][hit[rows]] == o["t"].view(np.uint32)[rows][hit[rows]]).all(), name
+    assert (data[rows] == odata[rows]).all(), name
+    return o, hit
+
+
+@pytest.fixture(scope="module")
+def tmpdir_vox(tmp_path_factory):
+    return tmp_path_factory.mktemp("refvox")
+
+
+def _load(svo, tmpdir, name):
+    path = os.path.join(str(tmpdir), name + ".vox")
+    svo.Save(path)
+    sc = yvref.Scene(path)
+    assert sc.root() == svo.GetRoot()                                                    # svodata.h:36
+    return sc
+
+
+def test_init_ray_dir_is_the_references_bit_for_bit():
+    """InitRayDir of the product (host side of the C ABI) and of the oracle against RendererBase::InitRayDir itself."""
+    rng = np.random.RandomState(5)
+    sizes_w = [64, 160, 333, 512, 640, 1024, 1920, 3840, 7680]
+    sizes_h = [48, 77, 128, 480, 512, 768, 1080, 2160, 4320]
+    for it in range(3000):
+        d = rng.randn(3)
+        up = rng.randn(3) if it % 2 else np.array([0.0, 0.0, 1.0])
+        fov = float(np.float32(rng.uniform(5, 170))) if it % 3 else [70.0, 40.0, 55.0, 110.0, 90.0, 60.0][it % 6]
+        W, H = int(rng.choice(sizes_w)), int(rng.choice(sizes_h))
+        ref = np.concatenate(yvref.init_ray_dir(d, up, fov, W, H))
+        mine = np.concatenate(yv.init_ray_dir(tuple(d), tuple(up), fov, W, H)).astype(np.float32)
+        orc = np.concatenate(yvo.init_ray_dir(yvo.camera(tuple(d), tuple(d), tuple(up), fov, W, H)))
+        assert ref.tobytes() == mine.tobytes(), (it, d, up, fov, W, H)
+        assert ref.tobytes() == orc.tobytes(), (it, d, up, fov, W, H)
+
+
+SCENES = {
+    "fractal8": lambda: scenes.fractal(8),
+    "sphere6": lambda: scenes.single_sphere(6),
+    "dense4": lambda: scenes.dense_random(4, 0.08)[0],
+    "two_level": lambda: yv.SVOData.FromNodes(scenes.two_level_tree()[1], scenes.two_level_tree()[0]),
+}
+
+
+@pytest.mark.parametrize("scene_name", list(SCENES))
+def test_simple_renderer_frames(scene_name, tmpdir_vox):
+    """SimpleRenderer::RenderFrame over Load()ed pools: RGBA, hit distance bits and VoxData of every pixel."""
+    svo = SCENES[scene_name]()
+    sc = _load(svo, tmpdir_vox, scene_name)
+    hits = 0
+    for cam in scenes.CAMERAS:
+        o, hit = check_ppu_frame(sc, svo.nodes(), svo.GetRoot(), cam, 160, 120)
+        hits += int(hit.sum())
+    assert hits > 1000
+    sc.close()
+
+
+@pytest.mark.parametrize("scene_name", ["fractal8", "dense4"])
+def test_hit_ids_through_tagged_leaves(scene_name, tmpdir_vox):
+    """Every leaf word = node*8+child, so the VoxData the reference shades with (ppu_renderer.cpp:67) is res.node /
+    res.child (:29-30): hit ids of the reference's RecTrace == the oracle's, pixel by pixel."""
+    svo = SCENES[scene_name]()
+    tagged = yv.SVOData.FromNodes(svo.GetRoot(), tag_leaves(svo.nodes()))
+    sc = _load(tagged, tmpdir_vox, scene_name + "_tagged")
+    nodes = tagged.nodes()
+    n_hit = 0
+    for name, pos, d, up, fov in scenes.CAMERAS:
+        W, H = 200, 144
+        o = yvo.render(nodes, tagged.GetRoot(), yvo.camera(pos, d, up, fov, W, H), threads=4)
+        data = yvref.ppu_frame(sc, pos, d, up, fov, W, H, yvref.PROBE_DATA)
+        hit = o["node"] != yvo.MISS_NODE
+        assert (data[~hit] == 0).all(), name
+        assert ((data >> 3)[hit] == o["node"][hit]).all(), name
+        assert ((data & 7)[hit] == o["child"][hit].astype(np.uint32)).all(), name
+        n_hit += int(hit.sum())
+    assert n_hit > 5000
+    sc.close()
+
+
+def test_threaded_renderer_strips(tmpdir_vox):
+    """TreadedRenderer: four strips of H/4 rows (ppu_renderer.cpp:129-141) give the SimpleRenderer frame; with
+    H % 4 != 0 the last rows are never rendered."""
+    svo = scenes.fractal(8)
+    sc = _load(svo, tmpdir_vox, "fractal8_thr")
+    for H in (120, 122):
+        for cam in (scenes.CAMERAS[1], scenes.CAMERAS[4]):
+            check_ppu_frame(sc, svo.nodes(), svo.GetRoot(), cam, 160, H, threaded=True)
+    name, pos, d, up, fov = scenes.CAMERAS[1]
+    mine = yvo.render_threaded_ref(svo.nodes(), svo.GetRoot(), yvo.camera(pos, d, up, fov, 160, 122), prefill=0x5a)
+    ref = yvref.ppu_frame(sc, pos, d, up, fov, 160, 122, threaded=True).view(np.uint8).reshape(122, 160, 4)
+    assert (mine[:120] == ref[:120]).all() and (mine[120:] == 0x5a).all()
+    sc.close()
+
+
+def test_defaults_and_missing_scene(tmpdir_vox):
+    """RendererBase(): 640x480, up (0,0,1), fov 70 (renderer_base.h:25); RenderFrame without a scene returns NULL
+    (ppu_renderer.cpp:78-79, :123-124)."""
+    assert yvref.ppu_frame(None, (0.5, 0.5, 0.3), (-1, -1, 1.5), None, 0, 0, 0) is None
+    assert yvref.ppu_frame(None, (0.5, 0.5, 0.3), (-1, -1, 1.5), None, 0, 0, 0, threaded=True) is None
+    svo = scenes.single_sphere(6)
+    sc = _load(svo, tmpdir_vox, "sphere6_defaults")
+    pos, d = (1.3, 1.2, 0.9), (-0.8, -0.7, -0.4)
+    ref = yvref.ppu_frame(sc, pos, d, None, 0, 0, 0)
+    assert ref.shape == (480, 640)
+    o = yvo.render(svo.nodes(), svo.GetRoot(), yvo.camera(pos, d, (0, 0, 1), 70.0, 640, 480), threads=4)
+    assert (ref.view(np.uint8).reshape(480, 640, 4) == o["rgba"]).all()
+    assert (o["node"] != yvo.MISS_NODE).sum() > 1000
+    sc.close()
+
+
+@pytest.mark.parametrize("scene_name", ["fractal8", "sphere6", "dense4"])
+def test_spu_program_frames(scene_name):
+    """The SPU program end to end: same hits, same distance bits, same VoxData; its clear colour is (0,0,0,255)
+    (trace_spu.cpp:127); FetchNode is called exactly as often as the oracle counts node visits (:23 / :102)."""
+    svo = SCENES[scene_name]()
+    nodes, root = svo.nodes(), svo.GetRoot()
+    for name, pos, d, up, fov in scenes.CAMERAS:
+        W, H = 160, 128
+        cam = yvo.camera(pos, d, up, fov, W, H)
+        o = yvo.render(nodes, root, cam, threads=4)
+        d0, du, dv = yvref.init_ray_dir(d, up, fov, W, H)
+        odata, hit = oracle_data(nodes, o)
+        rgba, fetches, misses = yvref.spu_frame(nodes, root, pos, d0, du, dv, W, H, yvref.PROBE_SHADE)
+        expect = o["rgba"].copy()
+        expect[~hit] = (0, 0, 0, 255)
+        assert (rgba.view(np.uint8).reshape(H, W, 4) == expect).all(), name
+        assert fetches == o["stats"]["node_visits"], name
+        assert 0 < misses <= fetches
+        tbits, _, _ = yvref.spu_frame(nodes, root, pos, d0, du, dv, W, H, yvref.PROBE_T)
+        assert (tbits[hit] == o["t"].view(np.uint32)[hit]).all(), name
+        data, _, _ = yvref.spu_frame(nodes, root, pos, d0, du, dv, W, H, yvref.PROBE_DATA)
+        assert (data[hit] == odata[hit]).all(), name
+
+
+def test_spu_program_covers_whole_blocks_only():
+    """gridSize = viewSize / BlockSize (trace_spu.cpp:162): a 170x100 view is 10x6 blocks; the rest is never written."""
+    svo = scenes.fractal(8)
+    nodes, root = svo.nodes(), svo.GetRoot()
+    name, pos, d, up, fov = scenes.CAMERAS[1]
+    W, H = 170, 100
+    o = yvo.render(nodes, root, yvo.camera(pos, d, up, fov, W, H), threads=4, want_visits=True)
+    d0, du, dv = yvref.init_ray_dir(d, up, fov, W, H)
+    out, fetches, _ = yvref.spu_frame(nodes, root, pos, d0, du, dv, W, H, yvref.PROBE_SHADE, fill=0x11223344)
+    bw, bh = (W // yvref.SPU_BLOCK) * yvref.SPU_BLOCK, (H // yvref.SPU_BLOCK) * yvref.SPU_BLOCK
+    assert (out[bh:] == 0x11223344).all() and (out[:, bw:] == 0x11223344).all()
+    hit = o["node"] != yvo.MISS_NODE
+    expect = o["rgba"].copy()
+    expect[~hit] = (0, 0, 0, 255)
+    assert (out.view(np.uint8).reshape(H, W, 4)[:bh, :bw] == expect[:bh, :bw]).all()
+    assert fetches == int(o["visits"][:bh, :bw].sum())
+
+
+@pytest.mark.parametrize("spec", POOLS, ids=lambda s: "seed%d_d%d_n%g" % (s[0], s[1], s[2]))
+def test_random_pools_on_both_reference_builds(spec, tmpdir_vox):
+    """Seeded random pools (ragged depths, shared sub-trees, FullNode slots, junk in unused fields), random cameras
+    inside and outside the cube: the PPU renderer and the SPU program against the oracle, ids included."""
+    root, raw = _random_pool(*spec)
+    svo = yv.SVOData.FromNodes(root, tag_leaves(raw))
+    nodes = svo.nodes()
+    sc = _load(svo, tmpdir_vox, "pool_%d_%d" % (spec[0], spec[1]))
+    hits = 0
+    for i, (pos, d, up, fov) in enumerate(_cams(spec[0] * 13 + spec[1], 6)):
+        W, H = [(96, 80), (112, 64)][i % 2]
+        cam_spec = ("cam%d" % i, pos, d, up, fov)
+        o, hit = check_ppu_frame(sc, nodes, svo.GetRoot(), cam_spec, W, H)
+        d0, du, dv = yvref.init_ray_dir(d, up, fov, W, H)
+        tbits, fetches, _ = yvref.spu_frame(nodes, svo.GetRoot(), pos, d0, du, dv, W, H, yvref.PROBE_T)
+        data, _, _ = yvref.spu_frame(nodes, svo.GetRoot(), pos, d0, du, dv, W, H, yvref.PROBE_DATA)
+        assert (tbits[hit] == o["t"].view(np.uint32)[hit]).all(), (spec, i)
+        assert ((data >> 3)[hit] == o["node"][hit]).all() and ((data & 7)[hit] == o["child"][hit].astype(np.uint32)).all()
+        assert fetches == o["stats"]["node_visits"], (spec, i)
+        hits += int(hit.sum())
+    assert hits > 0
+    sc.close()

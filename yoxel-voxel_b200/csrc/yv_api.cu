@@ -297,7 +297,9 @@ int ensure_frame_buffers(yv_renderer *r) {
 }
 
 // RendererBase::InitRayDir (cell/renderer_base.h:50-61), float32 with the cg:: operator order
-// (nest/include/geometry/primitives/point.h:416-440,462-499); tan evaluated in double, rounded once.
+// (nest/include/geometry/primitives/point.h:416-440,462-499). `tan(cg::grad2rad(m_fov / 2)) / m_viewSize.x` (:56) has a
+// float argument, so C++ picks the float overload and the division is a float division: da = tanf(rad) / (float)W —
+// that is what the reference's own header computes when compiled (tests/test_reference_renderer.py).
 struct ViewBasis { float fwd[3], right[3], down[3], d2; };   // SSNA: the frame InitRayDir builds; down = -up', d2 = 2*da
 
 void init_ray_dir_raw(const float vdir[3], const float vup[3], float fov, int width, int height,
@@ -318,7 +320,7 @@ void init_ray_dir_raw(const float vdir[3], const float vup[3], float fov, int wi
   cross3(right, fwd, upv);
   const float half_deg = fov / 2;
   const float half_rad = half_deg * (float)(3.14159265358979323846 / 180.0);
-  const float da = (float)(std::tan((double)half_rad) / (double)width);
+  const float da = tanf(half_rad) / (float)width;
   const float w = (float)width, h = (float)height;
   for (int i = 0; i < 3; ++i) {
     du[i] = (2.0f * right[i]) * da;
