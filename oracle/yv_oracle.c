@@ -1,8 +1,10 @@
 /* yv_oracle.c — CPU oracle for the SVO ray-caster path.  TEST INFRASTRUCTURE ONLY.
  *
- * Plain-C restatement of the reference CPU tracer. PARITY UNPINNED by golden vectors (see yv_oracle.h):
- * the reference holds none for this path and its tracer does not build here; the traversal is
- * checked against the reference's scalar prototype compiled into oracle/_ref, the rest is unpinned.
+ * Plain-C restatement of the reference CPU tracer. The reference holds no golden vector for this path; the
+ * restatement is pinned by running the reference's own sources instead (see yv_oracle.h): cell/ppu_renderer.cpp and
+ * cell/spu/trace_spu.cpp compile unmodified into oracle/_ref behind stand-ins for the absent cpp/*.h, and this file
+ * reproduces their frames, hit distances, hit ids and node-fetch counts bit for bit. Only what the snapshot does not
+ * contain at all (AdjustDir eps, SetupTrace body, VoxData packing, Shade, LOD, SSNA, secondary rays) stays unpinned.
  *
  * Every function cites the reference lines whose behaviour it restates (paths relative to
  * /root/reference). All ray arithmetic is IEEE-754 binary32, round-to-nearest, and this file

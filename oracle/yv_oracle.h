@@ -4,17 +4,27 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it;
  * the product (yoxel-voxel_b200/) never links, imports or calls anything in oracle/.
  *
- * PARITY UNPINNED by golden vectors: the reference snapshot ships no golden vectors, no scene files and no test for
- * this path, and its tracer for the path does not compile (the cpp/ directory with trace_utils.h, vox_node.h,
- * shader.h, rdd.h is absent — SURVEY.md §0.2, §8c). What pins the oracle instead:
- *   - the traversal (ray set-up, FindFirstChild, GoNext, recursion order, which node is hit) against reference code
- *     run here: the snapshot's scalar prototype of the same traversal, cell/spu/trace_spu.c_, compiled unmodified
- *     into oracle/_ref (oracle/Makefile target `ref`, stand-in headers in oracle/ref_shim/) —
- *     tests/test_reference_prototype.py: identical on every ray without an exact edge crossing;
+ * How the oracle is pinned. The reference snapshot ships no golden vectors, no scene files and no test for this path,
+ * and as shipped its tracer does not compile (the cpp/ directory with stdafx.h, trace_utils.h, vox_node.h, shader.h,
+ * rdd.h, utils.h is absent, as are Boost.Thread and the Cell SDK — SURVEY.md §0.2, §8c). oracle/Makefile (target `ref`)
+ * compiles the reference's sources anyway — unmodified, from where they lie — behind stand-ins for exactly those
+ * headers (oracle/ref_shim/, each stating what it replaces and on what evidence), into oracle/_ref:
+ *   - cell/ppu_renderer.cpp (+ renderer_base.h, svorenderer.h, svodata.h, alignedarray.h, nest/include/geometry):
+ *     SVOData::Load, the setters and defaults, InitRayDir, the per-pixel loop, RecTrace, Simple/TreadedRenderer;
+ *   - cell/spu/trace_spu.cpp: the SPU program with the reference's own FindFirstChildSPU / GoNextSPU / RecTrace /
+ *     FetchNode cache / RenderBlock;
+ *   - cell/spu/trace_spu.c_: the first scalar (double) tracer.
+ *   tests/test_reference_renderer.py: on test scenes, seeded random pools and random cameras the oracle's RGBA frame,
+ *   the bits of every hit distance, the VoxData, the hit ids (through leaf words that name node and child), the
+ *   number of node fetches and InitRayDir's nine floats are identical to what those builds produce;
+ *   tests/golden/reference_golden.npz holds their output for the boxes where /root/reference does not exist
+ *   (tests/test_reference_golden.py, CPU and GPU); tests/test_reference_prototype.py covers the scalar prototype.
  *   - hand-computed rays, a brute-force voxel-grid marcher (a different algorithm), structural properties —
  *     tests/test_oracle.py.
- * Shading, VoxData packing, the AdjustDir epsilon, LOD, SSNA and the secondary rays have no reference code at all;
- * they are builder decisions written down in include/yv_format.h and remain unpinned.
+ * STILL UNPINNED — no reference code exists for it, so the stand-ins carry OUR statement of it and agreement there
+ * proves nothing: the AdjustDir epsilon, the body of SetupTrace (documented in voxel.tex:305-326 and mirrored by
+ * trace_spu.c_:79-93), the VoxData bit layout, the Shade formula, and everything the CUDA renderer added (LOD, SSNA,
+ * Phong lights) plus the secondary rays; those are builder decisions written down in include/yv_format.h.
  */
 #ifndef YV_ORACLE_H
 #define YV_ORACLE_H
