@@ -27,7 +27,10 @@ int yv_ref_shader_probe = 0;
 
 void *yv_ref_scene_load(const char *path) {
   SVOData *s = new SVOData;
-  s->Load(path);
+  std::streambuf *out = std::cout.rdbuf(NULL);      // Load announces itself on std::cout (svodata.h:33,49); callers
+  s->Load(path);                                    // such as bench.py own stdout, so the text is dropped
+  std::cout.rdbuf(out);
+  std::cout.clear();
   return s;
 }
 unsigned int yv_ref_scene_root(void *scene) { return static_cast<SVOData *>(scene)->GetRoot(); }
