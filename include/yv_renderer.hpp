@@ -8,8 +8,10 @@
 //                                                 CreateSPURenderer -> CreateB200Renderer)
 //   Render(d_ptr) .. demo/SVORenderer.h:36       (device-pointer variant)
 // so a driver written like cell/main.cpp:21-40 compiles unchanged against it. Inside the reference
-// tree, define YV_USE_REFERENCE_TYPES before including this header: the adapter then derives from the
-// tree's own ISVORenderer and uses cg::point_3f / point_2i / Color32.
+// tree, include the tree's svorenderer.h and define YV_USE_REFERENCE_TYPES before including this header: the
+// adapter then derives from the tree's own ISVORenderer, takes the tree's SVOData / point_3f / point_2i / Color32
+// and imports the scene's node pool on SetScene (integration/b200_renderer.cpp is that translation unit; the
+// tests build the reference's unmodified cell/main.cpp against it — see INTEGRATION.md).
 // Error behaviour follows the reference: no exceptions; RenderFrame() returns NULL when it cannot
 // render (no scene, no GPU — there is no CPU fallback); yv_last_error() has the reason.
 #pragma once
@@ -17,6 +19,7 @@
 #include <cstdint>
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "yv_b200.h"
 
@@ -71,11 +74,41 @@ namespace yv {
 
 class B200Renderer : public YV_NS ISVORenderer {
  public:
-  explicit B200Renderer(int device = 0) : r_(nullptr) { yv_renderer_create(device, &r_); }
-  ~B200Renderer() override { yv_renderer_destroy(r_); }
+  explicit B200Renderer(int device = 0) : r_(nullptr), own_(nullptr) { yv_renderer_create(device, &r_); }
+  ~B200Renderer() override { yv_renderer_destroy(r_); yv_svo_free(own_); }
   bool ok() const { return r_ != nullptr; }
 
+#ifndef YV_USE_REFERENCE_TYPES
   void SetScene(YV_NS SVOData *svo) override { if (r_) yv_set_scene(r_, svo ? svo->handle() : nullptr); }
+#else
+  // The tree's SVOData (cell/svodata.h:22-55) owns a host pool of 40-byte VoxNodes — the layout of yv_vox_node — and
+  // exposes GetRoot() and operator[] but not its size, so the pool handed to the library ends at the highest node id
+  // reachable from the root. The scene pointer stays borrowed (renderer_base.h:28); the library keeps its own copy.
+  void SetScene(SVOData *svo) override {
+    if (r_) yv_set_scene(r_, nullptr);
+    yv_svo_free(own_); own_ = nullptr;
+    if (svo) {
+      const VoxNodeId root = svo->GetRoot();
+      uint32_t count = 0;
+      if (!IsNull(root)) {
+        std::vector<VoxNodeId> todo(1, root);
+        std::vector<bool> seen;
+        while (!todo.empty()) {
+          const VoxNodeId id = todo.back(); todo.pop_back();
+          if (id >= seen.size()) seen.resize(id + 1 > 2 * seen.size() ? id + 1 : 2 * seen.size(), false);
+          if (seen[id]) continue;
+          seen[id] = true;
+          if (id + 1 > count) count = id + 1;
+          const VoxNode &n = (*svo)[id];
+          for (int c = 0; c < 8; ++c)
+            if (!GetLeafFlag(n.flags, c) && !IsNull(n.child[c])) todo.push_back(n.child[c]);
+        }
+      }
+      yv_svo_from_memory(root, count ? reinterpret_cast<const yv_vox_node *>(&(*svo)[0]) : nullptr, count, &own_);
+    }
+    if (r_) yv_set_scene(r_, own_);
+  }
+#endif
   void SetViewPos(const YV_NS point_3f &p) override { const float v[3] = { p.x, p.y, p.z }; if (r_) yv_set_view_pos(r_, v); }
   void SetViewDir(const YV_NS point_3f &p) override { const float v[3] = { p.x, p.y, p.z }; if (r_) yv_set_view_dir(r_, v); }
   void SetViewUp(const YV_NS point_3f &p) override { const float v[3] = { p.x, p.y, p.z }; if (r_) yv_set_view_up(r_, v); }
@@ -106,11 +139,14 @@ class B200Renderer : public YV_NS ISVORenderer {
 
  private:
   yv_renderer *r_;
+  yv_svo *own_;           // reference-types mode: the library-side copy of the tree's pool
 };
 
+#ifndef YV_USE_REFERENCE_TYPES
 // CreateSimpleRenderer / CreateThreadedRenderer / CreateSPURenderer (cell/svorenderer.h:26-30)
 inline std::shared_ptr<YV_NS ISVORenderer> CreateB200Renderer(int device = 0) {
   return std::shared_ptr<YV_NS ISVORenderer>(new B200Renderer(device));
 }
+#endif     // in the tree the factory is written with the tree's own shared_ptr (integration/b200_renderer.cpp)
 
 }  // namespace yv
