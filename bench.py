@@ -498,6 +498,15 @@ def main():
         cpu_baseline = {"value": o2["stats"]["rays"] / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
                         "sample": "one whole %dx%d frame, %d row strips (%.2f s)" % (a.width, a.height, cores, dt),
                         "ms_per_frame": 1e3 * dt}
+        # the CPU tracer at 1 thread, at the reference's constant of 4 (ppu_renderer.cpp:129) and on every core
+        sweep = {}
+        for t in sorted({1, 4, cores}):
+            if t == cores:
+                sweep[str(t)] = cpu_baseline["value"]
+            else:
+                ot, dtt = oracle_frame(nodes, root, a, 0, t)
+                sweep[str(t)] = ot["stats"]["rays"] / dtt / 1e6
+        cpu_baseline["mrays_by_threads"] = sweep
         gpu_img = r.RenderFrame()
         parity = {"rgba_identical_to_oracle": bool((gpu_img == o["rgba"]).all()),
                   "rays_identical": bool(o["stats"]["rays"] == int(rays_step)),

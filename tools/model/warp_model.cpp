@@ -60,6 +60,19 @@ int main(int argc,char**argv){
     }
     printf("T=%d: warp-trips base %.0f merged %.0f ratio %.3f\n",T,base,merged,merged/base);
   }
+  // tail relaunch model: a warp that is down to <= T live lanes queues those pixels and exits; a second launch traces the
+  // queued pixels from the start, 32 per warp in queue order
+  if(TW==8) for(int T: {1,2,3,4,6,8}){
+    double base=0, k1=0, k2=0; std::vector<int> q;
+    for(int ty=0;ty<H;ty+=4)for(int tx=0;tx<W;tx+=8){
+      int L[32],n=0,mx=0; for(int j=0;j<4;j++)for(int i=0;i<8;i++){int yy=ty+j,xx=tx+i; int v=(yy<H&&xx<W)?trips[yy*W+xx]:0; L[n++]=v; mx=std::max(mx,v);}
+      base+=(mx+3)/4*4;
+      int k=0; for(;;k+=4){ int act=0; for(int i=0;i<32;i++) if(L[i]>k) act++; if(act<=T) break; }
+      k1+=k; for(int i=0;i<32;i++) if(L[i]>k) q.push_back(L[i]);
+    }
+    for(size_t i=0;i<q.size();i+=32){ int mx=0; for(size_t j=i;j<std::min(q.size(),i+32);j++) mx=std::max(mx,q[j]); k2+=(mx+3)/4*4; }
+    printf("relaunch T=%d: queued %.1f%% of rays; warp-trips base %.0f -> %.0f + %.0f = ratio %.3f\n",T,100.0*q.size()/(W*H),base,k1,k2,(k1+k2)/base);
+  }
   // persistent-refill model: one warp streams over 8x8 tiles (Morton order inside), refills idle lanes when active<=thr (checked every 4 trips)
   if(TW==8) for(int thr: {0,4,8,12,16,20,24,28}){
     // stream: tiles in raster order; sample every 7th row of tiles to keep it fast
