@@ -4,6 +4,7 @@ depth=int(sys.argv[1])
 svo=yv.SVOData.SphereFractal(depth)
 recs,leaves=svo.packed()
 np.ascontiguousarray(recs,np.uint32).tofile('tools/model/_data/recs.bin')
+np.ascontiguousarray(leaves,np.uint32).tofile('tools/model/_data/leaves.bin')
 W,H=1920,1080
 d0,du,dv=yv.init_ray_dir((-1,-1,1.5),(0,0,1),70.0,W,H)
 np.concatenate([d0,du,dv]).astype(np.float32).tofile('tools/model/_data/cam.bin')
