@@ -469,20 +469,65 @@ def main():
                "checksum": int(img[::16, ::16].astype(np.uint64).sum())}
         r.SetStream(stream.cuda_stream)
     else:
-        # the timed region already ends with every pixel resident on GPU 0; add rank 0's D2H of the batch
-        d2h_s = 0.0
-        if rank == 0 and gather == "p2p":
-            pinned = torch.empty(target_bytes, dtype=torch.uint8, pin_memory=True)
-            t0 = time.perf_counter()
-            yv.lib().yv_copy_to_host(local, ctypes.c_void_p(pinned.data_ptr()), ctypes.c_void_p(target_ptr), target_bytes)
-            d2h_s = time.perf_counter() - t0
-        elif rank == 0:
-            t0 = time.perf_counter()
-            torch.stack(gather_list).cpu()
-            d2h_s = time.perf_counter() - t0
-        e2e = {"value": rays_step * a.steps / (total_s + d2h_s * a.steps) / 1e6, "unit": "Mrays/s",
-               "h2d_bytes_per_step": 40 * world, "d2h_bytes_per_step": target_bytes,
-               "api": "yv_render_frame_device into GPU 0's buffer (%s) + D2H of the gathered pixels on rank 0" % gather}
+        # One host frame (tiles) / one host batch of N frames (frames) in shared memory, registered with every GPU:
+        # each rank stores its pixels straight into it over its own PCIe link (yv_host_register +
+        # yv_render_frame_device), host camera in, host pixels out. Timed per step on the host clock around the
+        # synchronous call, L2 flushed and ranks aligned by a barrier outside the timed region, max over ranks.
+        e2e = None
+        try:
+            shared = multigpu.SharedHostFrame(dist, rank, world, local, target_bytes, os.environ.get("MASTER_PORT", "0"))
+        except yv.YVError as ex:
+            shared = None
+            if rank == 0:
+                print("shared host frame unavailable (%s)" % ex, file=sys.stderr)
+        okf = torch.tensor([1 if shared is not None else 0], device=dev)
+        dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+        if int(okf.item()) == 1:
+            h_dst = shared.ptr + (0 if tiles_mode else rank * frame_bytes)
+            e2e_t = []
+            for i in range(warm + a.steps):
+                if flush is not None:
+                    flush.zero_()
+                torch.cuda.synchronize()
+                dist.barrier()
+                t0 = time.perf_counter()
+                fpos, fdir = camera_for(frame_of(i - warm)) if (a.flythrough and i >= warm) else (pos, d)
+                r.SetViewPos(fpos); r.SetViewDir(fdir); r.SetViewUp(UP); r.SetFOV(FOV)
+                r.Render(h_dst, sync=True)
+                e2e_t.append(time.perf_counter() - t0)
+            e2e_s = torch.tensor([sum(e2e_t[warm:])], dtype=torch.float64, device=dev)
+            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+            dist.barrier()
+            same = None
+            if rank == 0 and gather == "p2p" and not a.flythrough:
+                # the frame the GPUs stored into host memory == the frame they stored into GPU 0 over NVLink
+                ref = np.empty(target_bytes, np.uint8)
+                yv.lib().yv_copy_to_host(local, ctypes.c_void_p(ref.ctypes.data), ctypes.c_void_p(target_ptr), target_bytes)
+                same = bool((ref == shared.array).all())
+            e2e = {"value": rays_step * a.steps / float(e2e_s.item()) / 1e6, "unit": "Mrays/s",
+                   "h2d_bytes_per_step": 40 * world, "d2h_bytes_per_step": target_bytes,
+                   "ms_per_step": 1e3 * float(e2e_s.item()) / a.steps,
+                   "api": "yv_set_view_* + yv_render_frame_device into one pinned host %s shared by the ranks (yv_host_register): "
+                          "every GPU stores its pixels over its own PCIe link" % ("frame" if tiles_mode else "batch of %d frames" % world),
+                   "identical_to_nvlink_gathered": same}
+        if shared is not None:
+            dist.barrier()
+            shared.close()
+        if e2e is None:
+            # fallback: the timed region already ends with every pixel resident on GPU 0; add rank 0's D2H of the batch
+            d2h_s = 0.0
+            if rank == 0 and gather == "p2p":
+                pinned = torch.empty(target_bytes, dtype=torch.uint8, pin_memory=True)
+                t0 = time.perf_counter()
+                yv.lib().yv_copy_to_host(local, ctypes.c_void_p(pinned.data_ptr()), ctypes.c_void_p(target_ptr), target_bytes)
+                d2h_s = time.perf_counter() - t0
+            elif rank == 0:
+                t0 = time.perf_counter()
+                torch.stack(gather_list).cpu()
+                d2h_s = time.perf_counter() - t0
+            e2e = {"value": rays_step * a.steps / (total_s + d2h_s * a.steps) / 1e6, "unit": "Mrays/s",
+                   "h2d_bytes_per_step": 40 * world, "d2h_bytes_per_step": target_bytes,
+                   "api": "yv_render_frame_device into GPU 0's buffer (%s) + D2H of the gathered pixels on rank 0" % gather}
 
     if rank != 0:
         if world > 1:

@@ -239,6 +239,15 @@ int yv_ipc_export(void *d_ptr, uint8_t handle[64]);
 int yv_ipc_open(int device, const uint8_t handle[64], void **d_ptr);
 int yv_ipc_close(void *d_ptr);
 
+/* ---- a caller-owned host frame as render target -------------------------------------------- */
+/* RenderFrame's consumer reads host memory (const Color32*, cell/svorenderer.h:23; cell/main.cpp:36). With several
+ * processes (one per GPU) rendering parts of one frame, or frames of one batch, the cheapest way to the host is for
+ * every GPU to store its pixels straight into ONE host frame over its own PCIe link: map a shared-memory segment in
+ * every process, register it here, and pass the returned address to yv_render_frame_device. yv_host_register
+ * page-locks [host_ptr, host_ptr + bytes) for `device` and returns the address the kernel stores through. */
+int yv_host_register(int device, void *host_ptr, size_t bytes, void **device_ptr);
+int yv_host_unregister(void *host_ptr);
+
 /* RendererBase::InitRayDir (cell/renderer_base.h:50-61): the per-frame ray basis the kernel
  * consumes, computed on the host (pure function; exposed for tests and external ray generators) */
 int yv_init_ray_dir(const float dir[3], const float up[3], float fov_deg, int width, int height,

@@ -70,3 +70,36 @@ def test_band_gather_world2_gloo(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert np.load(tmp_path / "ok.npy")[0]
+
+
+def _shared_frame_worker(rank, world, port, tmpdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    svo = scenes.fractal(8)
+    name, pos, d, up, fov = scenes.CAMERAS[1]
+    W, H, band = 96, 70, 16
+    cam = yvo.camera(pos, d, up, fov, W, H)
+    # the host side of the multi-GPU e2e path: one frame in shared memory, every rank writes its own row blocks
+    # straight into it (on the GPU box the writer is the render kernel, through yv_host_register; here the oracle)
+    shared = multigpu.SharedHostFrame(dist, rank, world, 0, W * H * 4, "test%d" % port, register=False)
+    frame = shared.array.reshape(H, W, 4)
+    rows = multigpu.interleaved_rows(rank, world, H, band)
+    full = yvo.render(svo.nodes(), svo.GetRoot(), cam)["rgba"]
+    frame[rows] = full[rows]
+    dist.barrier()
+    if rank == 0:
+        np.save(os.path.join(tmpdir, "shared_ok.npy"), np.array([(frame == full).all(), not os.path.exists(shared.path)]))
+    dist.barrier()
+    del frame
+    shared.close()
+    dist.destroy_process_group()
+
+
+def test_shared_host_frame_world2_gloo(tmp_path):
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_shared_frame_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ok = np.load(tmp_path / "shared_ok.npy")
+    assert ok[0] and ok[1]

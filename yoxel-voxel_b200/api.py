@@ -148,6 +148,8 @@ def lib():
         "yv_ipc_export": (i32, [vp, vp]),
         "yv_ipc_open": (i32, [i32, vp, P(vp)]),
         "yv_ipc_close": (i32, [vp]),
+        "yv_host_register": (i32, [i32, vp, C.c_size_t, P(vp)]),
+        "yv_host_unregister": (i32, [vp]),
         "yv_init_ray_dir": (i32, [P(f32), P(f32), f32, i32, i32, P(f32), P(f32), P(f32)]),
         "yv_device_count": (i32, []),
         "yv_device_name": (i32, [i32, C.c_char_p, C.c_size_t]),

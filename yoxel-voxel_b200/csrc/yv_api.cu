@@ -1358,4 +1358,24 @@ int yv_ipc_close(void *d_ptr) {
   return YV_OK;
 }
 
+int yv_host_register(int device, void *host_ptr, size_t bytes, void **device_ptr) {
+  if (!host_ptr || !device_ptr || bytes == 0) return fail(YV_ERR_ARG, "null argument");
+  YV_CUDA(cudaSetDevice(device));
+  YV_CUDA(cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+  void *d = nullptr;
+  const cudaError_t e = cudaHostGetDevicePointer(&d, host_ptr, 0);
+  if (e != cudaSuccess) {
+    cudaHostUnregister(host_ptr);
+    return fail(YV_ERR_CUDA, std::string("cudaHostGetDevicePointer: ") + cudaGetErrorString(e));
+  }
+  *device_ptr = d;
+  return YV_OK;
+}
+
+int yv_host_unregister(void *host_ptr) {
+  if (!host_ptr) return YV_OK;
+  YV_CUDA(cudaHostUnregister(host_ptr));
+  return YV_OK;
+}
+
 }  // extern "C"

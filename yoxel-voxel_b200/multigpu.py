@@ -13,6 +13,7 @@ Two gather paths:
 torch.distributed is used only for the handle exchange, barriers and the NCCL baseline.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -91,3 +92,45 @@ def open_gather_target(dist, rank, world, device, nbytes):
         return buf.ptr, buf
     m = PeerMapping(device, payload[0])
     return m.ptr, m
+
+
+class SharedHostFrame:
+    """One host frame (or batch of frames) shared by the ranks of a node: a /dev/shm segment mapped by every process and
+    registered with its GPU (yv_host_register), so that each GPU stores its share of the pixels straight into host
+    memory over its own PCIe link — the counterpart, for a host consumer, of the NVLink gather into GPU 0
+    (the SPEs' DMA of finished blocks into the PPU's colour buffer, cell/spu/trace_spu.cpp:171-176).
+    Collective over `dist` (any backend; dist=None for a single process). `register=False` maps without a GPU."""
+
+    def __init__(self, dist, rank, world, device, nbytes, tag, register=True):
+        import mmap
+        self.path = "/dev/shm/yv_frame_%s.bin" % tag
+        self.nbytes, self.rank, self.registered = int(nbytes), rank, False
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(self.nbytes)
+        if dist is not None and world > 1:
+            dist.barrier()
+        self._f = open(self.path, "r+b")
+        self._mm = mmap.mmap(self._f.fileno(), self.nbytes)
+        self.array = np.frombuffer(self._mm, dtype=np.uint8)
+        self.host_ptr = self.array.ctypes.data
+        self.ptr = self.host_ptr
+        if register:
+            d = C.c_void_p()
+            api._check(api.lib().yv_host_register(int(device), C.c_void_p(self.host_ptr), self.nbytes, C.byref(d)))
+            self.ptr, self.registered = d.value, True
+        if dist is not None and world > 1:
+            dist.barrier()
+        if rank == 0:
+            os.unlink(self.path)              # every rank holds its mapping; the name is no longer needed
+
+    def close(self):
+        if self.registered:
+            api.lib().yv_host_unregister(C.c_void_p(self.host_ptr))
+            self.registered = False
+        self.array = None
+        try:
+            self._mm.close()
+        except BufferError:
+            pass
+        self._f.close()
