@@ -3,6 +3,8 @@
 Bars (BASELINE.json north_star): hit node/child ids bit-exact; hit distance t within 1e-4 relative;
 per-pixel RGB within 1 LSB. The kernel uses the same float32 operations in the same order as the
 oracle, so the tests additionally report (and require) exact equality of t and RGBA."""
+import os
+
 import numpy as np
 import pytest
 
@@ -259,6 +261,30 @@ def test_counters_equal_oracle_visits(renderer):
         assert (visits == o["visits"]).all()
         assert pops.sum() > 0
     renderer.EnableCounters(False)
+
+
+def test_render_into_a_registered_host_frame(renderer):
+    """yv_host_register: a caller-owned (here: shared-memory) host frame as the render target; two interleaved halves
+    written by two launches compose the frame the renderer itself returns."""
+    from yoxel_voxel_b200 import multigpu
+    svo = scenes.fractal(10)
+    renderer.SetOption("persistent", 0)
+    renderer.SetScene(svo)
+    cam = scenes.CAMERAS[1]
+    W, H = 640, 400
+    img, *_ = _render_gpu(renderer, cam, W, H)
+    shared = multigpu.SharedHostFrame(None, 0, 1, 0, W * H * 4, "pytest%d" % os.getpid())
+    try:
+        assert shared.registered and not os.path.exists(shared.path)
+        shared.array[:] = 0x7f
+        for phase in (0, 1):                          # what ranks 0 and 1 of a two-GPU frame would each store
+            renderer.SetInterleave(32, 2, phase)
+            renderer.Render(shared.ptr)
+        renderer.SetInterleave(32, 1, 0)
+        assert (shared.array.reshape(H, W, 4) == img).all()
+    finally:
+        renderer.SetInterleave(32, 1, 0)
+        shared.close()
 
 
 def test_device_pointer_render_and_timing(renderer):
