@@ -232,3 +232,24 @@ def test_random_pools_on_both_reference_builds(spec, tmpdir_vox):
         hits += int(hit.sum())
     assert hits > 0
     sc.close()
+
+
+def test_edited_pools_are_valid_reference_pools(tmpdir_vox):
+    """A pool produced by DynamicSVO editing (BuildRange GROW / CLEAR, free-list reuse, collapsed octets) and an
+    iso-volume pool, Save()d, Load()ed by the reference's SVOData and rendered by the reference's renderer: what
+    the builder writes is what the reference reads (ore/src/main.cpp:121-124 on one side, cell/svodata.h:31-50 on the
+    other), and the oracle agrees on every pixel."""
+    bld = yv.DynamicSVO()
+    bld.BuildRange(6, (32, 33, 30), yv.BuildMode.GROW, yv.MakeSphereSource(19, (200, 120, 40), False))
+    bld.BuildRange(6, (40, 30, 22), yv.BuildMode.GROW, yv.MakeSphereSource(9, (40, 220, 90), False))
+    bld.BuildRange(6, (32, 33, 14), yv.BuildMode.CLEAR, yv.MakeSphereSource(8, (250, 250, 250), True))   # Demo.cpp:109
+    bld.BuildRange(6, (22, 40, 40), yv.BuildMode.CLEAR, yv.MakeSphereSource(6, (250, 250, 250), True))
+    cams = [("edit_front", (0.5, 0.5, -1.2), (0.05, 0.1, 1.0), (0, 1, 0), 60.0), scenes.CAMERAS[2], scenes.CAMERAS[4]]
+    for name, svo in (("edited", bld), ("iso8", yv.SVOData.IsoVolume(8, threads=8))):
+        sc = _load(svo, tmpdir_vox, name)
+        hits = 0
+        for cam in cams:
+            o, hit = check_ppu_frame(sc, svo.nodes(), svo.GetRoot(), cam, 160, 120)
+            hits += int(hit.sum())
+        assert hits > 2000, name
+        sc.close()
