@@ -29,8 +29,12 @@ def available():
         return True
     if not os.path.exists("/root/reference/cell/ppu_renderer.cpp"):
         return False
-    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
-    return True
+    try:
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"),
+                               "_ref/libppu_renderer_ref.so", "_ref/libtrace_spu_f32_ref.so"])
+    except (subprocess.CalledProcessError, OSError):
+        return False
+    return os.path.exists(PPU_SO) and os.path.exists(SPU_SO)
 
 
 def _v(a):
