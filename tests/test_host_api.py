@@ -172,3 +172,12 @@ def test_cpp_adapter_builds_and_refuses_without_gpu(tmp_path):
         pytest.skip("GPU present: covered by the gpu test")
     p = subprocess.run([exe, "--fractal", "8", str(tmp_path / "o.ppm"), "64", "48"], capture_output=True, text=True)
     assert p.returncode == 2 and "no CPU fallback" in p.stderr       # RenderFrame() == NULL, like the reference
+
+
+def test_host_register_rejects_bad_arguments():
+    import ctypes as C
+    d = C.c_void_p()
+    assert yv.lib().yv_host_register(0, None, 4096, C.byref(d)) == -1            # YV_ERR_ARG, before any CUDA call
+    buf = (C.c_uint8 * 4096)()
+    assert yv.lib().yv_host_register(0, C.cast(buf, C.c_void_p), 0, C.byref(d)) == -1
+    assert yv.lib().yv_host_unregister(None) == 0
