@@ -64,6 +64,9 @@ typedef struct yv_source yv_source;        /* VoxelSource (ore/src/main.cpp:106-
 int yv_svo_create(yv_svo **out);                                         /* DynamicSVO() — empty scene        */
 int yv_source_sphere(int radius, uint8_t r, uint8_t g, uint8_t b, int inverted, yv_source **out);   /* MakeSphereSource (:69) */
 int yv_source_raw(const int size[3], const uint32_t *voxdata, yv_source **out);                      /* MakeRawSource (:37-52): VoxData words, x fastest, 0 = empty */
+/* MakeRawSource in the reference's own argument form (:37-52, call site scene_gen.py:20-79): per voxel a Color32 (R,G,B,A)
+ * and a Normal32 (int8 x,y,z,pad); alpha 0 = empty, 255 = surface voxel, anything else = buried (part of a FullNode) */
+int yv_source_raw_colors_normals(const int size[3], const uint8_t *colors_rgba, const int8_t *normals_xyzw, yv_source **out);
 int yv_source_iso(const int size[3], const uint8_t *data, int iso_level, int inside,
                   uint8_t r, uint8_t g, uint8_t b, yv_source **out);     /* MakeIsoSource + SetIsoLevel/SetInside/SetColor (:54-67,112-116) */
 void yv_source_free(yv_source *src);

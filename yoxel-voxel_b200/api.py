@@ -89,6 +89,7 @@ def lib():
         "yv_svo_create": (i32, [P(vp)]),
         "yv_source_sphere": (i32, [i32, C.c_uint8, C.c_uint8, C.c_uint8, i32, P(vp)]),
         "yv_source_raw": (i32, [P(i32), vp, P(vp)]),
+        "yv_source_raw_colors_normals": (i32, [P(i32), vp, vp, P(vp)]),
         "yv_source_iso": (i32, [P(i32), vp, i32, i32, C.c_uint8, C.c_uint8, C.c_uint8, P(vp)]),
         "yv_source_free": (None, [vp]),
         "yv_source_size": (i32, [vp, P(i32), P(i32)]),
@@ -227,7 +228,18 @@ def MakeSphereSource(radius, color, inverted=False):          # ore/src/main.cpp
     return VoxelSource(h)
 
 
-def MakeRawSource(voxdata):                                   # ore/src/main.cpp:37-52; array [z][y][x] of VoxData words
+def MakeRawSource(voxdata, colors=None, normals=None):         # ore/src/main.cpp:37-52
+    """MakeRawSource(voxdata): array [z][y][x] of VoxData words, 0 = empty; or, as the reference's scripts call it
+    (scene_gen.py:79), MakeRawSource(size, colors, normals) with size = (x, y, z), colors uint8 [z][y][x][4] (alpha 0 empty,
+    255 surface, else buried) and normals int8 [z][y][x][4]."""
+    if colors is not None:
+        sx, sy, sz = (int(v) for v in voxdata)
+        col = np.ascontiguousarray(colors, dtype=np.uint8).reshape(sz, sy, sx, 4)
+        nrm = np.ascontiguousarray(normals, dtype=np.int8).reshape(sz, sy, sx, 4)
+        h = C.c_void_p()
+        _check(lib().yv_source_raw_colors_normals((C.c_int * 3)(sx, sy, sz), col.ctypes.data_as(C.c_void_p),
+                                                  nrm.ctypes.data_as(C.c_void_p), C.byref(h)))
+        return VoxelSource(h)
     vox = np.ascontiguousarray(voxdata, dtype=np.uint32)
     size = (C.c_int * 3)(vox.shape[2], vox.shape[1], vox.shape[0])
     h = C.c_void_p()

@@ -38,24 +38,47 @@ RangeClass SphereSource::TryRange(const int p[3], int size, uint32_t &vox) const
 RawSource::RawSource(const int size[3], const uint32_t *v) {
   for (int a = 0; a < 3; ++a) size_[a] = std::max(1, size[a]);
   vox_.assign(v, v + (size_t)size_[0] * size_[1] * size_[2]);
+  kind_.resize(vox_.size());
+  for (size_t i = 0; i < vox_.size(); ++i) kind_[i] = vox_[i] ? 2 : 0;
+}
+RawSource::RawSource(const int size[3], const uint8_t *c, const int8_t *n) {
+  for (int a = 0; a < 3; ++a) size_[a] = std::max(1, size[a]);
+  const size_t count = (size_t)size_[0] * size_[1] * size_[2];
+  vox_.assign(count, 0u);
+  kind_.assign(count, 0);
+  for (size_t i = 0; i < count; ++i) {
+    const uint8_t alpha = c[4 * i + 3];
+    if (alpha == 0) continue;
+    if (alpha != 255) { kind_[i] = 1; continue; }
+    kind_[i] = 2;
+    vox_[i] = pack_voxdata(c[4 * i], c[4 * i + 1], c[4 * i + 2], (float)n[4 * i], (float)n[4 * i + 1], (float)n[4 * i + 2]);
+  }
 }
 void RawSource::GetSize(int s[3]) const { for (int a = 0; a < 3; ++a) s[a] = size_[a]; }
 void RawSource::GetPivot(int p[3]) const { p[0] = p[1] = p[2] = 0; }
 RangeClass RawSource::TryRange(const int p[3], int size, uint32_t &vox) const {
   int lo[3], hi[3];
+  bool clipped = false;
   for (int a = 0; a < 3; ++a) {
     lo[a] = std::max(0, p[a]); hi[a] = std::min(size_[a], p[a] + size);
     if (lo[a] >= hi[a]) return RangeClass::Empty;
+    clipped = clipped || lo[a] != p[a] || hi[a] != p[a] + size;
   }
   if (size == 1) {
-    vox = vox_[((size_t)lo[2] * size_[1] + lo[1]) * size_[0] + lo[0]];
-    return vox ? RangeClass::Voxel : RangeClass::Empty;
+    const size_t i = ((size_t)lo[2] * size_[1] + lo[1]) * size_[0] + lo[0];
+    vox = vox_[i];
+    return kind_[i] == 2 ? RangeClass::Voxel : (kind_[i] == 1 ? RangeClass::Full : RangeClass::Empty);
   }
+  bool any = false, all_buried = !clipped;      // a cube that sticks out of the brick is never Full
   for (int z = lo[2]; z < hi[2]; ++z)
     for (int y = lo[1]; y < hi[1]; ++y)
-      for (int x = lo[0]; x < hi[0]; ++x)
-        if (vox_[((size_t)z * size_[1] + y) * size_[0] + x]) return RangeClass::Mixed;
-  return RangeClass::Empty;
+      for (int x = lo[0]; x < hi[0]; ++x) {
+        const uint8_t k = kind_[((size_t)z * size_[1] + y) * size_[0] + x];
+        any = any || k != 0;
+        all_buried = all_buried && k == 1;
+        if (any && !all_buried) return RangeClass::Mixed;
+      }
+  return any ? RangeClass::Full : RangeClass::Empty;
 }
 
 IsoBrickSource::IsoBrickSource(const int size[3], const uint8_t *d) {

@@ -47,15 +47,20 @@ class SphereSource : public VoxelSource {
   int radius_; uint8_t col_[3]; bool inverted_;
 };
 
-// MakeRawSource(size, colours, normals) (ore/src/main.cpp:37-52): dense brick of VoxData words, 0 = empty
+// MakeRawSource(size, colours, normals) (ore/src/main.cpp:37-52): dense brick, x fastest. Two forms:
+//   VoxData words, 0 = empty;
+//   the reference's own pair of arrays — Color32 RGBA and Normal32 (int8 x,y,z,pad) per voxel — where the colour's
+//   alpha tells the kind of voxel the way scene_gen.py:20-62 writes it: 0 empty, 255 surface, anything else buried
+//   ("internal": no data, becomes part of a FullNode).
 class RawSource : public VoxelSource {
  public:
-  RawSource(const int size[3], const uint32_t *voxdata);   // x fastest; copies
+  RawSource(const int size[3], const uint32_t *voxdata);   // copies
+  RawSource(const int size[3], const uint8_t *colors_rgba, const int8_t *normals_xyzw);
   void GetSize(int size[3]) const override;
   void GetPivot(int pivot[3]) const override;
   RangeClass TryRange(const int p[3], int size, uint32_t &voxdata) const override;
  private:
-  int size_[3]; std::vector<uint32_t> vox_;
+  int size_[3]; std::vector<uint32_t> vox_; std::vector<uint8_t> kind_;   // kind: 0 empty, 1 buried, 2 surface voxel
 };
 
 // MakeIsoSource(size, uint8 data) + SetIsoLevel / SetInside / SetColor (ore/src/main.cpp:54-67,112-116)

@@ -1271,6 +1271,11 @@ int yv_source_raw(const int size[3], const uint32_t *voxdata, yv_source **out) {
   *out = new yv_source{ new yv::RawSource(size, voxdata) };
   return YV_OK;
 }
+int yv_source_raw_colors_normals(const int size[3], const uint8_t *colors_rgba, const int8_t *normals_xyzw, yv_source **out) {
+  if (!out || !size || !colors_rgba || !normals_xyzw || size[0] < 1 || size[1] < 1 || size[2] < 1) return fail(YV_ERR_ARG, "bad argument");
+  *out = new yv_source{ new yv::RawSource(size, colors_rgba, normals_xyzw) };
+  return YV_OK;
+}
 int yv_source_iso(const int size[3], const uint8_t *data, int iso_level, int inside, uint8_t r, uint8_t g, uint8_t b, yv_source **out) {
   if (!out || !size || !data || size[0] < 1 || size[1] < 1 || size[2] < 1) return fail(YV_ERR_ARG, "bad argument");
   yv::IsoBrickSource *s = new yv::IsoBrickSource(size, data);
