@@ -13,6 +13,8 @@
  *     SVOData::Load, the setters and defaults, InitRayDir, the per-pixel loop, RecTrace, Simple/TreadedRenderer;
  *   - cell/spu/trace_spu.cpp: the SPU program with the reference's own FindFirstChildSPU / GoNextSPU / RecTrace /
  *     FetchNode cache / RenderBlock;
+ *   - cell/main.cpp + cell/spu_renderer.cpp + cell/spu/trace_spu.cpp: the complete Cell application as one executable
+ *     (oracle/_ref/cell_main_spu), its SPEs played by the host CPU; the frame it writes equals this oracle's;
  *   - cell/spu/trace_spu.c_: the first scalar (double) tracer.
  *   tests/test_reference_renderer.py: on test scenes, seeded random pools and random cameras the oracle's RGBA frame,
  *   the bits of every hit distance, the VoxData, the hit ids (through leaf words that name node and child), the
