@@ -574,15 +574,17 @@ def main():
     alg_bytes_step = vis_step * NODE_BYTES + px_step * PIXEL_BYTES        # all GPUs
     kernel_s = total_s / a.steps
     achieved = alg_bytes_step / world / kernel_s / 1e9                    # per GPU (per launch)
-    traffic = None
+    traffic, l2_traffic = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic = tj.get("dram_bytes_per_launch")
+            l2_traffic = tj.get("l2_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "yv::render_frame<%s>" % schedule,
+                "traffic": traffic, "l2_traffic": l2_traffic, "peak_source": peak_src, "kernel": "yv::render_frame<%s>" % schedule,
                 "algorithmic_bytes_per_launch": alg_bytes_step / world,
                 "node_visits_per_ray": vis_step / rays_step, "pop_refetches_per_ray": pop_step / rays_step,
                 "kernel_ms": 1e3 * kernel_s}
