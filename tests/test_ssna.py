@@ -4,6 +4,8 @@ demo/SVORenderer.cpp:55-79,126-147; normal reconstruction after demo/dumps/ztool
 The kernel bodies are absent from the snapshot, so include/yv_format.h "SSNA" is the written spec. The CPU tests pin
 the oracle's statement of it to closed-form cases (taps, planes, a sphere); the GPU tests require the CUDA passes
 to reproduce the oracle's frame bit for bit."""
+import os
+
 import numpy as np
 import pytest
 
@@ -240,3 +242,46 @@ def test_gpu_ssna_device_render_and_partition_errors():
         assert np.array_equal(_gpu_frame(renderer, OUTSIDE, W, H)[..., 3], host[..., 3])
     finally:
         renderer.close()
+
+
+def _view_space(cam_dir, up, n_world):
+    fwd = np.array(cam_dir, np.float64); fwd /= np.linalg.norm(fwd)
+    right = np.cross(fwd, np.array(up, np.float64)); right /= np.linalg.norm(right)
+    down = -np.cross(right, fwd)
+    return np.array([n_world @ right, n_world @ down, n_world @ fwd])
+
+
+def _check_against_prototype(z, proto):
+    """The oracle's SSNA normal, taken back to view space, is minus the prototype's (which points away from the
+    camera: nz = +d^2 z^2, ztools.py:38) at every pixel the prototype defines (it drops the one-pixel border)."""
+    H, W = z.shape
+    cam_dir, up = (0.3, -0.5, 0.2), (0, 0, 1)
+    cam = yvo.camera((0.1, 0.2, 0.3), cam_dir, up=up, fov=70.0, width=W, height=H)         # ztools.py:16: fov = 70
+    worst = 0.0
+    for y in range(1, H - 1, 3):
+        for x in range(1, W - 1, 2):
+            n = yvo.ssna_normal(cam, z, x, y)
+            nv = _view_space(cam_dir, up, n.astype(np.float64))
+            worst = max(worst, float(np.abs(nv + proto[y - 1, x - 1]).max()))
+    assert worst < 2e-4, worst
+
+
+def test_normals_equal_the_reference_prototype_golden():
+    """calcNormals of demo/dumps/ztools.py:23-44, run by tests/golden/make_ztools_golden.py, against the oracle."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ztools_normals.npz"))
+    for i in range(2):
+        _check_against_prototype(g["z%d" % i], g["n%d" % i])
+
+
+def test_normals_equal_the_reference_prototype_live():
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_ztools_golden.py")
+    spec = importlib.util.spec_from_file_location("make_ztools_golden", path)
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    if not os.path.exists(mod.ZTOOLS):
+        pytest.skip("the prototype lives in /root/reference")
+    calc = mod.load_calc_normals()
+    rng = np.random.RandomState(8)
+    y, x = np.mgrid[:40, :56].astype(np.float64)
+    z = (0.9 + 0.2 * np.sin(x / 5.0) * np.sin(y / 6.0) + rng.rand(40, 56) * 2e-3).astype(np.float32)
+    _check_against_prototype(z, calc(z.astype(np.float64)))
