@@ -1,0 +1,89 @@
+"""The reference's Python boundary: its scripts do `from ore.ore import *` (gen_spheres.py:2, gen_largevol.py:2,
+scene_gen.py:3, qtview.py:10) and `ore` wraps a compiled `_ore` (ore/src/main.cpp) whose C++ sources are not in the
+snapshot. integration/python/ore provides that package over libyv_b200; here the reference's OWN gen_spheres.py is
+executed against it — the file is read from /root/reference and run as it stands, except that its Python-2 print
+statements become print() calls — and the scene it saves must be the batch builder's sphere fractal."""
+import io
+import os
+import re
+import sys
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+import scenes
+import yvo
+import yoxel_voxel_b200 as yv
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "integration", "python"))
+REF = "/root/reference"
+
+
+def py2_prints_to_calls(src):
+    """`print a, b` -> `print(a, b)`; a trailing comma becomes end=' '. Nothing else is touched."""
+    out = []
+    for line in src.splitlines():
+        m = re.match(r"^(\s*)print\s+(.*?)(,?)\s*$", line)
+        if m and not m.group(2).startswith("("):
+            line = "%sprint(%s%s)" % (m.group(1), m.group(2), ", end=' '" if m.group(3) else "")
+        out.append(line)
+    return "\n".join(out) + "\n"
+
+
+def test_module_surface_matches_the_bindings():
+    from ore import ore
+    for name in ("point_3i", "point_3f", "BuildMode", "VoxelSource", "RawSource", "SphereSource", "IsoSource",
+                 "MakeRawSource", "MakeSphereSource", "MakeIsoSource", "DynamicSVO", "p3i", "p3f"):       # main.cpp:84-130, ore.py:6-12
+        assert hasattr(ore, name), name
+    for meth in ("BuildRange", "Save", "Load", "TraceRay", "CountChangedPages", "CountTransfrerSize", "GetNodeCountByLevel1"):
+        assert hasattr(ore.DynamicSVO, meth), meth
+    assert ore.BuildMode.GROW != ore.BuildMode.CLEAR
+    p = ore.p3i(np.array([1.9, 2.1, 3.0]))
+    assert (p.x, p.y, p.z) == (1, 2, 3)
+    s = ore.MakeSphereSource(4, (10, 20, 30), False)
+    assert tuple(s.GetSize()) == (9, 9, 9) and tuple(s.GetPivot()) == (4, 4, 4)
+    with pytest.raises(ValueError):
+        ore.MakeIsoSource(ore.point_3i(4, 4, 4), np.zeros(10, np.uint8))          # "incorrect data buffer size", main.cpp:62-63
+
+
+def test_editing_through_the_ore_surface():
+    from ore.ore import DynamicSVO, MakeSphereSource, MakeIsoSource, BuildMode, p3i, point_3i
+    bld = DynamicSVO()
+    bld.BuildRange(6, p3i((32, 33, 30)), BuildMode.GROW, MakeSphereSource(19, (200, 120, 40), False))
+    ref = yv.SVOData.SingleSphere(6, (32, 33, 30), 19, (200, 120, 40))
+    assert bld.nodecount == ref.nodecount
+    assert bld.CountChangedPages() > 0 and bld.CountTransfrerSize() % (256 * 40) == 0
+    assert bld.CountChangedPages() == 0 and bld.CountTransfrerSize() == 0         # nothing written since the last poll
+    bld.BuildRange(6, p3i((32, 33, 12)), BuildMode.CLEAR, MakeSphereSource(6, (250, 250, 250), True))
+    assert bld.CountChangedPages() > 0
+    vol = np.zeros((8, 8, 8), np.uint8); vol[2:6, 2:6, 2:6] = 255
+    iso = MakeIsoSource(point_3i(8, 8, 8), vol)
+    iso.SetIsoLevel(200); iso.SetColor((1, 2, 3))
+    n0 = bld.nodecount
+    bld.BuildRange(6, point_3i(50, 50, 50), BuildMode.GROW, iso)
+    assert bld.nodecount > n0 and sum(bld.GetNodeCountByLevel1()) == bld.nodecount
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "gen_spheres.py")), reason="the script lives in /root/reference")
+def test_the_references_gen_spheres_script_runs_on_the_library(tmp_path):
+    src = py2_prints_to_calls(open(os.path.join(REF, "gen_spheres.py")).read())
+    (tmp_path / "data").mkdir()
+    cwd = os.getcwd()
+    os.chdir(str(tmp_path))
+    try:
+        with redirect_stdout(io.StringIO()) as log:
+            exec(compile(src, "gen_spheres.py", "exec"), {"__name__": "__main__"})
+    finally:
+        os.chdir(cwd)
+    assert "saveing..." in log.getvalue()                                   # gen_spheres.py:34
+    made = yv.SVOData().Load(str(tmp_path / "data" / "spheres.vox"))        # :35
+    ref = scenes.fractal(11)                                                # the batch builder's statement of the same scene
+    assert made.nodecount == ref.nodecount
+    for name, pos, d, up, fov in (scenes.CAMERAS[1], scenes.CAMERAS[2]):
+        cam = yvo.camera(pos, d, up, fov, 160, 120)
+        a = yvo.render(made.nodes(), made.GetRoot(), cam, threads=8)
+        b = yvo.render(ref.nodes(), ref.GetRoot(), cam, threads=8)
+        assert (a["rgba"] == b["rgba"]).all() and a["t"].tobytes() == b["t"].tobytes()
+        assert (a["node"] != yvo.MISS_NODE).sum() > 1000
