@@ -87,3 +87,39 @@ def test_the_references_gen_spheres_script_runs_on_the_library(tmp_path):
         b = yvo.render(ref.nodes(), ref.GetRoot(), cam, threads=8)
         assert (a["rgba"] == b["rgba"]).all() and a["t"].tobytes() == b["t"].tobytes()
         assert (a["node"] != yvo.MISS_NODE).sum() > 1000
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "gen_largevol.py")), reason="the script lives in /root/reference")
+def test_the_references_gen_largevol_script_runs_on_the_library(tmp_path):
+    """gen_largevol.py iso-surfaces whatever bricks of data/VolumeData/d_0219_NNNN it finds (256x256x128 uint8 each, the CT
+    data set is not shipped) and skips the rest (:18-24). Two seeded bricks are put in place; the scene the script saves
+    equals the one the same two BuildRange calls give through this repo's own API."""
+    rng = np.random.RandomState(219)
+    z, y, x = np.mgrid[0:128, 0:256, 0:256].astype(np.float32)
+    bricks = {}
+    for (k, j, i) in ((3, 0, 0), (3, 0, 1)):
+        c = rng.uniform(60, 190, 3)
+        r2 = (x - c[0]) ** 2 + (y - c[1]) ** 2 + ((z - 64) * 2) ** 2
+        bricks[(k, j, i)] = np.clip(255 - np.sqrt(r2) * 2.5, 0, 255).astype(np.uint8)
+    vd = tmp_path / "data" / "VolumeData"
+    vd.mkdir(parents=True)
+    for (k, j, i), d in bricks.items():
+        d.tofile(str(vd / ("d_0219_%04d" % (k * 64 + j * 8 + i))))                      # gen_largevol.py:17
+    src = py2_prints_to_calls(open(os.path.join(REF, "gen_largevol.py")).read())
+    cwd = os.getcwd()
+    os.chdir(str(tmp_path))
+    try:
+        with redirect_stdout(io.StringIO()) as log:
+            exec(compile(src, "gen_largevol.py", "exec"), {"__name__": "__main__"})
+    finally:
+        os.chdir(cwd)
+    assert log.getvalue().count("error") == 320 - 2                                    # 5 x 8 x 8 bricks, two present
+    made = yv.SVOData().Load(str(tmp_path / "data" / "large_vol.vox"))                  # :41
+    mine = yv.DynamicSVO()
+    for (k, j, i), d in bricks.items():
+        mine.BuildRange(11, (i * 256, j * 256, k * 128), yv.BuildMode.GROW, yv.MakeIsoSource(d, iso_level=200))
+    assert made.nodecount == mine.livenodes and made.nodecount > 2000
+    cam = yvo.camera((0.12, 0.06, 0.5), (0.0, 0.0, -1.0), (0, 1, 0), 40.0, 160, 120)        # straight down on the two blobs
+    a = yvo.render(made.nodes(), made.GetRoot(), cam, threads=8)
+    b = yvo.render(mine.nodes(), mine.GetRoot(), cam, threads=8)
+    assert (a["rgba"] == b["rgba"]).all() and (a["node"] != yvo.MISS_NODE).sum() > 200
