@@ -285,3 +285,22 @@ def test_normals_equal_the_reference_prototype_live():
     y, x = np.mgrid[:40, :56].astype(np.float64)
     z = (0.9 + 0.2 * np.sin(x / 5.0) * np.sin(y / 6.0) + rng.rand(40, 56) * 2e-3).astype(np.float32)
     _check_against_prototype(z, calc(z.astype(np.float64)))
+
+
+def test_blur_taps_do_not_depend_on_the_exp_overload():
+    """`float v = exp(-(tx + ty))` (demo/SVORenderer.cpp:70) picks the float overload in C++; the spec evaluates it in double
+    and rounds once. For the 49 taps of the 7x7 kernel the two give the same floats, so the table is pinned either way."""
+    import ctypes
+    libm = ctypes.CDLL("libm.so.6")
+    libm.expf.restype = ctypes.c_float; libm.expf.argtypes = [ctypes.c_float]
+    K, f = 7, np.float32
+    h, v = f(K // 2), np.zeros((K, K), np.float32)
+    for y in range(K):
+        for x in range(K):
+            tx = f(f(f(2.0) * f(f(x) - h)) / h); ty = f(f(f(2.0) * f(f(y) - h)) / h)
+            v[y, x] = libm.expf(float(-f(f(tx * tx) + f(ty * ty))))
+    s = f(0)
+    for y in range(K):
+        for x in range(K):
+            s = f(s + v[y, x])
+    assert (yvo.blur_taps() == (v / s).astype(np.float32)).all()
