@@ -123,3 +123,16 @@ def test_the_references_gen_largevol_script_runs_on_the_library(tmp_path):
     a = yvo.render(made.nodes(), made.GetRoot(), cam, threads=8)
     b = yvo.render(mine.nodes(), mine.GetRoot(), cam, threads=8)
     assert (a["rgba"] == b["rgba"]).all() and (a["node"] != yvo.MISS_NODE).sum() > 200
+
+
+@pytest.mark.gpu
+def test_trace_ray_through_the_ore_surface():
+    """DynamicSVO.TraceRay(p3f, p3f) as qtview.py:66-67 uses it: the distance at which an edit is placed."""
+    from ore.ore import DynamicSVO, MakeSphereSource, BuildMode, p3i, p3f
+    bld = DynamicSVO()
+    bld.BuildRange(6, p3i((32, 32, 32)), BuildMode.GROW, MakeSphereSource(16, (200, 120, 40), False))
+    t = bld.TraceRay(p3f((0.5, 0.5, -1.0)), p3f((0.0, 0.0, 1.0)))
+    assert abs(t - (1.0 + 0.25)) < 2.0 / 64                 # the sphere's near pole is at z = 0.5 - 16/64
+    hit, node, child, t_ref = yvo.trace_ray(bld.nodes(), bld.GetRoot(), (0.5, 0.5, -1.0), (0.0, 0.0, 1.0))
+    assert hit and np.float32(t) == np.float32(t_ref)
+    assert bld.TraceRay(p3f((0.5, 0.5, -1.0)), p3f((0.0, 1.0, 0.0))) == 0.0       # a miss reports t = 0
