@@ -2,7 +2,7 @@
  *
  * Plain-C restatement of the reference CPU tracer. The reference holds no golden vector for this path; the
  * restatement is pinned by running the reference's own sources instead (see yv_oracle.h): cell/ppu_renderer.cpp and
- * cell/spu/trace_spu.cpp compile unmodified into oracle/_ref behind stand-ins for the absent cpp/*.h, and this file
+ * cell/spu/trace_spu.cpp compile unmodified into oracle/_ref behind stand-ins for the absent cpp/ headers, and this file
  * reproduces their frames, hit distances, hit ids and node-fetch counts bit for bit. Only what the snapshot does not
  * contain at all (AdjustDir eps, SetupTrace body, VoxData packing, Shade, LOD, SSNA, secondary rays) stays unpinned.
  *
@@ -157,6 +157,10 @@ typedef struct {
   float t;
   /* counters */
   uint64_t visits, iters;
+  /* optional model of the SPU program's software node cache (cell/spu/trace_spu.cpp:15-35): 2048 direct-mapped
+     slots indexed by id % 2048; a fetch of an id that is not in its slot is a miss (a DMA) and takes the slot */
+  uint32_t *cache_ids;
+  uint64_t cache_misses;
 } trace_ctx;
 
 /* PPURendererBase::RecTrace (cell/ppu_renderer.cpp:18-41); `level` = depth of node `id` (root 0) */
@@ -165,6 +169,10 @@ static int rec_trace(trace_ctx *c, yv_node_id id, v3 t1, v3 t2, int level) {
   if (id >= c->count) return 0;                             /* malformed pool: assert in ref (:54) */
   const yv_vox_node *node = &c->nodes[id];                  /* :23  <- counted node fetch */
   c->visits++;
+  if (c->cache_ids) {                                       /* FetchNode, trace_spu.cpp:21-35 */
+    const uint32_t ofs = id % YVO_SPU_CACHE_SIZE;
+    if (c->cache_ids[ofs] != id) { c->cache_ids[ofs] = id; c->cache_misses++; }
+  }
   int ch = find_first_child(&t1, &t2);                      /* :24 */
   for (;;) {
     int cc = ch ^ (int)c->dir_flags;
@@ -655,6 +663,37 @@ int yvo_trace_ray(const yv_vox_node *nodes, uint32_t node_count, yv_node_id root
   if (hit_child) *hit_child = hit ? c.child : YV_MISS_CHILD;
   if (hit_t)     *hit_t = hit ? c.t : 0.0f;
   return hit;
+}
+
+/* The SPU program's node traffic (cell/spu/trace_spu.cpp): one run with blockStart 0 / blockStride 1 over the
+ * viewSize / 16 blocks (:162-168), pixels of a block row by row (:123-124), the cache cleared to EmptyNode at the
+ * start of the run (:155-156). Returns the fetchCount / missCount the program prints (:179). */
+int yvo_spu_cache_model(const yv_vox_node *nodes, uint32_t node_count, yv_node_id root, const yvo_camera *cam,
+                        uint64_t *fetches, uint64_t *misses) {
+  if (!nodes || !cam || cam->width <= 0 || cam->height <= 0) return -1;
+  yvo_raydir rdd;
+  yvo_init_ray_dir(cam, &rdd);
+  const v3 pos = v3_from(cam->pos), dir0 = v3_from(rdd.dir0), du = v3_from(rdd.du), dv = v3_from(rdd.dv);
+  uint32_t *ids = (uint32_t *)malloc(YVO_SPU_CACHE_SIZE * sizeof(uint32_t));
+  if (!ids) return -2;
+  for (uint32_t i = 0; i < YVO_SPU_CACHE_SIZE; ++i) ids[i] = YV_EMPTY_NODE;
+  trace_ctx c;
+  memset(&c, 0, sizeof c);
+  c.nodes = nodes; c.count = node_count; c.cache_ids = ids;
+  const int B = 16, gx = cam->width / B, gy = cam->height / B;            /* BlockSize, trace_spu.h:5 */
+  for (int block = 0; block < gx * gy; ++block) {
+    const int bx = block % gx, by = block / gx;
+    for (int y = 0; y < B; ++y)
+      for (int x = 0; x < B; ++x) {
+        v3 d = v3_add(v3_add(dir0, v3_scale(du, (float)(bx * B + x))), v3_scale(dv, (float)(by * B + y)));
+        d = adjust_dir(v3_normalized(d));
+        trace_ray(&c, root, pos, d);
+      }
+  }
+  if (fetches) *fetches = c.visits;
+  if (misses) *misses = c.cache_misses;
+  free(ids);
+  return 0;
 }
 
 /* SVOData::Load (cell/svodata.h:31-50): root, two discarded words, count, raw nodes. */

@@ -97,6 +97,12 @@ int yvo_render_threaded_ref(const yv_vox_node *nodes, uint32_t node_count, yv_no
 
 /* Trace one arbitrary ray (DynamicSVO::TraceRay-like; ore/src/main.cpp:125).
  * Returns 1 on hit. */
+/* Model of the SPU program's software node cache (cell/spu/trace_spu.cpp:15-35,155-156,162-168): fetches and misses
+ * of one run over the whole frame in the program's own block and pixel order. */
+#define YVO_SPU_CACHE_SIZE 2048u
+int yvo_spu_cache_model(const yv_vox_node *nodes, uint32_t node_count, yv_node_id root, const yvo_camera *cam,
+                        uint64_t *fetches, uint64_t *misses);
+
 int yvo_trace_ray(const yv_vox_node *nodes, uint32_t node_count, yv_node_id root,
                   const float pos[3], const float dir[3],
                   uint32_t *hit_node, int32_t *hit_child, float *hit_t);

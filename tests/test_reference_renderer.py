@@ -186,6 +186,9 @@ def test_spu_program_frames(scene_name):
         assert (rgba.view(np.uint8).reshape(H, W, 4) == expect).all(), name
         assert fetches == o["stats"]["node_visits"], name
         assert 0 < misses <= fetches
+        # the software node cache (2048 direct-mapped slots, id % 2048, trace_spu.cpp:15-35): the program's miss count
+        # equals the oracle's model of it run in the program's block and pixel order
+        assert (fetches, misses) == yvo.spu_cache_model(nodes, root, cam), name
         tbits, _, _ = yvref.spu_frame(nodes, root, pos, d0, du, dv, W, H, yvref.PROBE_T)
         assert (tbits[hit] == o["t"].view(np.uint32)[hit]).all(), name
         data, _, _ = yvref.spu_frame(nodes, root, pos, d0, du, dv, W, H, yvref.PROBE_DATA)

@@ -160,6 +160,17 @@ def trace_ray(nodes, root, pos, d):
     return bool(hit), n.value, c.value, t.value
 
 
+def spu_cache_model(nodes, root, cam):
+    """(fetches, misses) of the SPU program's 2048-entry direct-mapped node cache over one run (trace_spu.cpp:15-35)."""
+    nodes = np.ascontiguousarray(nodes, dtype=NODE_DTYPE)
+    f, m = C.c_uint64(), C.c_uint64()
+    L = lib()
+    L.yvo_spu_cache_model.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    rc = L.yvo_spu_cache_model(nodes.ctypes.data_as(C.c_void_p), len(nodes), int(root), C.byref(cam), C.byref(f), C.byref(m))
+    assert rc == 0
+    return f.value, m.value
+
+
 def set_tie_order(order):
     """Test-only: 0 = the path's GoNext tie order (default), 1 = the scalar prototype's (cell/spu/vector.h:45-59)."""
     lib().yvo_set_tie_order(int(order))
