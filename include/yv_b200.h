@@ -39,10 +39,15 @@ int yv_abi_version(void);
 
 /* SVOData::Load(const char*)  (cell/svodata.h:31-50) */
 int yv_svo_load(const char *path, yv_svo **out);
+/* SVOData::Load on an object renderers already hold: the reference reloads in place and SetScene keeps the pointer
+ * (cell/svodata.h:31-50, cell/renderer_base.h:28). The pool inside the handle is replaced, device copies are re-made
+ * at the next frame, bound renderers stay valid. On failure the old scene is kept. */
+int yv_svo_load_into(yv_svo *svo, const char *path);
 /* scene built elsewhere (demo/SVORenderer.h:14 SetScene(DynamicSVO*)): copies the pool */
 int yv_svo_from_memory(yv_node_id root, const yv_vox_node *nodes, uint32_t count, yv_svo **out);
 /* DynamicSVO::Save (ore/src/main.cpp:123) */
 int yv_svo_save(const yv_svo *svo, const char *path);
+/* renderers that still hold the scene fall back to "no scene" (RenderFrame -> NULL) */
 void yv_svo_free(yv_svo *svo);
 /* SVOData::GetRoot / operator[] (cell/svodata.h:52-54) */
 yv_node_id yv_svo_root(const yv_svo *svo);
@@ -89,6 +94,10 @@ int yv_svo_update(yv_svo *svo, int device, uint64_t *bytes_transferred);
  * the raw pool is copied page-wise and re-laid-out breadth-first by GPU kernels (environment YV_HOST_PACK=1, or a
  * pool with shared sub-trees, uses the host repack instead). Implicit at the first render if not called. */
 int yv_svo_upload(yv_svo *svo, int device);
+/* "Broadcast at load" for a replicated scene: make the packed pool resident on dst_device by copying it from
+ * src_device over NVLink / PCIe P2P (uploading and re-packing it on src_device first if it is not there yet) instead
+ * of a second upload through the host. A multi-device renderer does this by itself. */
+int yv_svo_replicate(yv_svo *svo, int src_device, int dst_device);
 /* bytes resident on `device` for this scene (0 if not uploaded) */
 uint64_t yv_svo_device_bytes(const yv_svo *svo, int device);
 /* repacked record / leaf counts, for roofline arithmetic and tests */
@@ -103,6 +112,27 @@ int yv_svo_packed_copy(yv_svo *svo, uint32_t *records_out, uint32_t *leaves_out)
 
 /* CreateSimpleRenderer / CreateThreadedRenderer / CreateSPURenderer (cell/svorenderer.h:26-30) */
 int yv_renderer_create(int device, yv_renderer **out);
+/* CreateSPURenderer (cell/svorenderer.h:30; cell/spu_renderer.cpp:30-90): ONE renderer that drives every GPU whose bit is
+ * set in device_mask inside each frame call, the way SPURenderer drives every SPE: GPU k of n renders the blocks b of
+ * the frame with b % n == k (blockStart / blockStride, cell/spu_renderer.cpp:80-83, cell/spu/trace_spu.cpp:164) and
+ * stores its pixels straight into the one frame the call returns (the SPEs' DMA into the PPU's colour buffer,
+ * trace_spu.cpp:171-176). The scene is uploaded and re-packed once, on the first GPU of the mask, and copied to the
+ * others over NVLink. Every other entry point takes the handle unchanged; yv_set_rows / yv_set_interleave are refused
+ * (the group owns the partition: yv_set_partition), SSNA needs a single-device handle. */
+#define YV_ALL_DEVICES (~(uint64_t)0)      /* every GPU of the machine: spe_cpu_info_get(SPE_COUNT_USABLE_SPES), spu_renderer.cpp:73 */
+int yv_renderer_create_multi(uint64_t device_mask, yv_renderer **out);
+/* the same with an explicit list of CUDA ordinals; a GPU may be listed more than once (its members then share that
+ * GPU: useful to exercise the group machinery on a single-GPU machine) */
+int yv_renderer_create_group(const int *devices, int count, yv_renderer **out);
+int yv_renderer_device_count(const yv_renderer *r);              /* GPUs behind the handle (1 for yv_renderer_create) */
+int yv_renderer_device(const yv_renderer *r, int k);             /* CUDA ordinal of member k, -1 if out of range       */
+/* mode 0 (default): blocks of band_rows rows (multiple of 16, default 32) dealt round-robin over the GPUs;
+ * mode 1: contiguous bands (band_rows ignored). */
+int yv_set_partition(yv_renderer *r, int mode, int band_rows);
+/* device time member k spent on its own share of the last frame (imbalance across the group), ms */
+float yv_member_frame_ms(const yv_renderer *r, int k);
+/* wall time and bytes of the last replication of the scene over peer copies (0 when none happened) */
+int yv_replicate_stats(const yv_renderer *r, double *ms, uint64_t *bytes);
 void yv_renderer_destroy(yv_renderer *r);
 
 int yv_set_scene(yv_renderer *r, yv_svo *svo);                 /* SetScene      (:12) borrowed   */
@@ -159,6 +189,16 @@ int yv_render_frame_device(yv_renderer *r, void *d_rgba);
 /* same, asynchronous on the renderer's stream (pair with yv_sync) */
 int yv_render_frame_device_async(yv_renderer *r, void *d_rgba);
 int yv_sync(yv_renderer *r);
+/* Frames in flight, for flythrough batches: yv_render_frame_async starts a frame with the camera as set and returns
+ * at once; yv_wait_frame blocks until that frame is complete where its consumer reads it. Up to "slots" (option,
+ * default 2) frames may be outstanding, so the delivery of frame k overlaps the traversal of frame k+1 — what the
+ * CUDA demo gets from rendering into a mapped PBO while the previous one is displayed (demo/Demo.cpp:172-181).
+ * dst == NULL: the frame lands in a renderer-owned pinned host slot (returned by yv_wait_frame, valid until that slot
+ * is reused); else dst is a caller-owned full-frame buffer — page-locked / registered host memory or device memory.
+ * Delivery follows option "zero_copy": 1 = the kernels store into the target; 0 (and every frame with a second pass)
+ * = the frame is drawn in HBM and moved by the copy engine(s), each GPU of a group moving its own rows. */
+int yv_render_frame_async(yv_renderer *r, void *dst, int *ticket);
+int yv_wait_frame(yv_renderer *r, int ticket, const uint8_t **rgba);
 /* renderer-owned device frame buffer (full frame), for callers that have none */
 int yv_device_framebuffer(yv_renderer *r, void **d_rgba);
 
@@ -222,7 +262,8 @@ int yv_set_stream(yv_renderer *r, void *cuda_stream);
  *   "layout"      0 = packed 16-byte records (default; re-packed and re-uploaded in full after an edit),
  *                 1 = the raw reference pool mirrored page by page (yv_svo_update) — for scenes under edit
  *   "stack"       where the traversal stack lives: 0 local memory, 4 = four-entry
- *                 shared-memory ring spilling to local memory */
+ *                 shared-memory ring spilling to local memory
+ *   "slots"       frames in flight for yv_render_frame_async (2..4, default 2) */
 int yv_set_option(yv_renderer *r, const char *name, int value);
 int yv_get_option(const yv_renderer *r, const char *name, int *value);
 

@@ -36,7 +36,9 @@ class SVOData {
   ~SVOData() { yv_svo_free(h_); }
   SVOData(const SVOData &) = delete;
   SVOData &operator=(const SVOData &) = delete;
-  void Load(const char *fn) { reset(); yv_svo_load(fn, &h_); }                       // :31 (failures: GetRoot()==EmptyNode)
+  // :31 — reloads in place, as the reference does: renderers that were given this object (SetScene keeps the pointer,
+  // renderer_base.h:28) stay valid. Failures: a fresh object keeps GetRoot()==EmptyNode, a loaded one keeps its scene.
+  void Load(const char *fn) { if (h_) yv_svo_load_into(h_, fn); else yv_svo_load(fn, &h_); }
   bool BuildSphereFractal(int depth, int threads) { reset(); return yv_svo_build_sphere_fractal(depth, threads, &h_) == 0; }
   bool BuildIsoVolume(int depth, uint32_t seed, int iso, int threads) { reset(); return yv_svo_build_iso_volume(depth, seed, iso, threads, &h_) == 0; }
   bool Save(const char *fn) const { return h_ && yv_svo_save(h_, fn) == 0; }
@@ -75,6 +77,14 @@ namespace yv {
 class B200Renderer : public YV_NS ISVORenderer {
  public:
   explicit B200Renderer(int device = 0) : r_(nullptr), own_(nullptr) { yv_renderer_create(device, &r_); }
+  // SPURenderer's "every usable SPE" (cell/spu_renderer.cpp:73): one renderer over the GPUs of `device_mask`
+  // (YV_ALL_DEVICES = all of them); each RenderFrame() splits the frame's blocks over them (:80-83)
+  struct Devices { uint64_t mask; };
+  explicit B200Renderer(Devices d) : r_(nullptr), own_(nullptr) { yv_renderer_create_multi(d.mask, &r_); }
+  explicit B200Renderer(const std::vector<int> &ordinals) : r_(nullptr), own_(nullptr) {
+    if (!ordinals.empty()) yv_renderer_create_group(ordinals.data(), (int)ordinals.size(), &r_);
+  }
+  int DeviceCount() const { return r_ ? yv_renderer_device_count(r_) : 0; }
   ~B200Renderer() override { yv_renderer_destroy(r_); yv_svo_free(own_); }
   bool ok() const { return r_ != nullptr; }
 
@@ -146,6 +156,10 @@ class B200Renderer : public YV_NS ISVORenderer {
 // CreateSimpleRenderer / CreateThreadedRenderer / CreateSPURenderer (cell/svorenderer.h:26-30)
 inline std::shared_ptr<YV_NS ISVORenderer> CreateB200Renderer(int device = 0) {
   return std::shared_ptr<YV_NS ISVORenderer>(new B200Renderer(device));
+}
+// all GPUs of `device_mask` behind one ISVORenderer (CreateSPURenderer's role on a multi-accelerator machine)
+inline std::shared_ptr<YV_NS ISVORenderer> CreateB200MultiRenderer(uint64_t device_mask = YV_ALL_DEVICES) {
+  return std::shared_ptr<YV_NS ISVORenderer>(new B200Renderer(B200Renderer::Devices{ device_mask }));
 }
 #endif     // in the tree the factory is written with the tree's own shared_ptr (integration/b200_renderer.cpp)
 

@@ -181,3 +181,68 @@ def test_host_register_rejects_bad_arguments():
     buf = (C.c_uint8 * 4096)()
     assert yv.lib().yv_host_register(0, C.cast(buf, C.c_void_p), 0, C.byref(d)) == -1
     assert yv.lib().yv_host_unregister(None) == 0
+
+
+# ---- untrusted pools and files ------------------------------------------------------------------
+def _cyclic_pool():
+    cyc = np.zeros(2, yv.NODE_DTYPE)
+    cyc[0]["child"][:] = [1, 0, 1, 0, 1, 0, 1, 0]
+    cyc[1]["child"][:] = [0, 1, 0, 1, 0, 1, 0, 1]
+    return cyc
+
+
+def test_cyclic_pool_is_rejected_without_exhausting_memory():
+    """A two-node pool whose nodes are each other's children would grow the breadth-first frontier eight-fold per level;
+    the repack must find the cycle first and fail with a format error, quickly."""
+    import time
+    svo = yv.SVOData.FromNodes(0, _cyclic_pool())
+    t0 = time.time()
+    with pytest.raises(yv.YVError) as e:
+        svo.packed()
+    assert e.value.code == -3 and "cyclic" in str(e.value) and time.time() - t0 < 5.0
+
+
+def test_shared_subtrees_are_still_duplicated():
+    """A DAG (one sub-tree referenced twice) is legal: the repack expands it."""
+    leaf = yv.pack_voxdata(10, 200, 30, 0, 1, 0)
+    nodes = np.zeros(2, yv.NODE_DTYPE)
+    nodes["child"][:] = yv.EMPTY_NODE
+    nodes[0]["child"][3] = leaf; nodes[0]["flags"] = 1 << 3
+    nodes[1]["child"][0] = 0; nodes[1]["child"][5] = 0
+    svo = yv.SVOData.FromNodes(1, nodes)
+    recs, leaves = svo.packed()
+    assert recs.shape[0] == 3 and leaves.shape[0] == 2 and (recs[1:, 3] == 0).all()
+
+
+def test_vox_header_count_is_checked_against_the_file(tmp_path):
+    """svodata.h:40-42 trusts the header's node count; a 16-byte file claiming 4 G nodes must not allocate 160 GB."""
+    fn = tmp_path / "liar.vox"
+    np.array([0, 0x5956, 3, 0xFFFFFFF0], "<u4").tofile(str(fn))
+    with pytest.raises(yv.YVError) as e:
+        yv.SVOData().Load(str(fn))
+    assert "truncated" in str(e.value)
+
+
+def test_load_reloads_in_place(tmp_path):
+    """SVOData::Load on a loaded object replaces the pool inside the same handle (cell/svodata.h:31-50)."""
+    a, b = scenes.fractal(7), scenes.single_sphere(6)
+    fa, fb = str(tmp_path / "a.vox"), str(tmp_path / "b.vox")
+    a.Save(fa); b.Save(fb)
+    svo = yv.SVOData().Load(fa)
+    h, v0 = svo._h.value, svo.version
+    assert svo.nodes().tobytes() == a.nodes().tobytes()
+    svo.Load(fb)
+    assert svo._h.value == h and svo.version > v0 and svo.nodes().tobytes() == b.nodes().tobytes()
+    assert svo.packed()[0].shape[0] == b.packed()[0].shape[0]
+    with pytest.raises(yv.YVError):
+        svo.Load(str(tmp_path / "missing.vox"))
+    assert svo.nodes().tobytes() == b.nodes().tobytes()           # a failed reload keeps the scene
+
+
+def test_multi_device_renderer_needs_gpus():
+    if conftest.has_gpu():
+        pytest.skip("GPU present")
+    for make in (lambda: yv.SVORenderer(devices="all"), lambda: yv.SVORenderer(devices=[0, 0])):
+        with pytest.raises(yv.YVError) as e:
+            make()
+        assert e.value.code == -4 and "no CPU fallback" in str(e.value)

@@ -15,11 +15,12 @@ import numpy as np
 __all__ = [
     "YVError", "lib", "lib_path", "SVOData", "SVORenderer", "CreateB200Renderer",
     "pack_voxdata", "device_count", "init_ray_dir", "BuildMode", "VoxelSource",
-    "MakeSphereSource", "MakeRawSource", "MakeIsoSource", "DynamicSVO", "LightParams", "CudaRenderer", "NODE_DTYPE", "EMPTY_NODE", "FULL_NODE",
+    "MakeSphereSource", "MakeRawSource", "MakeIsoSource", "DynamicSVO", "LightParams", "CudaRenderer", "NODE_DTYPE", "EMPTY_NODE", "FULL_NODE", "ALL_DEVICES",
 ]
 
 EMPTY_NODE = 0x80000000
 FULL_NODE = 0x80000001
+ALL_DEVICES = 0xFFFFFFFFFFFFFFFF     # YV_ALL_DEVICES
 
 # VoxNode (reaction/report/main.tex:46-51): 40 bytes
 NODE_DTYPE = np.dtype([("flags", "<u4"), ("data", "<u4"), ("child", "<u4", (8,))])
@@ -74,6 +75,17 @@ def lib():
         "yv_last_error": (C.c_char_p, []),
         "yv_abi_version": (i32, []),
         "yv_svo_load": (i32, [C.c_char_p, P(vp)]),
+        "yv_svo_load_into": (i32, [vp, C.c_char_p]),
+        "yv_svo_replicate": (i32, [vp, i32, i32]),
+        "yv_renderer_create_multi": (i32, [C.c_uint64, P(vp)]),
+        "yv_renderer_create_group": (i32, [P(i32), i32, P(vp)]),
+        "yv_renderer_device_count": (i32, [vp]),
+        "yv_renderer_device": (i32, [vp, i32]),
+        "yv_set_partition": (i32, [vp, i32, i32]),
+        "yv_member_frame_ms": (f32, [vp, i32]),
+        "yv_replicate_stats": (i32, [vp, P(C.c_double), P(C.c_uint64)]),
+        "yv_render_frame_async": (i32, [vp, vp, P(i32)]),
+        "yv_wait_frame": (i32, [vp, i32, P(vp)]),
         "yv_svo_from_memory": (i32, [u32, vp, u32, P(vp)]),
         "yv_svo_save": (i32, [vp, C.c_char_p]),
         "yv_svo_free": (None, [vp]),
@@ -294,10 +306,16 @@ class SVOData:
         return int(lib().yv_svo_live_node_count(self._h))
 
     # -- construction ------------------------------------------------------------------------
-    def Load(self, fn):                                   # svodata.h:31
-        self._release()
-        _check(lib().yv_svo_load(os.fsencode(fn), C.byref(self._h)))
+    def Load(self, fn):                                   # svodata.h:31 — reloads in place: renderers that hold this
+        if self._h.value:                                 # scene (SetScene keeps the pointer) stay valid
+            _check(lib().yv_svo_load_into(self._h, os.fsencode(fn)))
+        else:
+            _check(lib().yv_svo_load(os.fsencode(fn), C.byref(self._h)))
         return self
+
+    def Replicate(self, src_device, dst_device):
+        """Copy the packed pool from one GPU to another over NVLink instead of uploading it again."""
+        _check(lib().yv_svo_replicate(self._h, int(src_device), int(dst_device)))
 
     @classmethod
     def _adopt(cls, handle):
@@ -401,11 +419,58 @@ class SVOData:
 class SVORenderer:
     """ISVORenderer (cell/svorenderer.h:5-24) + the CUDA SVORenderer extras (demo/SVORenderer.h)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None):
+        """device: one GPU. devices: a list of CUDA ordinals, or "all" — ONE renderer that splits every frame's blocks
+        over those GPUs (SPURenderer over every usable SPE, cell/spu_renderer.cpp:65-90)."""
         self._h = C.c_void_p()
         self._scene = None
-        self.device = int(device)
-        _check(lib().yv_renderer_create(self.device, C.byref(self._h)))
+        if devices is None:
+            self.device = int(device)
+            _check(lib().yv_renderer_create(self.device, C.byref(self._h)))
+        else:
+            if isinstance(devices, str) and devices == "all":
+                _check(lib().yv_renderer_create_multi(C.c_uint64(ALL_DEVICES), C.byref(self._h)))
+            else:                                          # explicit ordinals; one listed twice is driven by two members
+                devs = [int(d) for d in devices]
+                _check(lib().yv_renderer_create_group((C.c_int * len(devs))(*devs), len(devs), C.byref(self._h)))
+            self.device = int(lib().yv_renderer_device(self._h, 0))
+
+    def DeviceCount(self):
+        return int(lib().yv_renderer_device_count(self._h))
+
+    def Devices(self):
+        return [int(lib().yv_renderer_device(self._h, k)) for k in range(self.DeviceCount())]
+
+    def SetPartition(self, mode="interleaved", band_rows=32):
+        """How a multi-device renderer splits a frame: blocks of band_rows rows dealt round-robin (the SPU program's
+        block stride, cell/spu/trace_spu.cpp:164) or contiguous "bands"."""
+        _check(lib().yv_set_partition(self._h, {"interleaved": 0, "bands": 1}[mode], int(band_rows)))
+
+    def MemberFrameMs(self):
+        """Device time every GPU of the group spent on its own share of the last frame."""
+        return [float(lib().yv_member_frame_ms(self._h, k)) for k in range(self.DeviceCount())]
+
+    def ReplicateStats(self):
+        ms, b = C.c_double(), C.c_uint64()
+        _check(lib().yv_replicate_stats(self._h, C.byref(ms), C.byref(b)))
+        return float(ms.value), int(b.value)
+
+    def RenderFrameAsync(self, dst_ptr=None):
+        """Start a frame (camera as set) and return its ticket; see WaitFrame."""
+        t = C.c_int()
+        _check(lib().yv_render_frame_async(self._h, C.c_void_p(int(dst_ptr)) if dst_ptr else None, C.byref(t)))
+        return t.value
+
+    def WaitFrame(self, ticket, as_array=True):
+        """Block until frame `ticket` is complete; returns the (H, W, 4) uint8 view of where it was delivered
+        (as_array=False: the address)."""
+        p = C.c_void_p()
+        _check(lib().yv_wait_frame(self._h, int(ticket), C.byref(p)))
+        if not as_array:
+            return p.value
+        w, h = self.GetResolution()
+        buf = (C.c_uint8 * (w * h * 4)).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.uint8).reshape(h, w, 4)
 
     def SetScene(self, svo):                              # svorenderer.h:12
         self._scene = svo
@@ -628,6 +693,7 @@ class CudaRenderer:
         return None if self._img is None else self._img[..., :3].copy()      # (d_img.get() copies as well)
 
 
-def CreateB200Renderer(device=0):
-    """Factory in the style of CreateSimpleRenderer / CreateThreadedRenderer (cell/svorenderer.h:26-30)."""
-    return SVORenderer(device)
+def CreateB200Renderer(device=0, devices=None):
+    """Factory in the style of CreateSimpleRenderer / CreateThreadedRenderer / CreateSPURenderer
+    (cell/svorenderer.h:26-30); devices="all" or a list = one renderer over several GPUs."""
+    return SVORenderer(device, devices)

@@ -144,6 +144,12 @@ void DynamicSVO::adopt_existing() {
   page_version_.assign((svo_.nodes.size() + kPageNodes - 1) / kPageNodes, version_);
 }
 
+void DynamicSVO::reset_after_reload() {
+  free_.clear();
+  ++version_;
+  page_version_.assign((svo_.nodes.size() + kPageNodes - 1) / kPageNodes, version_);
+}
+
 uint32_t DynamicSVO::alloc_node() {
   uint32_t id;
   if (!free_.empty()) { id = free_.back(); free_.pop_back(); }

@@ -94,6 +94,7 @@ class DynamicSVO {
   int CountChangedPages(uint32_t since_version) const;
   const std::vector<uint32_t> &page_versions() const { return page_version_; }
   void adopt_existing();     // after Load / a batch build: treat the current pool as version 1
+  void reset_after_reload(); // the pool was replaced wholesale (SVOData::Load on a live scene): every page is new
 
  private:
   struct Ref { int kind; uint32_t v; };    // 0 empty, 1 full, 2 leaf(VoxData), 3 node(id)

@@ -126,31 +126,32 @@ struct RingStack {
   uint4 *base;
   uint4 spill[2 * kMaxStack];
   int lo;        // entries [lo, sp) live in the ring
-  __device__ __forceinline__ RingStack(uint4 *area) : base(area + threadIdx.x), lo(0) {}
+  const int pitch;   // threads per CTA: the ring is laid out [slot][half][thread]
+  __device__ __forceinline__ RingStack(uint4 *area) : base(area + threadIdx.x), lo(0), pitch((int)blockDim.x) {}
   __device__ __forceinline__ void reset() { lo = 0; }
   __device__ __forceinline__ void push(int sp, const U4 &a, const U4 &b) {
     if (sp - lo == K) {
       const int slot = lo & (K - 1);
-      spill[2 * lo] = base[(2 * slot) * kCtaThreads];
-      spill[2 * lo + 1] = base[(2 * slot + 1) * kCtaThreads];
+      spill[2 * lo] = base[(2 * slot) * pitch];
+      spill[2 * lo + 1] = base[(2 * slot + 1) * pitch];
       ++lo;
     }
     const int slot = sp & (K - 1);
-    base[(2 * slot) * kCtaThreads] = to_uint4(a); base[(2 * slot + 1) * kCtaThreads] = to_uint4(b);
+    base[(2 * slot) * pitch] = to_uint4(a); base[(2 * slot + 1) * pitch] = to_uint4(b);
   }
   __device__ __forceinline__ void pop(int sp, U4 &a, U4 &b) {
     if (sp < lo) { lo = sp; a = to_u4(spill[2 * sp]); b = to_u4(spill[2 * sp + 1]); return; }
     const int slot = sp & (K - 1);
-    a = to_u4(base[(2 * slot) * kCtaThreads]); b = to_u4(base[(2 * slot + 1) * kCtaThreads]);
+    a = to_u4(base[(2 * slot) * pitch]); b = to_u4(base[(2 * slot + 1) * pitch]);
   }
 };
 
 template <int STACK> struct StackOf { using type = LocalStack; };
 template <> struct StackOf<kStackRing4> { using type = RingStack<4>; };
 
-// shared-memory bytes the stack variant needs per CTA
-__host__ __device__ inline size_t stack_smem_bytes(int stack) {
-  return stack == kStackRing4 ? 4 * 2 * sizeof(uint4) * kCtaThreads : 0;
+// shared-memory bytes the stack variant needs per CTA of `threads` threads
+__host__ __device__ inline size_t stack_smem_bytes(int stack, int threads = kCtaThreads) {
+  return stack == kStackRing4 ? 4 * 2 * sizeof(uint4) * (size_t)threads : 0;
 }
 
 // node fetch policy (see trace_core.cuh). RAW = false: packed 16-byte records, optionally with the top of
@@ -208,6 +209,9 @@ struct NodeFetch {
     }
   }
 };
+
+// the raw pool is traversed as it was handed in: bound the descent in the kernel (trace_core.cuh, FetchTraits)
+template <bool COUNT, bool STAGED> struct FetchTraits<NodeFetch<COUNT, STAGED, true>> { static constexpr bool kGuardDepth = true; };
 
 // tile row (8 pixel rows) of this launch -> first pixel row, for contiguous and interleaved partitions
 __device__ __forceinline__ int tile_row_y(const RenderParams &p, int ty) {

@@ -33,6 +33,15 @@ int load_vox(const char *path, HostSVO &out, std::string &err) {
   out.root = hdr[0];
   out.depth = (hdr[1] == YV_VOX_MAGIC) ? hdr[2] : 0;   // the reference discards words 1,2 (svodata.h:38-39)
   const uint32_t count = hdr[3];
+  // the header word is untrusted: check it against what the file holds before allocating count * 40 bytes
+  {
+    const long here = std::ftell(f);
+    long size = -1;
+    if (here >= 0 && std::fseek(f, 0, SEEK_END) == 0) { size = std::ftell(f); std::fseek(f, here, SEEK_SET); }
+    if (size >= 0 && (uint64_t)count * sizeof(yv_vox_node) > (uint64_t)(size - here)) {
+      std::fclose(f); err = "truncated .vox node array"; out.nodes.clear(); return -3;
+    }
+  }
   out.nodes.resize(count);
   size_t got = count ? std::fread(out.nodes.data(), sizeof(yv_vox_node), count, f) : 0;
   std::fclose(f);

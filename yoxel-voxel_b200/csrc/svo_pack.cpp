@@ -3,6 +3,52 @@
 
 namespace yv {
 
+namespace {
+
+// A pool in which some node has two parents is a DAG (legal: shared sub-trees are duplicated by the repack) or cyclic
+// (not). Decide which, and how many records the duplication produces, BEFORE the breadth-first expansion allocates
+// anything: a small cyclic pool with branching would otherwise grow the frontier eight-fold per level until the host
+// runs out of memory. Memoised depth-first walk: state 0 = new, 1 = on the walk's path, 2 = done.
+int analyse_shared_pool(const HostSVO &svo, uint64_t limit, std::string &err) {
+  const size_t n = svo.nodes.size();
+  std::vector<uint8_t> state(n, 0);
+  std::vector<uint64_t> expanded(n, 0);                    // records the sub-tree of a node expands to (saturating)
+  struct Frame { uint32_t id; int next; };
+  std::vector<Frame> path{ Frame{ svo.root, 0 } };
+  state[svo.root] = 1; expanded[svo.root] = 1;
+  while (!path.empty()) {
+    Frame &f = path.back();
+    if (f.next == 8) {
+      state[f.id] = 2;
+      const uint64_t mine = expanded[f.id];
+      path.pop_back();
+      if (!path.empty()) {
+        uint64_t &up = expanded[path.back().id];
+        up = (up + mine > limit) ? limit + 1 : up + mine;
+      }
+      continue;
+    }
+    const int c = f.next++;
+    const yv_vox_node &nd = svo.nodes[f.id];
+    if ((nd.flags >> c) & 1u) continue;
+    const uint32_t v = nd.child[c];
+    if (YV_IS_NULL(v)) continue;
+    if (v >= n) { err = "child id outside node pool"; return -3; }
+    if (state[v] == 1) { err = "node pool is cyclic (node " + std::to_string(v) + " is its own descendant)"; return -6; }
+    if (state[v] == 2) {
+      uint64_t &up = expanded[f.id];
+      up = (up + expanded[v] > limit) ? limit + 1 : up + expanded[v];
+      continue;
+    }
+    state[v] = 1; expanded[v] = 1;
+    path.push_back(Frame{ v, 0 });
+  }
+  if (expanded[svo.root] > limit) { err = "packed pool exceeds 2^31 records (shared sub-trees are duplicated)"; return -4; }
+  return 0;
+}
+
+}  // namespace
+
 int pack_svo(const HostSVO &svo, PackedSVO &out, std::string &err) {
   out.records.clear(); out.leaves.clear(); out.level_start.clear(); out.node_data.clear();
   out.root_null = YV_IS_NULL(svo.root);
@@ -12,6 +58,9 @@ int pack_svo(const HostSVO &svo, PackedSVO &out, std::string &err) {
   const uint64_t kMaxRecords = 0x7fffffffull;
   const int kMaxLevels = 32;
   std::vector<uint32_t> cur{ svo.root }, nxt;      // reference ids of the current / next level
+  std::vector<bool> seen(svo.nodes.size(), false); // a node met twice: shared sub-tree or cycle, analysed before going on
+  bool analysed = false;
+  seen[svo.root] = true;
   out.records.reserve(svo.nodes.size());
   out.node_data.reserve(svo.nodes.size());
   uint64_t emitted = 0;
@@ -32,6 +81,12 @@ int pack_svo(const HostSVO &svo, PackedSVO &out, std::string &err) {
         if ((leaf_mask >> c) & 1u) out.leaves.push_back(v);
         else if (!YV_IS_NULL(v)) {
           if (v >= svo.nodes.size()) { err = "child id outside node pool"; return -3; }
+          if (seen[v] && !analysed) {
+            const int rc = analyse_shared_pool(svo, kMaxRecords, err);
+            if (rc) return rc;
+            analysed = true;
+          }
+          seen[v] = true;
           child_mask |= 1u << c; nxt.push_back(v); ++child_cursor;
         }
       }

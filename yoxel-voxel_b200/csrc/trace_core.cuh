@@ -279,8 +279,16 @@ YV_HD bool lean_begin(LeanState &s, const Fetch &fetch, const bool root_valid,
 // entered; it is reported as the hit with child = -1 and shaded with its sub-tree average VoxNode::data
 // (endNodeChild < 0 -> node.data, demo/SVORenderer.cpp:176-179). Returns kStepLodHit with s.idx = that node.
 enum : int { kStepLodHit = 3 };
+// A Fetch policy over a pool that nothing has checked for depth (the raw reference pool of a scene under edit, or a
+// .vox / caller-supplied pool traversed in place) sets FetchTraits<Fetch>::kGuardDepth: the traversal then counts
+// levels and treats a child node below level kMaxStack as empty, so neither a pool deeper than the explicit stack
+// nor a cyclic one can run the stack over or keep a ray descending for ever. (The packed layout is depth-checked
+// when it is made.)
+template <class Fetch> struct FetchTraits { static constexpr bool kGuardDepth = false; };
 template <bool LOD, class Fetch, class Stack>
 YV_HD int lean_step(LeanState &s, const Fetch &fetch, Stack &stk, const bool front_only, const float detail = 0.0f) {
+  constexpr bool GUARD = FetchTraits<Fetch>::kGuardDepth;
+  constexpr bool LEVELS = LOD || GUARD;
   uint32_t bit, e;
   bool descend, can_adv;
 #pragma unroll
@@ -295,6 +303,7 @@ YV_HD int lean_step(LeanState &s, const Fetch &fetch, Stack &stk, const bool fro
     const float tmin = fminf(fminf(s.Tx, s.Ty), s.Tz);             // compared only
     if (((s.masks & bit) != 0u) && (!front_only || tmin > 0.0f)) return kStepHit;           // :27
     descend = (((s.masks >> 8) & bit) != 0u) && (tmin > 0.0f);                               // :20,:35
+    if (GUARD) descend = descend && s.level < (uint32_t)kMaxStack;
     can_adv = (s.ch & e) == 0u;                                                              // :38
     if (LOD) {
       // child cube edge 2^-(level+1) < detail * t_enter   <=>   t_enter * (detail * 2^(level+1)) > 1
@@ -315,12 +324,12 @@ YV_HD int lean_step(LeanState &s, const Fetch &fetch, Stack &stk, const bool fro
   if (descend) {
     if (can_adv) {
       const U4 a = { YV_F2U(s.t1x), YV_F2U(s.t1y), YV_F2U(s.t1z), s.idx };
-      const U4 b = { YV_F2U(s.Tx), YV_F2U(s.Ty), YV_F2U(s.Tz), s.ch | (e << 3) | (LOD ? (s.level << 6) : 0u) };
+      const U4 b = { YV_F2U(s.Tx), YV_F2U(s.Ty), YV_F2U(s.Tz), s.ch | (e << 3) | (LEVELS ? (s.level << 6) : 0u) };
       stk.push(s.sp, a, b);
       ++s.sp;
     }
     s.idx = fetch.child_index(s.idx, s.child_base, s.masks, s.ch ^ s.flags);
-    if (LOD) ++s.level;
+    if (LEVELS) ++s.level;
   } else {
     if (s.sp == 0) return kStepMiss;
     --s.sp;
@@ -329,7 +338,7 @@ YV_HD int lean_step(LeanState &s, const Fetch &fetch, Stack &stk, const bool fro
     s.t1x = YV_U2F(a.x); s.t1y = YV_U2F(a.y); s.t1z = YV_U2F(a.z); s.idx = a.w;
     s.Tx = YV_U2F(b.x); s.Ty = YV_U2F(b.y); s.Tz = YV_U2F(b.z);
     s.ch = b.w & 7u; s.pend = (b.w >> 3) & 7u;                     // the parent's GoNext, applied next trip
-    if (LOD) s.level = b.w >> 6;
+    if (LEVELS) s.level = b.w >> 6;
   }
   lean_load_node(s, fetch, descend);                                                         // :23
   if (descend) lean_first_child(s);                                                          // :24

@@ -9,119 +9,27 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <string>
 #include <vector>
 
-#include "../../include/yv_b200.h"
+#include "yv_internal.h"
 #include "render_kernels.cuh"
-#include "dynamic_svo.h"
-#include "svo_host.h"
-#include "svo_pack.h"
 #include "svo_pack_gpu.h"
 
-namespace {
+namespace yvi {
 
 thread_local std::string g_err;
 
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
-#define YV_CUDA(call)                                                                         \
-  do {                                                                                        \
-    cudaError_t e_ = (call);                                                                  \
-    if (e_ != cudaSuccess)                                                                    \
-      return fail(YV_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
-  } while (0)
+}  // namespace yvi
 
-struct DeviceSVO {
-  uint4 *recs = nullptr;
-  uint32_t *leaves = nullptr;
-  uint32_t *node_data = nullptr;      // uploaded on first use of the LOD cut-off
-  size_t n_recs = 0, n_leaves = 0;
-  bool root_null = true;
-  int levels = 0;
-  uint32_t packed_version = 0;        // scene edit version the packed copy was made from
-  // raw mirror of the reference-layout pool, kept in step page by page (CudaSVO::Update)
-  yv_vox_node *raw = nullptr;
-  size_t raw_capacity = 0;            // nodes
-  uint32_t raw_version = 0;           // every page with a version <= this is on the device
-};
+using namespace yvi;
 
-}  // namespace
-
-struct yv_svo {
-  yv::HostSVO host;
-  yv::DynamicSVO dyn{ host };         // editing state (free list, page versions) over `host`
-  yv::PackedSVO packed;
-  bool packed_ok = false;
-  uint32_t packed_version = 0;
-  std::map<int, DeviceSVO> dev;
-  std::mutex mu;
-};
-
-struct yv_renderer {
-  int device = 0;
-  int sm_count = 0;
-  yv_svo *svo = nullptr;
-  // RendererBase state (renderer_base.h:10-18,25)
-  float pos[3] = { 0, 0, 0 }, dir[3] = { 1, 0, 0 }, up[3] = { 0, 0, 1 };
-  float fov = 70.0f;
-  yv_light lights[YV_MAX_LIGHTS] = {};   // SetLigth (demo/SVORenderer.h:34); any enabled light switches to Phong
-  bool show_normals = false;          // SetShowNormals (demo/SVORenderer.h:31)
-  bool ssna = false;                  // SetSSNA (demo/SVORenderer.h:28); the reference defaults to true, off here so that
-                                      // the default frame is the CPU tracer's (ISVORenderer) image
-  float ssna_voxel_size = YV_SSNA_VOXEL_SIZE;   // voxSize of demo/SVORenderer.cpp:129
-  float blur_taps[YV_BLURZ_KERN * YV_BLURZ_KERN] = {};
-  float jitter_amp = 0.0f;            // displaced ray origins (reaction/report/main.tex:107-114); 0 = off
-  uint32_t jitter_seed = 1;
-  uint4 *d_accum = nullptr;           // per-channel sums of yv_render_accumulated
-  float detail_coef = 0.0f;           // SVORenderer::m_detailCoef (demo/SVORenderer.h:56); 0 = off
-  int width = 0, height = 0;
-  int y0 = 0, y1 = 0;
-  bool rows_set = false;
-  int il_rows = 0, il_stride = 1, il_phase = 0;   // interleaved partition (il_stride > 1)
-  // secondary rays
-  int shadow = 0, ao_samples = 0;
-  uint32_t seed = 1;
-  float light[3] = { 0, 0, 0 }, voxel_size = 0.0f, ao_max_t = 0.0f;
-  // buffers
-  uint32_t *d_fb = nullptr;
-  uint8_t *h_fb = nullptr;            // pinned
-  size_t fb_pixels = 0;
-  uint32_t *d_hit_node = nullptr; int32_t *d_hit_child = nullptr; float *d_hit_t = nullptr;
-  uint32_t *d_counters = nullptr;
-  uint2 *d_shade_rec = nullptr;       // (VoxData, t) per pixel for the ShadeSimple pass
-  float *d_zbuf[2] = { nullptr, nullptr };   // m_zbuf[2] (demo/SVORenderer.cpp:85-86): BlurZ ping-pong
-  unsigned int *d_tile_counter = nullptr;
-  bool hits = false, counters = false;
-  // launch
-  cudaStream_t own_stream = nullptr, stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  // RenderFrame pipelining: row chunks rendered on two alternating streams, each chunk's D2H copy overlapped
-  static constexpr int kChunks = 8;
-  cudaStream_t aux[2] = { nullptr, nullptr }, copy_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_chunk[kChunks] = {}, ev_copy = nullptr;
-  bool suppress_events = false;
-  int opt_pipeline = 4;               // row chunks per RenderFrame (0/1 = no pipelining); 4 measured best at 1080p
-  int opt_zero_copy = 1;              // 1 = RenderFrame's kernel stores its pixels straight into the pinned host frame
-                                      // (posted PCIe writes overlap the traversal; no copy, one launch)
-  int opt_pipeline_taper = 100;       // each chunk is this many percent of the one before it (100 = equal chunks): the copy
-                                      // of the last chunk is the only one that is not hidden behind a kernel
-  bool timed = false;
-  int launches = 0;
-  int last_launches = 1;              // kernels launched by the most recent launch_frame call
-  // options
-  int opt_smem_nodes = 0;             // records staged in shared memory (585 = four levels)
-  int opt_persistent = 0;
-  int opt_refill = 20;                // persistent schedule: refill when <= this many lanes are live
-  int opt_sec_threshold = -1;         // secondary rays: serve waiting lanes when <= this many lanes are traversing (-1 = only when the warp has drained: best once the rays are range-limited)
-  int opt_sec_queue = 0;              // 1 = AO rays pooled per warp (render_sec_queue); measured slower than the per-lane stage machine (6.31 vs 5.60 ms on config 4)
-  int opt_layout = 0;                 // 0 = packed records (static scenes), 1 = raw reference pool (scenes under edit)
-  int opt_stack = 0;                  // yv::kStackLocal / kStackRing4
-};
-
-namespace {
+namespace yvi {
 
 int ensure_packed(yv_svo *svo) {
   if (svo->packed_ok && svo->packed_version == svo->dyn.version()) return YV_OK;
@@ -193,8 +101,13 @@ int sync_raw_locked(yv_svo *svo, int device, DeviceSVO **out, uint64_t *bytes_ou
   }
   const std::vector<uint32_t> &pv = svo->dyn.page_versions();
   size_t page = 0;
+  bool quiesced = false;
   while (page < pv.size()) {
     if (pv[page] <= d.raw_version) { ++page; continue; }
+    // Renderer streams are non-blocking, so nothing orders them against these copies: a frame launched with
+    // yv_render_frame_device_async may still be traversing the pages about to be overwritten. Wait for the device
+    // once per update that has anything to ship (an edit is host work of milliseconds; this is not the frame path).
+    if (!quiesced) { YV_CUDA(cudaDeviceSynchronize()); quiesced = true; }
     size_t end = page;
     while (end < pv.size() && pv[end] > d.raw_version) ++end;          // one copy per run of dirty pages
     const size_t first = page * yv::kPageNodes, last = std::min(n, end * yv::kPageNodes);
@@ -205,6 +118,9 @@ int sync_raw_locked(yv_svo *svo, int device, DeviceSVO **out, uint64_t *bytes_ou
     }
     page = end;
   }
+  // ... and the copies themselves (legacy-stream / private-stream, a pageable cudaMemcpy may return before its last DMA
+  // has landed) are complete before any renderer stream can read the pages
+  if (quiesced) YV_CUDA(cudaDeviceSynchronize());
   d.raw_version = svo->dyn.version();
   if (out) *out = &d;
   if (bytes_out) *bytes_out = bytes;
@@ -244,7 +160,13 @@ int ensure_uploaded(yv_svo *svo, int device, DeviceSVO **out) {
         done = true;
       }
       if (!had_raw) { cudaFree(d->raw); d->raw = nullptr; d->raw_capacity = 0; d->raw_version = 0; }   // only needed for the repack
-      if (!done && err.find("not a tree") == std::string::npos) return fail(YV_ERR_FORMAT, err);
+      // "not a tree" (shared sub-trees) and CUDA failures (the repack transiently needs ~96 B/node against ~25 B/node
+      // resident: a large scene can fit packed and still not fit the repack) go to the host pack; what is left is
+      // a structural error
+      const bool structural = err.find("not a tree") == std::string::npos && err.find("cuda") == std::string::npos &&
+                              err.find("CUDA") == std::string::npos && err.find("memory") == std::string::npos;
+      if (!done) cudaGetLastError();
+      if (!done && structural) return fail(YV_ERR_FORMAT, err);
     }
     if (!done) {
       int rc = ensure_packed(svo);
@@ -260,6 +182,7 @@ int ensure_uploaded(yv_svo *svo, int device, DeviceSVO **out) {
       if (d.n_leaves) { int urc = upload_staged(d.leaves, svo->packed.leaves.data(), d.n_leaves * sizeof(uint32_t)); if (urc) return urc; }
       d.packed_version = want;
     }
+    YV_CUDA(cudaDeviceSynchronize());               // the copy is complete before any (non-blocking) renderer stream reads it
     it = svo->dev.find(device);
   }
   if (out) *out = &it->second;
@@ -284,7 +207,9 @@ int ensure_frame_buffers(yv_renderer *r) {
   if (r->fb_pixels != n) {
     free_frame_buffers(r);
     YV_CUDA(cudaMalloc(&r->d_fb, std::max<size_t>(1, n) * 4));
-    YV_CUDA(cudaMallocHost(&r->h_fb, std::max<size_t>(1, n) * 4));
+    // portable + mapped: one address for the host and for every GPU (the members of a device group store into it);
+    // a group's peers deliver into the leader's frame and have no host frame of their own
+    if (!r->leader) YV_CUDA(cudaHostAlloc(&r->h_fb, std::max<size_t>(1, n) * 4, cudaHostAllocPortable | cudaHostAllocMapped));
     r->fb_pixels = n;
   }
   if (r->hits && !r->d_hit_node) {
@@ -526,7 +451,7 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
     p.node_data = ds->node_data;
     p.smem_nodes = 0;
   }
-  const size_t smem = (lod || raw) ? 0 : (size_t)p.smem_nodes * sizeof(uint4) + yv::stack_smem_bytes(r->opt_stack);
+  const size_t smem = (lod || raw) ? 0 : (size_t)p.smem_nodes * sizeof(uint4) + yv::stack_smem_bytes(r->opt_stack, yv::kFrameCta);
   if (smem > 227 * 1024) return fail(YV_ERR_ARG, "shared-memory request exceeds 227 KB (lower smem_nodes or change stack)");
 
   if (!r->suppress_events) YV_CUDA(cudaEventRecord(r->ev0, r->stream));
@@ -658,7 +583,55 @@ int render_frame_pipelined(yv_renderer *r) {
   return YV_OK;
 }
 
-}  // namespace
+void unbind_scene(yv_renderer *r) {
+  if (!r->svo) return;
+  std::lock_guard<std::mutex> lock(r->svo->mu);
+  std::vector<yv_renderer *> &b = r->svo->bound;
+  b.erase(std::remove(b.begin(), b.end(), r), b.end());
+  r->svo = nullptr;
+}
+
+void bind_scene(yv_renderer *r, yv_svo *svo) {
+  if (r->svo == svo) return;
+  unbind_scene(r);
+  r->svo = svo;
+  if (svo) { std::lock_guard<std::mutex> lock(svo->mu); svo->bound.push_back(r); }
+}
+
+bool single_pass_ssna(const yv_renderer *r) { return r->ssna && !(r->shadow || r->ao_samples > 0); }
+
+bool needs_second_pass(const yv_renderer *r) {
+  bool any_light = false;
+  for (int i = 0; i < YV_MAX_LIGHTS; ++i) any_light = any_light || r->lights[i].enabled;
+  return single_pass_ssna(r) || ((r->show_normals || any_light) && !(r->shadow || r->ao_samples > 0));
+}
+
+static void free_device_copies(yv_svo *svo) {
+  for (auto &kv : svo->dev) {
+    cudaSetDevice(kv.first);
+    cudaDeviceSynchronize();                      // no renderer stream is still reading the copies
+    cudaFree(kv.second.recs);
+    cudaFree(kv.second.leaves);
+    cudaFree(kv.second.node_data);
+    cudaFree(kv.second.raw);
+  }
+  svo->dev.clear();
+}
+
+// run a scene builder into a fresh handle; a failed or throwing build leaves nothing behind
+template <class Build>
+int build_scene(yv_svo **out, Build &&build) {
+  return guarded([&]() -> int {
+    yv_svo *s = new yv_svo; std::string err;
+    int rc = 0;
+    try { rc = build(s->host, err); } catch (...) { delete s; throw; }
+    if (rc) { delete s; return fail(YV_ERR_ARG, err); }
+    *out = s;
+    return YV_OK;
+  });
+}
+
+}  // namespace yvi
 
 // ---------------------------------------------------------------------------------------------
 // C ABI
@@ -670,24 +643,50 @@ int yv_abi_version(void) { return 1; }
 
 int yv_svo_load(const char *path, yv_svo **out) {
   if (!path || !out) return fail(YV_ERR_ARG, "null argument");
-  yv_svo *s = new yv_svo;
-  std::string err;
-  int rc = yv::load_vox(path, s->host, err);
-  if (rc) { delete s; return fail(rc <= -10 ? YV_ERR_FORMAT : YV_ERR_IO, err); }
-  *out = s;
-  return YV_OK;
+  return guarded([&]() -> int {
+    yv_svo *s = new yv_svo;
+    std::string err;
+    int rc = 0;
+    try { rc = yv::load_vox(path, s->host, err); } catch (...) { delete s; throw; }
+    if (rc) { delete s; return fail(rc <= -10 ? YV_ERR_FORMAT : YV_ERR_IO, err); }
+    *out = s;
+    return YV_OK;
+  });
+}
+
+// SVOData::Load on an object that renderers already hold (cell/svodata.h:31-50 reloads in place; SetScene keeps the
+// pointer, renderer_base.h:28): the pool is replaced inside the handle, device copies are dropped and re-made at the
+// next frame, and every renderer bound to the handle keeps a valid scene. On failure the old scene stays.
+int yv_svo_load_into(yv_svo *svo, const char *path) {
+  if (!svo || !path) return fail(YV_ERR_ARG, "null argument");
+  return guarded([&]() -> int {
+    yv::HostSVO fresh;
+    std::string err;
+    const int rc = yv::load_vox(path, fresh, err);
+    if (rc) return fail(rc <= -10 ? YV_ERR_FORMAT : YV_ERR_IO, err);
+    std::lock_guard<std::mutex> lock(svo->mu);
+    free_device_copies(svo);
+    svo->host.root = fresh.root; svo->host.depth = fresh.depth; svo->host.nodes.swap(fresh.nodes);
+    svo->dyn.reset_after_reload();
+    svo->packed = yv::PackedSVO(); svo->packed_ok = false;
+    return YV_OK;
+  });
 }
 
 int yv_svo_from_memory(yv_node_id root, const yv_vox_node *nodes, uint32_t count, yv_svo **out) {
   if (!out || (!nodes && count)) return fail(YV_ERR_ARG, "null argument");
-  yv_svo *s = new yv_svo;
-  s->host.root = root;
-  s->host.nodes.assign(nodes, nodes + count);
-  yv::normalize_flags(s->host);
-  std::string err;
-  if (yv::validate(s->host, err)) { delete s; return fail(YV_ERR_FORMAT, err); }
-  *out = s;
-  return YV_OK;
+  return guarded([&]() -> int {
+    yv_svo *s = new yv_svo;
+    try {
+      s->host.root = root;
+      s->host.nodes.assign(nodes, nodes + count);
+      yv::normalize_flags(s->host);
+    } catch (...) { delete s; throw; }
+    std::string err;
+    if (yv::validate(s->host, err)) { delete s; return fail(YV_ERR_FORMAT, err); }
+    *out = s;
+    return YV_OK;
+  });
 }
 
 int yv_svo_save(const yv_svo *svo, const char *path) {
@@ -699,13 +698,14 @@ int yv_svo_save(const yv_svo *svo, const char *path) {
 
 void yv_svo_free(yv_svo *svo) {
   if (!svo) return;
-  for (auto &kv : svo->dev) {
-    cudaSetDevice(kv.first);
-    cudaFree(kv.second.recs);
-    cudaFree(kv.second.leaves);
-    cudaFree(kv.second.node_data);
-    cudaFree(kv.second.raw);
+  // renderers that still hold this scene go back to "no scene" (RenderFrame -> NULL, cell/ppu_renderer.cpp:78-79)
+  // instead of keeping a dangling pointer
+  for (yv_renderer *r : std::vector<yv_renderer *>(svo->bound)) {
+    if (r->own_stream) { cudaSetDevice(r->device); cudaStreamSynchronize(r->stream); }
+    r->svo = nullptr;
   }
+  svo->bound.clear();
+  free_device_copies(svo);
   delete svo;
 }
 
@@ -714,31 +714,21 @@ uint32_t yv_svo_node_count(const yv_svo *svo) { return svo ? (uint32_t)svo->host
 uint32_t yv_svo_depth(const yv_svo *svo) { return svo ? svo->host.depth : 0u; }
 const yv_vox_node *yv_svo_nodes(const yv_svo *svo) { return svo && !svo->host.nodes.empty() ? svo->host.nodes.data() : nullptr; }
 
-static int finish_build(yv_svo *s, int rc, const std::string &err, yv_svo **out) {
-  if (rc) { delete s; return fail(YV_ERR_ARG, err); }
-  *out = s;
-  return YV_OK;
-}
-
 int yv_svo_build_sphere_fractal(int depth, int threads, yv_svo **out) {
   if (!out) return fail(YV_ERR_ARG, "null argument");
-  yv_svo *s = new yv_svo; std::string err;
-  return finish_build(s, yv::build_sphere_fractal(depth, threads, s->host, err), err, out);
+  return build_scene(out, [&](yv::HostSVO &h, std::string &err) { return yv::build_sphere_fractal(depth, threads, h, err); });
 }
 int yv_svo_build_iso_volume(int depth, uint32_t seed, int iso_level, int threads, yv_svo **out) {
   if (!out) return fail(YV_ERR_ARG, "null argument");
-  yv_svo *s = new yv_svo; std::string err;
-  return finish_build(s, yv::build_iso_volume(depth, seed, iso_level, threads, s->host, err), err, out);
+  return build_scene(out, [&](yv::HostSVO &h, std::string &err) { return yv::build_iso_volume(depth, seed, iso_level, threads, h, err); });
 }
 int yv_svo_build_single_sphere(int depth, int cx, int cy, int cz, int radius, uint8_t r, uint8_t g, uint8_t b, yv_svo **out) {
   if (!out) return fail(YV_ERR_ARG, "null argument");
-  yv_svo *s = new yv_svo; std::string err;
-  return finish_build(s, yv::build_single_sphere(depth, cx, cy, cz, radius, r, g, b, s->host, err), err, out);
+  return build_scene(out, [&](yv::HostSVO &h, std::string &err) { return yv::build_single_sphere(depth, cx, cy, cz, radius, r, g, b, h, err); });
 }
 int yv_svo_build_from_dense(int depth, const uint32_t *voxdata, yv_svo **out) {
   if (!out || !voxdata) return fail(YV_ERR_ARG, "null argument");
-  yv_svo *s = new yv_svo; std::string err;
-  return finish_build(s, yv::build_from_dense(depth, voxdata, s->host, err), err, out);
+  return build_scene(out, [&](yv::HostSVO &h, std::string &err) { return yv::build_from_dense(depth, voxdata, h, err); });
 }
 uint32_t yv_pack_voxdata(uint8_t r, uint8_t g, uint8_t b, float nx, float ny, float nz) {
   return yv::pack_voxdata(r, g, b, nx, ny, nz);
@@ -746,7 +736,7 @@ uint32_t yv_pack_voxdata(uint8_t r, uint8_t g, uint8_t b, float nx, float ny, fl
 
 int yv_svo_upload(yv_svo *svo, int device) {
   if (!svo) return fail(YV_ERR_ARG, "null scene");
-  return ensure_uploaded(svo, device, nullptr);
+  return guarded([&]() -> int { return ensure_uploaded(svo, device, nullptr); });
 }
 
 uint64_t yv_svo_device_bytes(const yv_svo *svo, int device) {
@@ -762,7 +752,7 @@ int yv_svo_device_packed_copy(yv_svo *svo, int device, uint32_t *n_records, uint
                               uint32_t *records_out, uint32_t *leaves_out, uint32_t *node_data_out) {
   if (!svo) return fail(YV_ERR_ARG, "null scene");
   DeviceSVO *d = nullptr;
-  int rc = ensure_uploaded(svo, device, &d);
+  int rc = guarded([&]() -> int { return ensure_uploaded(svo, device, &d); });
   if (rc) return rc;
   if (n_records) *n_records = (uint32_t)d->n_recs;
   if (n_leaves) *n_leaves = (uint32_t)d->n_leaves;
@@ -776,7 +766,7 @@ int yv_svo_device_packed_copy(yv_svo *svo, int device, uint32_t *n_records, uint
 int yv_svo_packed_counts(yv_svo *svo, uint32_t *records, uint32_t *leaves) {
   if (!svo) return fail(YV_ERR_ARG, "null scene");
   std::lock_guard<std::mutex> lock(svo->mu);
-  int rc = ensure_packed(svo);
+  int rc = guarded([&]() -> int { return ensure_packed(svo); });
   if (rc) return rc;
   if (records) *records = (uint32_t)svo->packed.records.size();
   if (leaves) *leaves = (uint32_t)svo->packed.leaves.size();
@@ -786,7 +776,7 @@ int yv_svo_packed_counts(yv_svo *svo, uint32_t *records, uint32_t *leaves) {
 int yv_svo_packed_copy(yv_svo *svo, uint32_t *records_out, uint32_t *leaves_out) {
   if (!svo) return fail(YV_ERR_ARG, "null scene");
   std::lock_guard<std::mutex> lock(svo->mu);
-  int rc = ensure_packed(svo);
+  int rc = guarded([&]() -> int { return ensure_packed(svo); });
   if (rc) return rc;
   if (records_out && !svo->packed.records.empty())
     std::memcpy(records_out, svo->packed.records.data(), svo->packed.records.size() * 16u);
@@ -833,6 +823,8 @@ int yv_renderer_create(int device, yv_renderer **out) {
   cudaError_t e = cudaStreamCreateWithFlags(&r->own_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&r->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&r->ev1);
+  if (e == cudaSuccess) e = cudaEventCreate(&r->ev_own0);
+  if (e == cudaSuccess) e = cudaEventCreate(&r->ev_own1);
   if (e == cudaSuccess) e = cudaMalloc(&r->d_tile_counter, sizeof(unsigned int));
   for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&r->aux[i], cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking);
@@ -849,9 +841,16 @@ int yv_renderer_create(int device, yv_renderer **out) {
 
 void yv_renderer_destroy(yv_renderer *r) {
   if (!r) return;
+  group_destroy_peers(r);
   cudaSetDevice(r->device);
   if (r->own_stream) cudaStreamSynchronize(r->own_stream);
+  if (r->copy_stream) cudaStreamSynchronize(r->copy_stream);
+  unbind_scene(r);
+  free_slots(r);
   free_frame_buffers(r);
+  if (r->ev_join) cudaEventDestroy(r->ev_join);
+  if (r->ev_own0) cudaEventDestroy(r->ev_own0);
+  if (r->ev_own1) cudaEventDestroy(r->ev_own1);
   cudaFree(r->d_tile_counter);
   if (r->ev0) cudaEventDestroy(r->ev0);
   if (r->ev1) cudaEventDestroy(r->ev1);
@@ -866,7 +865,9 @@ void yv_renderer_destroy(yv_renderer *r) {
 
 int yv_set_scene(yv_renderer *r, yv_svo *svo) {
   if (!r) return fail(YV_ERR_ARG, "null renderer");
-  r->svo = svo;
+  if (r->stream) { cudaSetDevice(r->device); cudaStreamSynchronize(r->stream); }   // no frame of the old scene in flight
+  bind_scene(r, svo);
+  for (yv_renderer *p : r->peers) bind_scene(p, svo);
   return YV_OK;
 }
 
@@ -963,6 +964,7 @@ int yv_get_fov(const yv_renderer *r, float *fov_deg) {
 
 int yv_set_rows(yv_renderer *r, int y0, int y1) {
   if (!r) return fail(YV_ERR_ARG, "null renderer");
+  if (!r->peers.empty()) return fail(YV_ERR_ARG, "a multi-device renderer partitions the frame itself (yv_set_partition)");
   if (y0 < 0 || y1 < y0) return fail(YV_ERR_ARG, "bad row band");
   r->y0 = y0; r->y1 = y1; r->rows_set = true;
   r->il_stride = 1;
@@ -971,6 +973,7 @@ int yv_set_rows(yv_renderer *r, int y0, int y1) {
 
 int yv_set_interleave(yv_renderer *r, int band_rows, int stride, int phase) {
   if (!r) return fail(YV_ERR_ARG, "null renderer");
+  if (!r->peers.empty() && stride > 1) return fail(YV_ERR_ARG, "a multi-device renderer partitions the frame itself (yv_set_partition)");
   if (stride < 1 || phase < 0 || phase >= stride || band_rows < 16 || band_rows % 16 != 0)
     return fail(YV_ERR_ARG, "interleave: band_rows must be a multiple of 16, 0 <= phase < stride");
   r->il_rows = band_rows; r->il_stride = stride; r->il_phase = phase;
@@ -1001,13 +1004,16 @@ int yv_enable_counters(yv_renderer *r, int enable) {
 
 int yv_render_frame_device_async(yv_renderer *r, void *d_rgba) {
   if (!r || !d_rgba) return fail(YV_ERR_ARG, "null argument");
-  return launch_frame(r, d_rgba);
+  return guarded([&]() -> int {
+    r->last_ms = -1.0f;
+    return r->peers.empty() ? launch_frame(r, d_rgba) : group_render_device(r, d_rgba);
+  });
 }
 
 int yv_sync(yv_renderer *r) {
   if (!r) return fail(YV_ERR_ARG, "null renderer");
   YV_CUDA(cudaSetDevice(r->device));
-  YV_CUDA(cudaStreamSynchronize(r->stream));
+  YV_CUDA(cudaStreamSynchronize(r->stream));      // a group's peers are joined into the leader's stream
   return YV_OK;
 }
 
@@ -1029,12 +1035,12 @@ int yv_render_frame(yv_renderer *r, const uint8_t **rgba) {
   if (!r || !rgba) return fail(YV_ERR_ARG, "null argument");
   *rgba = nullptr;                                     // reference returns NULL on failure
   if (!r->svo) return fail(YV_ERR_NOSCENE, "no scene set");
-  int rc = ensure_frame_buffers(r);
+  r->last_ms = -1.0f;
+  if (!r->peers.empty()) return guarded([&]() -> int { return group_render_frame(r, rgba); });
+  int rc = guarded([&]() -> int { return ensure_frame_buffers(r); });
   if (rc) return rc;
-  const bool ssna = r->ssna && !(r->shadow || r->ao_samples > 0);      // BlurZ reaches across row chunks: one launch
-  bool any_light = false;
-  for (int i = 0; i < YV_MAX_LIGHTS; ++i) any_light = any_light || r->lights[i].enabled;
-  const bool second_pass = ssna || ((r->show_normals || any_light) && !(r->shadow || r->ao_samples > 0));
+  const bool ssna = single_pass_ssna(r);               // BlurZ reaches across row chunks: one launch
+  const bool second_pass = needs_second_pass(r);
   if (r->opt_zero_copy && !second_pass) {       // (the ShadeSimple / SSNA passes read the frame back: keep it in HBM)
     rc = launch_frame(r, r->h_fb);              // pinned memory is device-addressable under UVA
     if (rc) return rc;
@@ -1096,16 +1102,35 @@ int yv_render_accumulated(yv_renderer *r, int frames, const uint8_t **rgba) {
   return YV_OK;
 }
 
+// one per-pixel plane of a frame drawn by a group: every member holds the rows it rendered
+static int gather_plane(yv_renderer *r, void *out, const void *(*plane)(const yv_renderer *)) {
+  const int n = group_size(r);
+  const size_t row = (size_t)r->width * 4, bytes = r->fb_pixels * 4;
+  if (n == 1) { YV_CUDA(cudaSetDevice(r->device)); YV_CUDA(cudaMemcpy(out, plane(r), bytes, cudaMemcpyDeviceToHost)); return YV_OK; }
+  std::vector<uint8_t> tmp(bytes);
+  for (int k = 0; k < n; ++k) {
+    yv_renderer *m = group_member(r, k);
+    if (!plane(m) || m->fb_pixels != r->fb_pixels) return fail(YV_ERR_ARG, "per-pixel buffers not enabled before the last frame");
+    YV_CUDA(cudaSetDevice(m->device));
+    YV_CUDA(cudaMemcpy(tmp.data(), plane(m), bytes, cudaMemcpyDeviceToHost));
+    for (int y = 0; y < r->height; ++y)
+      if (member_owns_row(r, k, n, y)) std::memcpy((uint8_t *)out + y * row, tmp.data() + y * row, row);
+  }
+  return YV_OK;
+}
+
 int yv_get_hits(yv_renderer *r, uint32_t *node, int32_t *child, float *t) {
   if (!r) return fail(YV_ERR_ARG, "null renderer");
   if (!r->hits || !r->d_hit_node) return fail(YV_ERR_ARG, "hit buffers not enabled before the last frame");
   YV_CUDA(cudaSetDevice(r->device));
   YV_CUDA(cudaStreamSynchronize(r->stream));
-  const size_t bytes = r->fb_pixels * 4;
-  if (node) YV_CUDA(cudaMemcpy(node, r->d_hit_node, bytes, cudaMemcpyDeviceToHost));
-  if (child) YV_CUDA(cudaMemcpy(child, r->d_hit_child, bytes, cudaMemcpyDeviceToHost));
-  if (t) YV_CUDA(cudaMemcpy(t, r->d_hit_t, bytes, cudaMemcpyDeviceToHost));
-  return YV_OK;
+  return guarded([&]() -> int {
+    int rc = YV_OK;
+    if (node) rc = gather_plane(r, node, [](const yv_renderer *m) -> const void * { return m->d_hit_node; });
+    if (!rc && child) rc = gather_plane(r, child, [](const yv_renderer *m) -> const void * { return m->d_hit_child; });
+    if (!rc && t) rc = gather_plane(r, t, [](const yv_renderer *m) -> const void * { return m->d_hit_t; });
+    return rc;
+  });
 }
 
 int yv_get_counters(yv_renderer *r, uint32_t *fetches_per_ray) {
@@ -1113,8 +1138,9 @@ int yv_get_counters(yv_renderer *r, uint32_t *fetches_per_ray) {
   if (!r->counters || !r->d_counters) return fail(YV_ERR_ARG, "counters not enabled before the last frame");
   YV_CUDA(cudaSetDevice(r->device));
   YV_CUDA(cudaStreamSynchronize(r->stream));
-  YV_CUDA(cudaMemcpy(fetches_per_ray, r->d_counters, r->fb_pixels * 4, cudaMemcpyDeviceToHost));
-  return YV_OK;
+  return guarded([&]() -> int {
+    return gather_plane(r, fetches_per_ray, [](const yv_renderer *m) -> const void * { return m->d_counters; });
+  });
 }
 
 // SVORenderer::DumpTraceData (demo/SVORenderer.cpp:158-192): <base>_<W>x<H>.dist / .color / .normal
@@ -1156,6 +1182,7 @@ int yv_dump_trace_data(yv_renderer *r, const char *fnbase) {
 
 float yv_last_frame_ms(const yv_renderer *r) {
   if (!r || !r->timed) return -1.0f;
+  if (r->last_ms >= 0.0f) return r->last_ms;          // measured at yv_wait_frame
   cudaSetDevice(r->device);
   if (cudaEventSynchronize(r->ev1) != cudaSuccess) return -1.0f;
   float ms = -1.0f;
@@ -1186,6 +1213,11 @@ int yv_set_option(yv_renderer *r, const char *name, int value) {
   else if (n == "pipeline") { if (value < 0 || value > yv_renderer::kChunks) return fail(YV_ERR_ARG, "pipeline must be 0..8 chunks"); r->opt_pipeline = value; }
   else if (n == "layout") { if (value != 0 && value != 1) return fail(YV_ERR_ARG, "layout must be 0 (packed) or 1 (raw)"); r->opt_layout = value; }
   else if (n == "refill") { if (value < 0 || value > 31) return fail(YV_ERR_ARG, "refill must be 0..31"); r->opt_refill = value; }
+  else if (n == "slots") {
+    if (value < 2 || value > yv_renderer::kSlots) return fail(YV_ERR_ARG, "slots must be 2..4 frames in flight");
+    for (int s = 0; s < yv_renderer::kSlots; ++s) if (r->slots[s].ticket >= 0) return fail(YV_ERR_ARG, "frames are in flight: yv_wait_frame first");
+    r->opt_slots = value; r->next_ticket = 0;
+  }
   else if (n == "stack") {
     if (value != yv::kStackLocal && value != yv::kStackRing4)
       return fail(YV_ERR_ARG, "stack must be 0 (local memory) or 4 (4-entry shared ring + local spill)");
@@ -1208,6 +1240,7 @@ int yv_get_option(const yv_renderer *r, const char *name, int *value) {
   else if (n == "layout") *value = r->opt_layout;
   else if (n == "refill") *value = r->opt_refill;
   else if (n == "stack") *value = r->opt_stack;
+  else if (n == "slots") *value = r->opt_slots;
   else return fail(YV_ERR_ARG, "unknown option " + n);
   return YV_OK;
 }
