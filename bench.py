@@ -53,6 +53,8 @@ def parse():
                     help="SetSSNA: BlurZ x5 + normals from the z-buffer (demo/SVORenderer.cpp:126-147); one GPU")
     ap.add_argument("--flythrough", action="store_true",
                     help="tiles partition: move the camera every step (BASELINE config 5: 64-frame flythrough)")
+    ap.add_argument("--cull", action="store_true",
+                    help="ablation: octant culling on (fewer node fetches, measured slower: profiles/README.md)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-l2-flush", action="store_true")
     return ap.parse_args()
@@ -387,6 +389,7 @@ def main():
         return step if (tiles_mode or world == 1) else step * world + rank
 
     r.EnableCounters(True)
+    r.SetOption("cull", 0)                                    # V-bar is the REFERENCE traversal's node-fetch count
     probe = torch.zeros(a.height, a.width, 4, dtype=torch.uint8, device=dev)
     vis_sum = pop_sum = hit_px = 0
     probe_frames = range(a.steps) if a.flythrough else [None]
@@ -399,8 +402,19 @@ def main():
         vis_sum += int(visits[my_rows].sum())
         pop_sum += int(pops[my_rows].sum())
         hit_px += int((probe[torch.as_tensor(my_rows, device=dev), :, 3] == 255).sum().item())
+    # what the timed kernel actually fetches for the same frame(s) (differs only with --cull)
+    r.SetOption("cull", 1 if a.cull else 0)
+    kern_vis = kern_pop = 0
+    for st in probe_frames:
+        if st is not None:
+            fpos, fdir = camera_for(frame_of(st))
+            r.SetViewPos(fpos); r.SetViewDir(fdir)
+        r.Render(probe.data_ptr(), sync=True)
+        visits, pops = r.GetCounters()
+        kern_vis += int(visits[my_rows].sum()); kern_pop += int(pops[my_rows].sum())
     r.EnableCounters(False)
     n_probe = len(probe_frames)
+    kern_vis //= n_probe; kern_pop //= n_probe
     my_px = len(my_rows) * a.width
     my_rays = my_px + (5 * hit_px // n_probe if a.secondary else 0)      # shadow + 4 AO per hit pixel
     vis_sum //= n_probe; pop_sum //= n_probe                  # per-step averages
@@ -442,12 +456,12 @@ def main():
     clocks = sampler.stop(wall0, wall1) if sampler else None
     step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    sums = torch.tensor([float(my_rays), float(my_px), float(vis_sum), float(pop_sum)], dtype=torch.float64, device=dev)
+    sums = torch.tensor([float(my_rays), float(my_px), float(vis_sum), float(pop_sum), float(kern_vis), float(kern_pop)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)          # max over ranks
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)              # units all ranks processed
     total_s = float(total_ms.item()) / 1e3
-    rays_step, px_step, vis_step, pop_step = (float(v) for v in sums.tolist())
+    rays_step, px_step, vis_step, pop_step, kvis_step, kpop_step = (float(v) for v in sums.tolist())
     value = rays_step * a.steps / total_s / 1e6
 
     # ---- e2e: the public host API with host buffers (camera in, RGBA8 frame out) -------------------
@@ -590,6 +604,8 @@ def main():
                 "traffic": traffic, "l2_traffic": l2_traffic, "peak_source": peak_src, "kernel": "yv::render_frame<%s>" % schedule,
                 "algorithmic_bytes_per_launch": alg_bytes_step / world,
                 "node_visits_per_ray": vis_step / rays_step, "pop_refetches_per_ray": pop_step / rays_step,
+                "kernel_node_fetches_per_ray": kvis_step / rays_step, "kernel_pop_refetches_per_ray": kpop_step / rays_step,
+                "octant_culling": bool(a.cull),
                 "kernel_ms": 1e3 * kernel_s}
 
     line = {

@@ -107,6 +107,10 @@ int yv_svo_device_packed_copy(yv_svo *svo, int device, uint32_t *n_records, uint
                               uint32_t *records_out, uint32_t *leaves_out, uint32_t *node_data_out);
 /* copy of the repacked host arrays (tests): records = 4 u32 each, leaves = 1 u32 each */
 int yv_svo_packed_copy(yv_svo *svo, uint32_t *records_out, uint32_t *leaves_out);
+/* the octant-occupancy ("grandchild") masks the culling traversal reads, one uint64 per record — byte c = which octants
+ * of child node c hold anything: from the host repack, and as they sit in the device's records (tests compare them) */
+int yv_svo_octant_masks(yv_svo *svo, uint64_t *out);
+int yv_svo_device_octant_masks(yv_svo *svo, int device, uint64_t *out);
 
 /* ---- renderer: ISVORenderer (cell/svorenderer.h:5-24) + SVORenderer (demo/SVORenderer.h) -- */
 
@@ -263,7 +267,14 @@ int yv_set_stream(yv_renderer *r, void *cuda_stream);
  *                 1 = the raw reference pool mirrored page by page (yv_svo_update) — for scenes under edit
  *   "stack"       where the traversal stack lives: 0 local memory, 4 = four-entry
  *                 shared-memory ring spilling to local memory
- *   "slots"       frames in flight for yv_render_frame_async (2..4, default 2) */
+ *   "slots"       frames in flight for yv_render_frame_async (2..4, default 2)
+ *   "cull"        1 = octant culling: a child node is entered only if one of the octants the ray can touch in it holds
+ *                 anything (the occupancy of every child's octants rides in the parent's 16-byte record). Conservative, so
+ *                 hit ids, t and pixels are those of the reference traversal; node fetches drop by ~30 %, but lanes of a
+ *                 warp stop descending in lock-step and the frame gets SLOWER (0.92 vs 0.70 ms on config 2,
+ *                 profiles/README.md) — so 0 is the default: enter every child node the reference enters
+ *                 (cell/ppu_renderer.cpp:35); yv_get_counters then returns exactly the reference's node-fetch counts.
+ *                 Packed layout, local stack, no staging. */
 int yv_set_option(yv_renderer *r, const char *name, int value);
 int yv_get_option(const yv_renderer *r, const char *name, int *value);
 

@@ -15,7 +15,7 @@ float g_detail = 0.0f;   // rp.detailCoef; > 0 switches the LOD cut-off on (lean
 bool g_lod_hit = false;
 const uint32_t *g_node_data = nullptr;
 uint64_t g_trips = 0;   // lean_step / trace_step calls of the last yve_render
-int g_mode = 2;   // 0 = trace_step (classic form), 2 = lean_step (what render_frame runs)
+int g_mode = 2;   // 0 = trace_step (classic form), 2 = lean_step, 3 = lean_step with octant culling (what render_frame runs)
 struct HostStack {
   StackEntry e[kMaxStack];
   int max_sp = 0;
@@ -44,11 +44,28 @@ struct HostFetch {
   uint32_t root_index() const { return 0u; }
 };
 
-bool trace(const HostFetch &fetch, bool root_valid, HostStack &stk, float ox, float oy, float oz,
+// the culling policy: the node's grandchild mask is put together from its children's records here (the product's
+// repack stores it in the record; tests/test_gpu_pack.py checks that array against the same definition)
+struct HostCullFetch : HostFetch {
+  void node(uint32_t idx, bool visit, uint32_t &masks, uint32_t &child_base, uint32_t &gm_lo, uint32_t &gm_hi) const {
+    const Rec r = get(idx, visit); masks = r.masks; child_base = r.child_base;
+    uint64_t g = 0; uint32_t k = 0;
+    for (uint32_t c = 0; c < 8; ++c)
+      if ((r.masks >> (8 + c)) & 1u) { const uint32_t m = recs[r.child_base + k++].masks; g |= (uint64_t)((m | (m >> 8)) & 0xffu) << (8 * c); }
+    gm_lo = (uint32_t)g; gm_hi = (uint32_t)(g >> 32);
+  }
+  uint32_t box(uint32_t flags, uint32_t ch0, uint32_t chx) const { return box_mask_stored(flags, ch0, chx); }
+};
+}  // namespace
+namespace yv { template <> struct FetchTraits<HostCullFetch> { static constexpr bool kGuardDepth = false; static constexpr bool kCull = true; }; }
+namespace {
+
+template <class Fetch>
+bool trace(const Fetch &fetch, bool root_valid, HostStack &stk, float ox, float oy, float oz,
            float dx, float dy, float dz, bool front_only, RayState &s, Rec &rec, uint64_t &steps,
            float tlimit = __builtin_huge_valf()) {
   dx = adjust_dir1(dx); dy = adjust_dir1(dy); dz = adjust_dir1(dz);
-  if (g_mode == 2) {
+  if (g_mode >= 2) {
     LeanState ls;
     if (!lean_begin(ls, fetch, root_valid, ox, oy, oz, dx, dy, dz)) return false;
     ls.tlimit = tlimit;
@@ -81,14 +98,13 @@ extern "C" void yve_set_mode(int mode) { g_mode = mode; }
 extern "C" uint64_t yve_trips() { return g_trips; }      // lean_step / trace_step calls of the last yve_render
 extern "C" void yve_set_lod(float detail, const uint32_t *node_data) { g_detail = detail; g_node_data = node_data; }
 
-extern "C" int yve_render(const uint32_t *records, const uint32_t *leaves, int root_valid,
-                          const float pos[3], const float dir0[3], const float du[3], const float dv[3],
-                          const float light[3], int width, int height,
-                          int shadow, int ao_samples, uint32_t seed, float voxel_size, float ao_max_t,
-                          uint32_t *hit_node, int32_t *hit_child, float *hit_t, uint32_t *rgba,
-                          uint64_t *out_fetches, int *out_max_sp, uint64_t *out_visits) {
-  const Rec *recs = reinterpret_cast<const Rec *>(records);
-  HostFetch fetch{ recs };
+template <class Fetch>
+int render_with(const Fetch &fetch, const uint32_t *leaves, int root_valid,
+                const float pos[3], const float dir0[3], const float du[3], const float dv[3],
+                const float light[3], int width, int height,
+                int shadow, int ao_samples, uint32_t seed, float voxel_size, float ao_max_t,
+                uint32_t *hit_node, int32_t *hit_child, float *hit_t, uint32_t *rgba,
+                uint64_t *out_fetches, int *out_max_sp, uint64_t *out_visits) {
   HostStack stk;
   uint64_t steps = 0;
   const bool sec = shadow || ao_samples > 0;
@@ -150,4 +166,21 @@ extern "C" int yve_render(const uint32_t *records, const uint32_t *leaves, int r
   if (out_visits) *out_visits = fetch.visits;
   if (out_max_sp) *out_max_sp = stk.max_sp;
   return 0;
+}
+
+extern "C" int yve_render(const uint32_t *records, const uint32_t *leaves, int root_valid,
+                          const float pos[3], const float dir0[3], const float du[3], const float dv[3],
+                          const float light[3], int width, int height,
+                          int shadow, int ao_samples, uint32_t seed, float voxel_size, float ao_max_t,
+                          uint32_t *hit_node, int32_t *hit_child, float *hit_t, uint32_t *rgba,
+                          uint64_t *out_fetches, int *out_max_sp, uint64_t *out_visits) {
+  const Rec *recs = reinterpret_cast<const Rec *>(records);
+  if (g_mode == 3) {
+    HostCullFetch fetch; fetch.recs = recs;
+    return render_with(fetch, leaves, root_valid, pos, dir0, du, dv, light, width, height, shadow, ao_samples, seed, voxel_size,
+                       ao_max_t, hit_node, hit_child, hit_t, rgba, out_fetches, out_max_sp, out_visits);
+  }
+  HostFetch fetch{ recs };
+  return render_with(fetch, leaves, root_valid, pos, dir0, du, dv, light, width, height, shadow, ao_samples, seed, voxel_size,
+                     ao_max_t, hit_node, hit_child, hit_t, rgba, out_fetches, out_max_sp, out_visits);
 }

@@ -25,7 +25,10 @@ def _compare(svo, cam_spec, W, H, sec_kw=None, mode=2):
     else:
         o = yvo.render(nodes, svo.GetRoot(), cam, threads=4)
         e = yve.render(recs, leaves, len(recs) > 0, pos, d0, du, dv, pos, W, H, mode=mode)
-        assert e["visits"] == o["stats"]["node_visits"]
+        if mode == 3:                            # octant culling: never more node fetches than the reference traversal
+            assert e["visits"] <= o["stats"]["node_visits"]
+        else:
+            assert e["visits"] == o["stats"]["node_visits"]
     assert (o["node"] == e["node"]).all(), name
     assert (o["child"] == e["child"]).all(), name
     assert o["t"].tobytes() == e["t"].tobytes(), name
@@ -33,18 +36,22 @@ def _compare(svo, cam_spec, W, H, sec_kw=None, mode=2):
     return o, e
 
 
-@pytest.mark.parametrize("mode", [2, 0], ids=["lean_step", "trace_step"])
+@pytest.mark.parametrize("mode", [3, 2, 0], ids=["lean_step_cull", "lean_step", "trace_step"])
 @pytest.mark.parametrize("cam", scenes.CAMERAS, ids=[c[0] for c in scenes.CAMERAS])
 def test_fractal_primary(cam, mode):
     o, e = _compare(scenes.fractal(9), cam, 160, 120, mode=mode)
     assert e["max_sp"] <= 8                      # stack depth < tree depth (tail pushes are elided)
-    assert e["fetches"] >= o["stats"]["node_visits"]
+    if mode != 3:
+        assert e["fetches"] >= o["stats"]["node_visits"]
+    elif cam[0] == "main_cpp_up":
+        assert e["visits"] < 0.8 * o["stats"]["node_visits"]        # the culling does cull (27 % here)
 
 
 @pytest.mark.parametrize("cam", [scenes.CAMERAS[2], scenes.CAMERAS[4], scenes.CAMERAS[5]], ids=lambda c: c[0])
 def test_single_sphere_and_dense(cam):
-    _compare(scenes.single_sphere(6), cam, 96, 96)
-    _compare(scenes.dense_random(5, 0.03)[0], cam, 96, 96)
+    for mode in (2, 3):
+        _compare(scenes.single_sphere(6), cam, 96, 96, mode=mode)
+        _compare(scenes.dense_random(5, 0.03)[0], cam, 96, 96, mode=mode)
 
 
 @pytest.mark.parametrize("sec", [
@@ -53,7 +60,8 @@ def test_single_sphere_and_dense(cam):
     dict(shadow=1, ao_samples=4, seed=7, light_pos=(0.6, 0.4, 1.2), voxel_size=1.0 / 512, ao_max_t=0.1),
 ], ids=["shadow", "ao4", "shadow+ao4"])
 def test_fractal_secondary(sec):
-    o, e = _compare(scenes.fractal(9), scenes.CAMERAS[1], 128, 96, sec)
+    _compare(scenes.fractal(9), scenes.CAMERAS[1], 128, 96, sec, mode=2)
+    o, e = _compare(scenes.fractal(9), scenes.CAMERAS[1], 128, 96, sec, mode=3)
     base = yvo.render(scenes.fractal(9).nodes(), scenes.fractal(9).GetRoot(),
                       yvo.camera(*scenes.CAMERAS[1][1:4], scenes.CAMERAS[1][4], 128, 96))
     assert (o["rgba"] != base["rgba"]).any()     # the secondary rays do change the picture

@@ -16,6 +16,7 @@ def _same(svo, check_data=True):
     assert drecs.shape == recs.shape and dleaves.shape == leaves.shape
     assert (drecs == recs).all() and (dleaves == leaves).all()
     nodes = svo.nodes()
+    assert (svo.octant_masks(0) == svo.octant_masks()).all()          # the culling traversal's occupancy words
     if len(recs) and check_data:       # (the host path uploads VoxNode::data only when the LOD cut-off is first used)
         assert (dnd == nodes["data"][recs[:, 3]]).all()
 

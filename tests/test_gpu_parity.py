@@ -126,13 +126,18 @@ def test_secondary_rays(renderer, sec, persistent):
     renderer.EnableCounters(True)
     for cam in (scenes.CAMERAS[1], scenes.CAMERAS[4]):
         o = _render_cpu(svo, cam, 397, 301, sec, visits=True)
-        for sec_queue in (0, 1):
+        for sec_queue, cull in ((0, 0), (1, 0), (0, 1)):
             renderer.SetOption("sec_queue", sec_queue)
+            renderer.SetOption("cull", cull)
             img, node, child, t = _render_gpu(renderer, cam, 397, 301, sec)
-            _check(o, img, node, child, t, "sec/q%d" % sec_queue)
+            _check(o, img, node, child, t, "sec/q%d/cull%d" % (sec_queue, cull))
             visits, pops = renderer.GetCounters()
-            assert (visits == o["visits"]).all(), "node visits differ (sec_queue=%d)" % sec_queue
+            if cull:                                  # octant culling: same pixels from fewer node fetches
+                assert (visits <= o["visits"]).all() and visits.sum() < 0.85 * o["visits"].sum()
+            else:
+                assert (visits == o["visits"]).all(), "node visits differ (sec_queue=%d)" % sec_queue
     renderer.EnableCounters(False)
+    renderer.SetOption("cull", 0)
     renderer.SetOption("sec_queue", 0)
     renderer.SetSecondary(0, 0)
 
@@ -248,18 +253,29 @@ def test_trace_rays_matches_oracle(renderer):
 
 
 def test_counters_equal_oracle_visits(renderer):
-    """The kernel dereferences exactly the nodes the oracle does (basis of the roofline's V-bar)."""
+    """With the octant culling off the kernel dereferences exactly the nodes the oracle does (basis of the roofline's
+    V-bar); with it on (option "cull") it produces the same hits from fewer dereferences."""
     svo = scenes.fractal(10)
     renderer.SetScene(svo)
     renderer.EnableCounters(True)
     cam = scenes.CAMERAS[1]
+    o = _render_cpu(svo, cam, 256, 256, visits=True)
     for persistent in (0, 1, 2):
         renderer.SetOption("persistent", persistent)
+        renderer.SetOption("cull", 0)
         _render_gpu(renderer, cam, 256, 256)
         visits, pops = renderer.GetCounters()
-        o = _render_cpu(svo, cam, 256, 256, visits=True)
         assert (visits == o["visits"]).all()
         assert pops.sum() > 0
+        renderer.SetOption("cull", 1)
+        img, node, child, t = _render_gpu(renderer, cam, 256, 256)
+        _check(o, img, node, child, t, "cull/%d" % persistent)
+        culled, cpops = renderer.GetCounters()
+        assert (culled <= visits).all()
+        if persistent != 2:                           # (the queue schedule has no culling variant)
+            assert culled.sum() < 0.8 * visits.sum() and cpops.sum() < pops.sum()
+        renderer.SetOption("cull", 0)
+    renderer.SetOption("persistent", 0)
     renderer.EnableCounters(False)
 
 

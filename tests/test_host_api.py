@@ -246,3 +246,23 @@ def test_multi_device_renderer_needs_gpus():
         with pytest.raises(yv.YVError) as e:
             make()
         assert e.value.code == -4 and "no CPU fallback" in str(e.value)
+
+
+def test_octant_masks_follow_their_definition():
+    """Byte c of a record's 64-bit octant mask = (leaf flags | child flags) of its child NODE c, 0 for leaf / empty slots
+    (svo_pack.h) — what the culling traversal relies on."""
+    for svo in (scenes.fractal(8), scenes.dense_random(5, 0.05)[0], scenes.single_sphere(6)):
+        recs, _ = svo.packed()
+        g = svo.octant_masks()
+        assert g.shape[0] == recs.shape[0]
+        occ = ((recs[:, 2] | (recs[:, 2] >> 8)) & 0xFF).astype(np.uint64)
+        child_mask = (recs[:, 2] >> 8) & 0xFF
+        want = np.zeros(len(recs), np.uint64)
+        rank = np.zeros(len(recs), np.int64)
+        for c in range(8):
+            has = ((child_mask >> c) & 1).astype(bool)
+            idx = recs[:, 0].astype(np.int64) + rank
+            want[has] |= occ[idx[has]] << np.uint64(8 * c)
+            rank += has
+        assert (g == want).all()
+        assert (g != 0).sum() > 0 or len(recs) == 1

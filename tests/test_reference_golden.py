@@ -142,6 +142,7 @@ def test_cuda_node_visits_equal_the_spu_programs_fetch_count(ref):
     """FetchNode calls of the reference's SPU program (trace_spu.cpp:33) == node visits counted by the kernel."""
     r = yv.SVORenderer(0)
     r.EnableCounters(True)
+    r.SetOption("cull", 0)             # count the reference traversal's node fetches (the default; stated because the count depends on it)
     try:
         for scene in SCENES:
             r.SetScene(yv.SVOData().Load(os.path.join(HERE, scene + ".vox")))

@@ -116,6 +116,8 @@ def lib():
         "yv_svo_device_packed_copy": (i32, [vp, i32, P(u32), P(u32), vp, vp, vp]),
         "yv_svo_packed_counts": (i32, [vp, P(u32), P(u32)]),
         "yv_svo_packed_copy": (i32, [vp, vp, vp]),
+        "yv_svo_octant_masks": (i32, [vp, vp]),
+        "yv_svo_device_octant_masks": (i32, [vp, i32, vp]),
         "yv_renderer_create": (i32, [i32, P(vp)]),
         "yv_renderer_destroy": (None, [vp]),
         "yv_set_scene": (i32, [vp, vp]),
@@ -390,6 +392,17 @@ class SVOData:
         leaves = np.zeros(nl.value, dtype=np.uint32)
         _check(lib().yv_svo_packed_copy(self._h, recs.ctypes.data_as(C.c_void_p), leaves.ctypes.data_as(C.c_void_p)))
         return recs, leaves
+
+    def octant_masks(self, device=None):
+        """One uint64 per packed record: byte c = occupied octants of child node c (host repack, or the device's copy)."""
+        nr = C.c_uint32()
+        _check(lib().yv_svo_packed_counts(self._h, C.byref(nr), None))
+        out = np.zeros(nr.value, np.uint64)
+        if device is None:
+            _check(lib().yv_svo_octant_masks(self._h, out.ctypes.data_as(C.c_void_p)))
+        else:
+            _check(lib().yv_svo_device_octant_masks(self._h, int(device), out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def device_packed(self, device=0):
         """The packed arrays as they sit on the device (records (n,4) u32, leaves, node_data)."""

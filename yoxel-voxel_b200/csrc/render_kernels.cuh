@@ -39,7 +39,8 @@
 namespace yv {
 
 struct RenderParams {
-  const uint4 *recs;           // packed records (svo_pack.h)
+  const uint4 *recs;           // packed records, device form (svo_pack.h): { child_base, masks, octants lo, octants hi }
+  const uint2 *info;           // { leaf_base, orig_id } per record, read by hits only
   const uint32_t *leaves;      // inline VoxData words
   const uint32_t *node_data;   // VoxNode::data per record (LOD hits only; NULL when detail == 0)
   float detail;                // rp.detailCoef (demo/SVORenderer.cpp:104); 0 = no LOD cut-off
@@ -158,24 +159,35 @@ __host__ __device__ inline size_t stack_smem_bytes(int stack, int threads = kCta
 // the tree staged in shared memory; RAW = true: the reference's 40-byte VoxNode pool as uploaded page by
 // page for scenes under edit (CudaSVO::Update, demo/SVORenderer.cpp:33-53): `recs` then points at the
 // pool viewed as uint32 words (flags, data, child[8]).
-template <bool COUNT, bool STAGED, bool RAW = false>
+// the 512 box masks of trace_core.cuh's octant culling, index (dirFlags << 6) | (ch0 << 3) | chx, in stored-child space
+struct BoxLut { uint8_t v[512]; };
+constexpr BoxLut make_box_lut() {
+  BoxLut t{};
+  for (uint32_t f = 0; f < 8; ++f)
+    for (uint32_t a = 0; a < 8; ++a)
+      for (uint32_t b = 0; b < 8; ++b) {
+        uint32_t box = 0;
+        for (uint32_t o = 0; o < 8; ++o)
+          if ((o & a) == a && (o | b) == b) box |= 1u << (o ^ f);
+        t.v[(f << 6) | (a << 3) | b] = (uint8_t)box;
+      }
+  return t;
+}
+__device__ const BoxLut kBoxLut = make_box_lut();
+
+template <bool COUNT, bool STAGED, bool RAW = false, bool CULL = false>
 struct NodeFetch {
   const uint4 *recs;
   const uint4 *staged;
   uint32_t staged_n;
   uint32_t root;                 // index of the root node (0 for the packed pool)
   mutable uint32_t visits, revisits;
+  const uint2 *info;             // { leaf_base, orig_id } per record (packed pool)
+  const uint8_t *lut;            // CULL: the box masks, staged in shared memory
   __device__ __forceinline__ const uint32_t *pool() const { return reinterpret_cast<const uint32_t *>(recs); }
-  __device__ __forceinline__ Rec load(uint32_t idx) const {
-    uint4 v;
-    if (STAGED && idx < staged_n) v = staged[idx];
-    else v = __ldg(recs + idx);
-    Rec r = { v.x, v.y, v.z, v.w };
-    return r;
-  }
-  __device__ __forceinline__ Rec get(uint32_t idx, bool visit) const {      // classic form (trace_step)
-    if (COUNT) { if (visit) ++visits; else ++revisits; }
-    return load(idx);
+  __device__ __forceinline__ uint4 load(uint32_t idx) const {
+    if (STAGED && idx < staged_n) return staged[idx];
+    return __ldg(recs + idx);
   }
   __device__ __forceinline__ uint32_t root_index() const { return root; }
   // one node dereference: the two child masks (+ child base for the packed layout)
@@ -187,31 +199,45 @@ struct NodeFetch {
       masks = leaf | ((~(flags >> 8) & ~leaf & 0xffu) << 8);              // child = not leaf, not null
       child_base = 0u;
     } else {
-      const Rec r = load(idx);
-      masks = r.masks; child_base = r.child_base;
+      const uint4 r = load(idx);
+      child_base = r.x; masks = r.y;
     }
+  }
+  // ... and, for the culling traversal, the occupancy of the children's octants that rides in the same 16 bytes
+  __device__ __forceinline__ void node(uint32_t idx, bool visit, uint32_t &masks, uint32_t &child_base,
+                                       uint32_t &gm_lo, uint32_t &gm_hi) const {
+    if (COUNT) { if (visit) ++visits; else ++revisits; }
+    const uint4 r = load(idx);
+    child_base = r.x; masks = r.y; gm_lo = r.z; gm_hi = r.w;
+  }
+  __device__ __forceinline__ uint32_t box(uint32_t flags, uint32_t ch0, uint32_t chx) const {
+    return lut[(flags << 6) | (ch0 << 3) | chx];
   }
   __device__ __forceinline__ uint32_t child_index(uint32_t idx, uint32_t child_base, uint32_t masks, uint32_t c) const {
     if (RAW) return __ldg(pool() + (size_t)idx * 10u + 2u + c);
     return child_base + (uint32_t)__popc((masks >> 8) & ((1u << c) - 1u));
   }
-  // a finished ray: reference node id and the VoxData to shade (leaf slot c, or the node's own data for LOD)
+  // a finished ray: reference node id and the VoxData to shade (leaf slot c, or the node's own data for LOD).
+  // `masks` = the masks of record idx (the traversal holds them when it reports a leaf hit; unused for a LOD hit)
   __device__ __forceinline__ void hit_info(const uint32_t *leaves, const uint32_t *node_data, uint32_t idx, uint32_t c,
-                                           bool lod_hit, uint32_t &orig_id, uint32_t &data) const {
+                                           uint32_t masks, bool lod_hit, uint32_t &orig_id, uint32_t &data) const {
     if (RAW) {
       orig_id = idx;
       data = __ldg(pool() + (size_t)idx * 10u + (lod_hit ? 1u : 2u + c));
     } else {
-      const Rec r = load(idx);
-      orig_id = r.orig_id;
+      const uint2 in = __ldg(info + idx);
+      orig_id = in.y;
       data = lod_hit ? __ldg(node_data + idx)
-                     : __ldg(leaves + r.leaf_base + (uint32_t)__popc(r.masks & 0xffu & ((1u << c) - 1u)));
+                     : __ldg(leaves + in.x + (uint32_t)__popc(masks & 0xffu & ((1u << c) - 1u)));
     }
   }
 };
 
 // the raw pool is traversed as it was handed in: bound the descent in the kernel (trace_core.cuh, FetchTraits)
-template <bool COUNT, bool STAGED> struct FetchTraits<NodeFetch<COUNT, STAGED, true>> { static constexpr bool kGuardDepth = true; };
+template <bool COUNT, bool STAGED, bool RAW, bool CULL> struct FetchTraits<NodeFetch<COUNT, STAGED, RAW, CULL>> {
+  static constexpr bool kGuardDepth = RAW;
+  static constexpr bool kCull = CULL && !RAW;
+};
 
 // tile row (8 pixel rows) of this launch -> first pixel row, for contiguous and interleaved partitions
 __device__ __forceinline__ int tile_row_y(const RenderParams &p, int ty) {
@@ -221,19 +247,22 @@ __device__ __forceinline__ int tile_row_y(const RenderParams &p, int ty) {
 
 enum : int { kLaneIdle = 0, kLaneActive = 1, kLaneHit = 2, kLaneMiss = 3, kLaneNew = 4, kLaneLodHit = 5 };
 
-template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED, bool LOD, bool RAW, bool JIT = false>
+template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED, bool LOD, bool RAW, bool JIT = false, bool CULL = false>
 __global__ void __launch_bounds__(kFrameCta, kFrameMinBlocks) render_frame(const __grid_constant__ RenderParams p) {
   extern __shared__ uint4 smem[];
+  __shared__ uint32_t box_lut[CULL ? 128 : 1];
   uint4 *staged = smem;
   uint4 *stack_area = smem + (STAGED ? p.smem_nodes : 0u);
-  if (STAGED) {
+  if (CULL)
+    for (uint32_t i = threadIdx.x; i < 128u; i += kFrameCta) box_lut[i] = reinterpret_cast<const uint32_t *>(kBoxLut.v)[i];
+  if (STAGED)
     for (uint32_t i = threadIdx.x; i < p.smem_nodes; i += kFrameCta) staged[i] = __ldg(p.recs + i);
-    __syncthreads();
-  }
+  if (STAGED || CULL) __syncthreads();
 
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  NodeFetch<COUNT, STAGED, RAW> fetch = { p.recs, staged, p.smem_nodes, p.root_index, 0u, 0u };
+  NodeFetch<COUNT, STAGED, RAW, CULL> fetch = { p.recs, staged, p.smem_nodes, p.root_index, 0u, 0u, p.info,
+                                                reinterpret_cast<const uint8_t *>(box_lut) };
   typename StackOf<STACK>::type stk(stack_area);
   LeanState s;
 
@@ -335,7 +364,7 @@ __global__ void __launch_bounds__(kFrameCta, kFrameMinBlocks) render_frame(const
         uint32_t hn = YV_MISS_NODE; int32_t hc = YV_MISS_CHILD; float ht = 0.0f;
         if (hit) {
           const uint32_t c = s.ch ^ s.flags;
-          fetch.hit_info(p.leaves, p.node_data, s.idx, c, lod_hit, hn, sdata);   // re-reads the hit node
+          fetch.hit_info(p.leaves, p.node_data, s.idx, c, s.masks, lod_hit, hn, sdata);
           hc = lod_hit ? -1 : (int32_t)c; ht = max3f(s.t1x, s.t1y, s.t1z);
           unpack_normal(sdata, nx, ny, nz);
           float dx, dy, dz;                                       // the primary direction, recomputed
@@ -449,12 +478,12 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_queue(const 
   const int tx = blockIdx.x % tiles_x32, ty = blockIdx.x / tiles_x32;
   const int wx0 = tx * 32 + (warp & 1) * 16, wy0 = tile_row_y(p, ty * 2 + (warp >> 1));
 
-  NodeFetch<COUNT, false> fetch = { p.recs, nullptr, 0u, 0u, 0u, 0u };
+  NodeFetch<COUNT, false> fetch = { p.recs, nullptr, 0u, 0u, 0u, 0u, p.info, nullptr };
   typename StackOf<STACK>::type stk(stack_area);
   LeanState s;
   const bool root_valid = p.root_valid != 0u;
   uint32_t root_masks = 0u, root_child_base = 0u;
-  if (root_valid) { const Rec r = fetch.load(0u); root_masks = r.masks; root_child_base = r.child_base; }
+  if (root_valid) { const uint4 r = fetch.load(0u); root_masks = r.y; root_child_base = r.x; }
 
   // ---- phase 0: set up 4 rays per lane, build the queue --------------------------------------------
   int qcount = 0;
@@ -540,7 +569,7 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_queue(const 
       ht = __uint_as_float(slots[2 * kQueueRays + slot]);
       hc = (int32_t)c;
       uint32_t data;
-      fetch.hit_info(p.leaves, p.node_data, idx, c, false, hn, data);
+      fetch.hit_info(p.leaves, p.node_data, idx, c, fetch.load(idx).y, false, hn, data);
       float nx, ny, nz, dx, dy, dz;
       unpack_normal(data, nx, ny, nz);
       primary_dir(p.dir0, p.du, p.dv, x, y, dx, dy, dz);
@@ -593,12 +622,12 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_sec_queue(co
   const bool in_frame = x < p.width && y < p.y1;
   const uint32_t pixel = (uint32_t)y * (uint32_t)p.width + (uint32_t)x;
 
-  NodeFetch<COUNT, false> fetch = { p.recs, nullptr, 0u, 0u, 0u, 0u };
+  NodeFetch<COUNT, false> fetch = { p.recs, nullptr, 0u, 0u, 0u, 0u, p.info, nullptr };
   LocalStack stk(nullptr);
   LeanState s;
   const bool root_valid = p.root_valid != 0u;
   uint32_t root_masks = 0u, root_child_base = 0u;
-  if (root_valid) { const Rec r = fetch.load(0u); root_masks = r.masks; root_child_base = r.child_base; }
+  if (root_valid) { const uint4 r = fetch.load(0u); root_masks = r.y; root_child_base = r.x; }
 
   // ---- A: primary ray, lock-step ------------------------------------------------------------------
   int state = kLaneIdle;
@@ -631,7 +660,7 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_sec_queue(co
   float nx = 0.f, ny = 0.f, nz = 0.f, Ox = 0.f, Oy = 0.f, Oz = 0.f, dl = 0.f, vis = 1.0f;
   if (hit) {
     const uint32_t c = s.ch ^ s.flags;
-    fetch.hit_info(p.leaves, p.node_data, s.idx, c, lod_hit, hn, sdata);
+    fetch.hit_info(p.leaves, p.node_data, s.idx, c, s.masks, lod_hit, hn, sdata);
     hc = lod_hit ? -1 : (int32_t)c; ht = max3f(s.t1x, s.t1y, s.t1z);
     unpack_normal(sdata, nx, ny, nz);
     float dx, dy, dz;
@@ -903,12 +932,12 @@ __global__ void __launch_bounds__(256) resolve_frames(const uint4 *sum, uint32_t
 // arbitrary rays (DynamicSVO::TraceRay, ore/src/main.cpp:125)
 // ---------------------------------------------------------------------------------------------
 template <bool RAW>
-__global__ void __launch_bounds__(128) trace_rays_kernel(const uint4 *recs, const uint32_t *leaves, uint32_t root_valid, uint32_t root_index,
+__global__ void __launch_bounds__(128) trace_rays_kernel(const uint4 *recs, const uint2 *info, const uint32_t *leaves, uint32_t root_valid, uint32_t root_index,
                                                          const float *pos, const float *dir, uint32_t count,
                                                          uint32_t *node, int32_t *child, float *t) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  NodeFetch<false, false, RAW> fetch = { recs, nullptr, 0u, root_index, 0u, 0u };
+  NodeFetch<false, false, RAW> fetch = { recs, nullptr, 0u, root_index, 0u, 0u, info, nullptr };
   LocalStack stk(nullptr);
   LeanState s;
   const float dx = adjust_dir1(dir[3 * i]), dy = adjust_dir1(dir[3 * i + 1]), dz = adjust_dir1(dir[3 * i + 2]);
@@ -921,7 +950,7 @@ __global__ void __launch_bounds__(128) trace_rays_kernel(const uint4 *recs, cons
     }
   }
   uint32_t hn = YV_MISS_NODE, data;
-  if (hit) fetch.hit_info(leaves, nullptr, s.idx, s.ch ^ s.flags, false, hn, data);
+  if (hit) fetch.hit_info(leaves, nullptr, s.idx, s.ch ^ s.flags, s.masks, false, hn, data);
   node[i] = hn;
   child[i] = hit ? (int32_t)(s.ch ^ s.flags) : YV_MISS_CHILD;
   t[i] = hit ? max3f(s.t1x, s.t1y, s.t1z) : 0.0f;

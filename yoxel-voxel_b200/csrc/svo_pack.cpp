@@ -50,7 +50,7 @@ int analyse_shared_pool(const HostSVO &svo, uint64_t limit, std::string &err) {
 }  // namespace
 
 int pack_svo(const HostSVO &svo, PackedSVO &out, std::string &err) {
-  out.records.clear(); out.leaves.clear(); out.level_start.clear(); out.node_data.clear();
+  out.records.clear(); out.leaves.clear(); out.level_start.clear(); out.node_data.clear(); out.octants.clear();
   out.root_null = YV_IS_NULL(svo.root);
   if (out.root_null) { out.level_start.push_back(0); return 0; }
   if (svo.root >= svo.nodes.size()) { err = "root id outside node pool"; return -1; }
@@ -101,7 +101,29 @@ int pack_svo(const HostSVO &svo, PackedSVO &out, std::string &err) {
     cur.swap(nxt);
   }
   out.level_start.push_back((uint32_t)emitted);
+  // grandchild masks: byte c of a record = occupied octants (leaf | child flags) of its child node c
+  out.octants.assign(out.records.size(), 0ull);
+  for (size_t i = 0; i < out.records.size(); ++i) {
+    const PackedRecord &r = out.records[i];
+    uint64_t g = 0; uint32_t k = 0;
+    for (uint32_t c = 0; c < 8; ++c)
+      if ((r.masks >> (8 + c)) & 1u) {
+        const uint32_t m = out.records[r.child_base + k++].masks;
+        g |= (uint64_t)((m | (m >> 8)) & 0xffu) << (8 * c);
+      }
+    out.octants[i] = g;
+  }
   return 0;
+}
+
+void device_layout(const PackedSVO &p, std::vector<DeviceRecord> &trav, std::vector<DeviceRecordInfo> &info) {
+  trav.resize(p.records.size()); info.resize(p.records.size());
+  for (size_t i = 0; i < p.records.size(); ++i) {
+    const PackedRecord &r = p.records[i];
+    const uint64_t g = i < p.octants.size() ? p.octants[i] : 0ull;
+    trav[i] = DeviceRecord{ r.child_base, r.masks, (uint32_t)g, (uint32_t)(g >> 32) };
+    info[i] = DeviceRecordInfo{ r.leaf_base, r.orig_id };
+  }
 }
 
 }  // namespace yv

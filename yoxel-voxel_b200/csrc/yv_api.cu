@@ -74,8 +74,8 @@ int upload_staged(void *dst, const void *src, size_t bytes) {
 }
 
 void free_packed_device(DeviceSVO &d) {
-  cudaFree(d.recs); cudaFree(d.leaves); cudaFree(d.node_data);
-  d.recs = nullptr; d.leaves = nullptr; d.node_data = nullptr; d.n_recs = d.n_leaves = 0;
+  cudaFree(d.recs); cudaFree(d.info); cudaFree(d.leaves); cudaFree(d.node_data);
+  d.recs = nullptr; d.info = nullptr; d.leaves = nullptr; d.node_data = nullptr; d.n_recs = d.n_leaves = 0;
 }
 
 // CudaSVO::Update (demo/SVORenderer.cpp:33-53; paging: reaction/report/main.tex:71): bring the device's raw
@@ -147,14 +147,15 @@ int ensure_uploaded(yv_svo *svo, int device, DeviceSVO **out) {
       yv::DevicePacked dp; std::string err;
       if (yv::pack_svo_on_device(d->raw, svo->host.nodes.size(), svo->host.root, dp, err) == 0) {
         if (dp.levels > yv::kMaxStack + 1) {
-          cudaFree(dp.recs); cudaFree(dp.leaves); cudaFree(dp.node_data);
+          cudaFree(dp.recs); cudaFree(dp.info); cudaFree(dp.leaves); cudaFree(dp.node_data);
           return fail(YV_ERR_FORMAT, "tree deeper than the traversal stack supports");
         }
-        d->recs = (uint4 *)dp.recs; d->leaves = dp.leaves; d->node_data = dp.node_data;
+        d->recs = (uint4 *)dp.recs; d->info = (uint2 *)dp.info; d->leaves = dp.leaves; d->node_data = dp.node_data;
         d->n_recs = dp.n_recs; d->n_leaves = dp.n_leaves; d->levels = dp.levels;
         d->root_null = YV_IS_NULL(svo->host.root);
         if (!d->recs) {                            // null root: keep valid (dummy) pointers
-          YV_CUDA(cudaMalloc(&d->recs, sizeof(uint4))); YV_CUDA(cudaMalloc(&d->leaves, sizeof(uint32_t)));
+          YV_CUDA(cudaMalloc(&d->recs, sizeof(uint4))); YV_CUDA(cudaMalloc(&d->info, sizeof(uint2)));
+          YV_CUDA(cudaMalloc(&d->leaves, sizeof(uint32_t)));
         }
         d->packed_version = want;
         done = true;
@@ -177,8 +178,15 @@ int ensure_uploaded(yv_svo *svo, int device, DeviceSVO **out) {
       d.root_null = svo->packed.root_null;
       d.levels = (int)svo->packed.level_start.size() - 1;
       YV_CUDA(cudaMalloc(&d.recs, std::max<size_t>(1, d.n_recs) * sizeof(uint4)));
+      YV_CUDA(cudaMalloc(&d.info, std::max<size_t>(1, d.n_recs) * sizeof(uint2)));
       YV_CUDA(cudaMalloc(&d.leaves, std::max<size_t>(1, d.n_leaves) * sizeof(uint32_t)));
-      if (d.n_recs) { int urc = upload_staged(d.recs, svo->packed.records.data(), d.n_recs * sizeof(uint4)); if (urc) return urc; }
+      if (d.n_recs) {
+        std::vector<yv::DeviceRecord> trav; std::vector<yv::DeviceRecordInfo> info;
+        yv::device_layout(svo->packed, trav, info);
+        int urc = upload_staged(d.recs, trav.data(), d.n_recs * sizeof(uint4));
+        if (!urc) urc = upload_staged(d.info, info.data(), d.n_recs * sizeof(uint2));
+        if (urc) return urc;
+      }
       if (d.n_leaves) { int urc = upload_staged(d.leaves, svo->packed.leaves.data(), d.n_leaves * sizeof(uint32_t)); if (urc) return urc; }
       d.packed_version = want;
     }
@@ -280,9 +288,9 @@ void init_ray_dir(const yv_renderer *r, float dir0[3], float du[3], float dv[3],
   init_ray_dir_raw(r->dir, r->up, r->fov, r->width, r->height, dir0, du, dv, basis);
 }
 
-template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED, bool LOD = false, bool RAW = false, bool JIT = false>
+template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED, bool LOD = false, bool RAW = false, bool JIT = false, bool CULL = false>
 int launch_kernel(yv_renderer *r, const yv::RenderParams &p, size_t smem) {
-  auto kern = yv::render_frame<SEC, COUNT, STACK, PERSISTENT, STAGED, LOD, RAW, JIT>;
+  auto kern = yv::render_frame<SEC, COUNT, STACK, PERSISTENT, STAGED, LOD, RAW, JIT, CULL>;
   if (smem > 48 * 1024) YV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long grid;
   if (PERSISTENT) {
@@ -349,6 +357,13 @@ int launch_lod(yv_renderer *r, const yv::RenderParams &p) {
                                 : launch_kernel<SEC, COUNT, yv::kStackLocal, false, false, true>(r, p, 0);
 }
 
+// octant culling (option "cull", off by default): packed pool, local-memory stack, no staging
+template <bool SEC, bool COUNT, bool LOD>
+int launch_cull(yv_renderer *r, const yv::RenderParams &p) {
+  return r->opt_persistent == 1 ? launch_kernel<SEC, COUNT, yv::kStackLocal, true, false, LOD, false, false, true>(r, p, 0)
+                                : launch_kernel<SEC, COUNT, yv::kStackLocal, false, false, LOD, false, false, true>(r, p, 0);
+}
+
 // displaced ray origins: primary rays, packed pool, tiles schedule, local-memory stack
 template <bool COUNT, bool LOD>
 int launch_jitter(yv_renderer *r, const yv::RenderParams &p) {
@@ -379,7 +394,7 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
     p.root_valid = YV_IS_NULL(r->svo->host.root) ? 0u : 1u;
     p.root_index = p.root_valid ? r->svo->host.root : 0u;
   } else {
-    p.recs = ds->recs; p.leaves = ds->leaves;
+    p.recs = ds->recs; p.info = ds->info; p.leaves = ds->leaves;
     p.root_valid = ds->root_null ? 0u : 1u;
   }
   p.smem_nodes = raw ? 0u : (uint32_t)std::min<size_t>((size_t)std::max(0, r->opt_smem_nodes), ds->n_recs);
@@ -456,7 +471,20 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
 
   if (!r->suppress_events) YV_CUDA(cudaEventRecord(r->ev0, r->stream));
   const int key = (sec ? 2 : 0) | (r->counters ? 1 : 0);
-  if (jitter) {
+  const bool cull = r->opt_cull && !raw && !jitter && r->opt_stack == yv::kStackLocal && p.smem_nodes == 0 &&
+                    r->opt_persistent != 2 && !(sec && r->opt_sec_queue && r->opt_persistent != 1);
+  if (cull) {
+    switch (key | (lod ? 4 : 0)) {
+      case 0: rc = launch_cull<false, false, false>(r, p); break;
+      case 1: rc = launch_cull<false, true, false>(r, p); break;
+      case 2: rc = launch_cull<true, false, false>(r, p); break;
+      case 3: rc = launch_cull<true, true, false>(r, p); break;
+      case 4: rc = launch_cull<false, false, true>(r, p); break;
+      case 5: rc = launch_cull<false, true, true>(r, p); break;
+      case 6: rc = launch_cull<true, false, true>(r, p); break;
+      default: rc = launch_cull<true, true, true>(r, p); break;
+    }
+  } else if (jitter) {
     if (lod) rc = r->counters ? launch_jitter<true, true>(r, p) : launch_jitter<false, true>(r, p);
     else rc = r->counters ? launch_jitter<true, false>(r, p) : launch_jitter<false, false>(r, p);
   } else if (sec && !raw && r->opt_sec_queue && r->opt_persistent != 1) {      // pooled AO rays (config 4)
@@ -611,6 +639,7 @@ static void free_device_copies(yv_svo *svo) {
     cudaSetDevice(kv.first);
     cudaDeviceSynchronize();                      // no renderer stream is still reading the copies
     cudaFree(kv.second.recs);
+    cudaFree(kv.second.info);
     cudaFree(kv.second.leaves);
     cudaFree(kv.second.node_data);
     cudaFree(kv.second.raw);
@@ -743,7 +772,7 @@ uint64_t yv_svo_device_bytes(const yv_svo *svo, int device) {
   if (!svo) return 0;
   auto it = svo->dev.find(device);
   if (it == svo->dev.end()) return 0;
-  return (uint64_t)it->second.n_recs * 16u + (uint64_t)it->second.n_leaves * 4u +
+  return (uint64_t)it->second.n_recs * 24u + (uint64_t)it->second.n_leaves * 4u +
          (it->second.node_data ? (uint64_t)it->second.n_recs * 4u : 0u);
 }
 
@@ -757,10 +786,46 @@ int yv_svo_device_packed_copy(yv_svo *svo, int device, uint32_t *n_records, uint
   if (n_records) *n_records = (uint32_t)d->n_recs;
   if (n_leaves) *n_leaves = (uint32_t)d->n_leaves;
   YV_CUDA(cudaSetDevice(device));
-  if (records_out && d->n_recs) YV_CUDA(cudaMemcpy(records_out, d->recs, d->n_recs * 16, cudaMemcpyDeviceToHost));
+  if (records_out && d->n_recs) {                    // the canonical record { child_base, leaf_base, masks, orig_id } (svo_pack.h)
+    return guarded([&]() -> int {
+      std::vector<uint4> trav(d->n_recs); std::vector<uint2> info(d->n_recs);
+      YV_CUDA(cudaMemcpy(trav.data(), d->recs, d->n_recs * 16, cudaMemcpyDeviceToHost));
+      YV_CUDA(cudaMemcpy(info.data(), d->info, d->n_recs * 8, cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < d->n_recs; ++i) {
+        records_out[4 * i] = trav[i].x; records_out[4 * i + 1] = info[i].x; records_out[4 * i + 2] = trav[i].y; records_out[4 * i + 3] = info[i].y;
+      }
+      if (leaves_out && d->n_leaves) YV_CUDA(cudaMemcpy(leaves_out, d->leaves, d->n_leaves * 4, cudaMemcpyDeviceToHost));
+      if (node_data_out && d->node_data) YV_CUDA(cudaMemcpy(node_data_out, d->node_data, d->n_recs * 4, cudaMemcpyDeviceToHost));
+      return YV_OK;
+    });
+  }
   if (leaves_out && d->n_leaves) YV_CUDA(cudaMemcpy(leaves_out, d->leaves, d->n_leaves * 4, cudaMemcpyDeviceToHost));
   if (node_data_out && d->n_recs && d->node_data) YV_CUDA(cudaMemcpy(node_data_out, d->node_data, d->n_recs * 4, cudaMemcpyDeviceToHost));
   return YV_OK;
+}
+
+// the grandchild masks (one uint64 per record, svo_pack.h): host repack / as they sit on the device
+int yv_svo_octant_masks(yv_svo *svo, uint64_t *out) {
+  if (!svo || !out) return fail(YV_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lock(svo->mu);
+  int rc = guarded([&]() -> int { return ensure_packed(svo); });
+  if (rc) return rc;
+  if (!svo->packed.octants.empty()) std::memcpy(out, svo->packed.octants.data(), svo->packed.octants.size() * 8u);
+  return YV_OK;
+}
+
+int yv_svo_device_octant_masks(yv_svo *svo, int device, uint64_t *out) {
+  if (!svo || !out) return fail(YV_ERR_ARG, "null argument");
+  DeviceSVO *d = nullptr;
+  int rc = guarded([&]() -> int { return ensure_uploaded(svo, device, &d); });
+  if (rc) return rc;
+  return guarded([&]() -> int {
+    std::vector<uint4> trav(d->n_recs);
+    YV_CUDA(cudaSetDevice(device));
+    if (d->n_recs) YV_CUDA(cudaMemcpy(trav.data(), d->recs, d->n_recs * 16, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < d->n_recs; ++i) out[i] = (uint64_t)trav[i].z | ((uint64_t)trav[i].w << 32);
+    return YV_OK;
+  });
 }
 
 int yv_svo_packed_counts(yv_svo *svo, uint32_t *records, uint32_t *leaves) {
@@ -1212,6 +1277,7 @@ int yv_set_option(yv_renderer *r, const char *name, int value) {
   else if (n == "pipeline_taper") { if (value < 10 || value > 100) return fail(YV_ERR_ARG, "pipeline_taper must be 10..100 percent"); r->opt_pipeline_taper = value; }
   else if (n == "pipeline") { if (value < 0 || value > yv_renderer::kChunks) return fail(YV_ERR_ARG, "pipeline must be 0..8 chunks"); r->opt_pipeline = value; }
   else if (n == "layout") { if (value != 0 && value != 1) return fail(YV_ERR_ARG, "layout must be 0 (packed) or 1 (raw)"); r->opt_layout = value; }
+  else if (n == "cull") r->opt_cull = value != 0;
   else if (n == "refill") { if (value < 0 || value > 31) return fail(YV_ERR_ARG, "refill must be 0..31"); r->opt_refill = value; }
   else if (n == "slots") {
     if (value < 2 || value > yv_renderer::kSlots) return fail(YV_ERR_ARG, "slots must be 2..4 frames in flight");
@@ -1238,6 +1304,7 @@ int yv_get_option(const yv_renderer *r, const char *name, int *value) {
   else if (n == "pipeline_taper") *value = r->opt_pipeline_taper;
   else if (n == "zero_copy") *value = r->opt_zero_copy;
   else if (n == "layout") *value = r->opt_layout;
+  else if (n == "cull") *value = r->opt_cull;
   else if (n == "refill") *value = r->opt_refill;
   else if (n == "stack") *value = r->opt_stack;
   else if (n == "slots") *value = r->opt_slots;
@@ -1268,10 +1335,10 @@ int yv_trace_rays(yv_renderer *r, const float *pos, const float *dir, uint32_t c
     const unsigned grid = (unsigned)((n + 127) / 128);
     if (raw) {
       const uint32_t valid = YV_IS_NULL(r->svo->host.root) ? 0u : 1u;
-      yv::trace_rays_kernel<true><<<grid, 128, 0, r->stream>>>(reinterpret_cast<const uint4 *>(ds->raw), nullptr, valid,
+      yv::trace_rays_kernel<true><<<grid, 128, 0, r->stream>>>(reinterpret_cast<const uint4 *>(ds->raw), nullptr, nullptr, valid,
                                                                valid ? r->svo->host.root : 0u, d_pos, d_dir, count, d_node, d_child, d_t);
     } else {
-      yv::trace_rays_kernel<false><<<grid, 128, 0, r->stream>>>(ds->recs, ds->leaves, ds->root_null ? 0u : 1u, 0u,
+      yv::trace_rays_kernel<false><<<grid, 128, 0, r->stream>>>(ds->recs, ds->info, ds->leaves, ds->root_null ? 0u : 1u, 0u,
                                                                 d_pos, d_dir, count, d_node, d_child, d_t);
     }
     e = cudaGetLastError();

@@ -44,7 +44,8 @@ int guarded(F &&body) {
 }
 
 struct DeviceSVO {
-  uint4 *recs = nullptr;
+  uint4 *recs = nullptr;              // { child_base, masks, octants lo, octants hi } per record (svo_pack.h, device form)
+  uint2 *info = nullptr;              // { leaf_base, orig_id } per record: read by hits only
   uint32_t *leaves = nullptr;
   uint32_t *node_data = nullptr;      // uploaded on first use of the LOD cut-off
   size_t n_recs = 0, n_leaves = 0;
@@ -141,6 +142,7 @@ struct yv_renderer {
   int opt_sec_queue = 0;              // 1 = AO rays pooled per warp (render_sec_queue); measured slower than the per-lane stage machine (6.31 vs 5.60 ms on config 4)
   int opt_layout = 0;                 // 0 = packed records (static scenes), 1 = raw reference pool (scenes under edit)
   int opt_stack = 0;                  // yv::kStackLocal / kStackRing4
+  int opt_cull = 0;                   // 1 = skip child nodes the ray crosses through empty octants only (trace_core.cuh); measured slower, off
 
   // ---- device group (yv_renderer_create_multi) ---------------------------------------------------------------
   // The handle the caller holds is the leader (its own `device` is the first of the mask); peers[i] drives one further GPU.

@@ -56,7 +56,7 @@ void copy_state(const yv_renderer *lead, yv_renderer *m) {
   m->opt_smem_nodes = lead->opt_smem_nodes; m->opt_persistent = lead->opt_persistent; m->opt_refill = lead->opt_refill;
   m->opt_sec_threshold = lead->opt_sec_threshold; m->opt_sec_queue = lead->opt_sec_queue;
   m->opt_layout = lead->opt_layout; m->opt_stack = lead->opt_stack;
-  m->opt_slots = lead->opt_slots;
+  m->opt_slots = lead->opt_slots; m->opt_cull = lead->opt_cull;
 }
 
 // Copy the packed pool of `svo` from src_dev to dst_dev with peer copies, asynchronously on `st` (a stream of dst_dev).
@@ -69,13 +69,15 @@ int replicate_packed_async(yv_svo *svo, int src_dev, int dst_dev, cudaStream_t s
   if (d.recs && d.packed_version == src.packed_version && d.n_recs == src.n_recs) { if (bytes) *bytes = 0; return YV_OK; }
   YV_CUDA(cudaSetDevice(dst_dev));
   YV_CUDA(cudaDeviceSynchronize());                          // nothing still reads the copy that is replaced
-  cudaFree(d.recs); cudaFree(d.leaves); cudaFree(d.node_data);
-  d.recs = nullptr; d.leaves = nullptr; d.node_data = nullptr;
+  cudaFree(d.recs); cudaFree(d.info); cudaFree(d.leaves); cudaFree(d.node_data);
+  d.recs = nullptr; d.info = nullptr; d.leaves = nullptr; d.node_data = nullptr;
   const size_t rb = std::max<size_t>(1, src.n_recs) * sizeof(uint4), lb = std::max<size_t>(1, src.n_leaves) * sizeof(uint32_t);
   YV_CUDA(cudaMalloc(&d.recs, rb));
+  YV_CUDA(cudaMalloc(&d.info, std::max<size_t>(1, src.n_recs) * sizeof(uint2)));
   YV_CUDA(cudaMalloc(&d.leaves, lb));
   uint64_t moved = 0;
   if (src.n_recs) { YV_CUDA(cudaMemcpyPeerAsync(d.recs, dst_dev, src.recs, src_dev, src.n_recs * sizeof(uint4), st)); moved += src.n_recs * sizeof(uint4); }
+  if (src.n_recs) { YV_CUDA(cudaMemcpyPeerAsync(d.info, dst_dev, src.info, src_dev, src.n_recs * sizeof(uint2), st)); moved += src.n_recs * sizeof(uint2); }
   if (src.n_leaves) { YV_CUDA(cudaMemcpyPeerAsync(d.leaves, dst_dev, src.leaves, src_dev, src.n_leaves * sizeof(uint32_t), st)); moved += src.n_leaves * sizeof(uint32_t); }
   if (src.node_data && src.n_recs) {
     YV_CUDA(cudaMalloc(&d.node_data, src.n_recs * sizeof(uint32_t)));
