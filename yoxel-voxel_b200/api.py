@@ -377,9 +377,15 @@ class SVOData:
     def depth(self):
         return int(lib().yv_svo_depth(self._h))
 
-    def nodes(self):
-        """Copy of the host node pool as a structured array (reference layout)."""
+    def nodes(self, copy=True):
+        """The host node pool as a structured array (reference layout). copy=False: a read-only view of the library's
+        own pool (no second 20 GB for a depth-14 volume), valid until the scene is edited, reloaded or freed."""
         n = self.nodecount
+        if not copy and n:
+            buf = (C.c_uint8 * (n * 40)).from_address(lib().yv_svo_nodes(self._h))
+            view = np.frombuffer(buf, dtype=NODE_DTYPE)
+            view.flags.writeable = False
+            return view
         out = np.zeros(n, dtype=NODE_DTYPE)
         if n:
             C.memmove(out.ctypes.data, lib().yv_svo_nodes(self._h), n * 40)
