@@ -135,7 +135,8 @@ int yv_renderer_device(const yv_renderer *r, int k);             /* CUDA ordinal
 int yv_set_partition(yv_renderer *r, int mode, int band_rows);
 /* device time member k spent on its own share of the last frame (imbalance across the group), ms */
 float yv_member_frame_ms(const yv_renderer *r, int k);
-/* wall time and bytes of the last replication of the scene over peer copies (0 when none happened) */
+/* wall time and bytes of the last replication of the scene over peer copies (0 when none happened): the copies to all
+ * peers run concurrently and are timed from the first one issued to the last one complete, allocations excluded */
 int yv_replicate_stats(const yv_renderer *r, double *ms, uint64_t *bytes);
 void yv_renderer_destroy(yv_renderer *r);
 

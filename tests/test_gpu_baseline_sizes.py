@@ -1,0 +1,171 @@
+"""GPU parity at the sizes BASELINE.json states ("parity tests ... at BASELINE.json's full sizes").
+
+  config 3  3840x2160 over the synthetic iso volume (depth 12 here: 31 M nodes build in seconds; the bench runs the
+            depth-13/14 volume with the same checks): row bands against the oracle for the fixed camera and for
+            cameras of bench.py's flythrough path, whose eye is INSIDE the cube (the `t < 0` quirk of the leaf test
+            preceding the child's t2 > 0 test, cell/ppu_renderer.cpp:20-33; eye inside: demo/Demo.cpp:95)
+  config 4  1920x1080 over the depth-12 sphere fractal, primary + shadow + 4 AO rays: the WHOLE frame — pixels, hit ids,
+            t bits and the per-pixel node-visit counts
+  config 5  7680x4320 flythrough frames of the iso volume through ONE renderer handle over several members (every GPU of
+            the box, or the same GPU listed twice on a one-GPU box): bands against the oracle, whole frame against the
+            single-member render
+Sizes are the stated ones; what is sampled is the set of rows handed to the CPU oracle (a full 8K oracle frame is
+~3 s per camera on 16 cores, the bands keep the file under a minute)."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+import scenes
+import yvo
+import yoxel_voxel_b200 as yv
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_spec = importlib.util.spec_from_file_location("yv_bench", os.path.join(ROOT, "bench.py"))
+bench = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(bench)
+
+ISO_DEPTH = 12
+UP, FOV = bench.UP, bench.FOV
+
+
+@pytest.fixture(scope="module")
+def iso():
+    return yv.SVOData.IsoVolume(ISO_DEPTH, seed=219, iso_level=200, threads=os.cpu_count() or 8)
+
+
+def _bands(H, n=6, rows=16):
+    step = max(rows, H // n)
+    return [(y, min(H, y + rows)) for y in range(8, H - rows, step)]
+
+
+def _check_bands(svo, nodes, pos, d, W, H, img, node, child, t, tag, want_hits=True):
+    cam = yvo.camera(pos, d, UP, FOV, W, H)
+    hits = 0
+    for (y0, y1) in _bands(H):
+        o = yvo.render(nodes, svo.GetRoot(), cam, threads=os.cpu_count() or 8, rows=(y0, y1))
+        assert (img[y0:y1] == o["rgba"][y0:y1]).all(), "%s rows %d..%d: rgba differs" % (tag, y0, y1)
+        if node is not None:
+            assert (node[y0:y1] == o["node"][y0:y1]).all(), "%s rows %d..%d: hit node ids differ" % (tag, y0, y1)
+            assert (child[y0:y1] == o["child"][y0:y1]).all(), "%s rows %d..%d: hit child ids differ" % (tag, y0, y1)
+            assert t[y0:y1].tobytes() == o["t"][y0:y1].tobytes(), "%s rows %d..%d: t bits differ" % (tag, y0, y1)
+        hits += int((o["node"][y0:y1] != yv.MISS_NODE).sum())
+    if want_hits:
+        assert hits > 1000, "%s: the sampled bands see almost nothing (%d hits)" % (tag, hits)
+    return hits
+
+
+def test_config3_iso_volume_4k_fixed_and_flythrough_cameras(iso):
+    W, H = 3840, 2160
+    r = yv.SVORenderer(0)
+    try:
+        r.EnableHits(True)
+        r.SetScene(iso)
+        r.SetResolution(W, H)
+        r.SetViewUp(UP); r.SetFOV(FOV)
+        nodes = iso.nodes(copy=False)
+        inside = 0
+        frames = [0, 7, 19, 31, 44, 58]                       # frame 0 = the fixed config-3 camera
+        for f in frames:
+            pos, d = bench.camera_for(f, "iso")
+            if f:
+                assert all(0.0 < c < 1.0 for c in pos)        # the flythrough eye is inside the unit cube
+                inside += 1
+            r.SetViewPos(pos); r.SetViewDir(d)
+            img = r.RenderFrame().copy()
+            node, child, t = r.GetHits()
+            _check_bands(iso, nodes, pos, d, W, H, img, node, child, t, "config3/frame%d" % f)
+        assert inside >= 4
+    finally:
+        r.close()
+
+
+def test_eye_inside_a_straddling_node_reports_leaves_behind_it(iso):
+    """The quirk the flythrough cameras exercise, made explicit: with the eye inside the volume some rays report a leaf
+    whose own interval lies behind the origin (t < 0) — the oracle does (cell/ppu_renderer.cpp:27-33 tests the leaf
+    flag before the child's t2 > 0), so must the kernel, bit for bit. Eye placed just under the terrain surface."""
+    W, H = 1920, 1080
+    r = yv.SVORenderer(0)
+    try:
+        r.EnableHits(True)
+        r.SetScene(iso)
+        r.SetResolution(W, H)
+        r.SetViewUp(UP); r.SetFOV(FOV)
+        nodes = iso.nodes(copy=False)
+        neg = 0
+        for pos, d in (((0.31, 0.42, 0.18), (0.5, 0.6, 0.62)), ((0.52, 0.47, 0.21), (0.2, -1.0, 0.3)), ((0.7, 0.3, 0.25), (-0.6, 0.5, 0.1))):
+            r.SetViewPos(pos); r.SetViewDir(d)
+            img = r.RenderFrame().copy()
+            node, child, t = r.GetHits()
+            _check_bands(iso, nodes, pos, d, W, H, img, node, child, t, "inside%s" % (pos,), want_hits=False)
+            neg += int(((t < 0) & (node != yv.MISS_NODE)).sum())
+        assert neg > 0, "no ray reported a leaf behind the eye: the quirk is not exercised"
+    finally:
+        r.close()
+
+
+def test_config4_full_frame_1080p_depth12_shadow_and_ao():
+    W, H = 1920, 1080
+    svo = scenes.fractal(12)
+    sec = dict(voxel_size=1.0 / 4096, **bench.SEC_ARGS)
+    r = yv.SVORenderer(0)
+    try:
+        r.EnableHits(True)
+        r.EnableCounters(True)
+        r.SetScene(svo)
+        r.SetResolution(W, H)
+        r.SetViewUp(UP); r.SetFOV(FOV)
+        r.SetViewPos(bench.BASE_POS); r.SetViewDir(bench.BASE_DIR)
+        r.SetSecondary(**sec)
+        img = r.RenderFrame().copy()
+        node, child, t = r.GetHits()
+        visits, _ = r.GetCounters()
+        o = yvo.render(svo.nodes(copy=False), svo.GetRoot(), yvo.camera(bench.BASE_POS, bench.BASE_DIR, UP, FOV, W, H),
+                       sec=yvo.secondary(**sec), threads=os.cpu_count() or 8, want_visits=True)
+        assert (node == o["node"]).all() and (child == o["child"]).all()
+        assert t.tobytes() == o["t"].tobytes()
+        assert (img == o["rgba"]).all(), "%d pixels differ" % int((img != o["rgba"]).any(axis=2).sum())
+        assert (visits == o["visits"]).all(), "node visits differ in %d pixels" % int((visits != o["visits"]).sum())
+        hit = int((node != yv.MISS_NODE).sum())
+        assert o["stats"]["rays"] == W * H + 5 * hit and hit > W * H // 3
+    finally:
+        r.close()
+
+
+def _group_devices():
+    n = yv.device_count()
+    return list(range(min(n, 8))) if n >= 2 else [0, 0]
+
+
+def test_config5_8k_flythrough_frames_through_one_handle(iso):
+    W, H = 7680, 4320
+    devs = _group_devices()
+    single = yv.SVORenderer(0)
+    group = yv.SVORenderer(devices=devs)
+    try:
+        nodes = iso.nodes(copy=False)
+        for r in (single, group):
+            r.SetScene(iso)
+            r.SetResolution(W, H)
+            r.SetViewUp(UP); r.SetFOV(FOV)
+        group.SetPartition("interleaved", 32)
+        for f in (5, 37):
+            pos, d = bench.camera_for(f, "iso")
+            for r in (single, group):
+                r.SetViewPos(pos); r.SetViewDir(d)
+            a = single.RenderFrame().copy()
+            b = group.RenderFrame()
+            assert (a == b).all(), "frame %d: the %d-member frame differs from the single-GPU frame" % (f, len(devs))
+            _check_bands(iso, nodes, pos, d, W, H, b, None, None, None, "config5/frame%d" % f)
+        # frames in flight deliver the same pixels
+        pos, d = bench.camera_for(37, "iso")
+        group.SetViewPos(pos); group.SetViewDir(d)
+        tk = group.RenderFrameAsync()
+        c = group.WaitFrame(tk)
+        assert (c == a).all()
+    finally:
+        group.close()
+        single.close()

@@ -402,7 +402,17 @@ inline uint32_t mix32(uint32_t x) { x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15
 // aligned sub-cube are attained at the sub-cube's corners: corner evaluation gives exact bounds.
 class IsoSource {
  public:
-  struct Ctx {};
+  // Per-cube context: the field at the cube's 8 corners once the cube is small enough for corner evaluation to be exact,
+  // and — filled in when its first child is classified — at the 27 points of its 3x3x3 half-size lattice, so that the
+  // eight children share their corners (19 new field evaluations per cube instead of 64). The field is a pure function
+  // of the integer lattice point, so the tree is the one the unshared evaluation built.
+  struct Ctx {
+    int x = 0, y = 0, z = 0, size = 0;
+    bool have8 = false;
+    mutable bool have27 = false;
+    float c8[8];
+    mutable float g27[27];
+  };
   IsoSource(int depth, uint32_t seed, int iso) : depth_(depth), n_(1 << depth), iso_((float)iso / 255.0f) {
     zmax_ = (n_ * 5) / 16;                       // slab: 640/2048 of the cube (gen_largevol.py:8-9: 5 of 16 brick layers)
     if (zmax_ < 2) zmax_ = std::min(n_, 2);
@@ -466,17 +476,32 @@ class IsoSource {
     return (float)f;
   }
 
-  RangeClass classify(const Ctx &, int x, int y, int z, int size, Ctx &, uint32_t &vox) const {
+  RangeClass classify(const Ctx &parent, int x, int y, int z, int size, Ctx &ctx, uint32_t &vox) const {
+    ctx.x = x; ctx.y = y; ctx.z = z; ctx.size = size; ctx.have8 = false; ctx.have27 = false;
     if (z >= zmax_) return RangeClass::Empty;
     float lo, hi;
     bool exact = true;
     for (const Octave &oc : oct_) if (size > n_ / oc.cells) exact = false;
     if (exact && z + size <= zmax_) {
       lo = 1e30f; hi = -1e30f;
-      for (int d = 0; d < 8; ++d) {
-        float v = field(x + ((d & 1) ? size : 0), y + ((d & 2) ? size : 0), z + ((d & 4) ? size : 0));
-        lo = std::min(lo, v); hi = std::max(hi, v);
+      if (parent.have8 && parent.size == 2 * size) {
+        if (!parent.have27) {                                    // the parent's 3x3x3 lattice, its own corners reused
+          for (int k = 0; k < 3; ++k) for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) {
+            float &g = parent.g27[(k * 3 + j) * 3 + i];
+            if (i != 1 && j != 1 && k != 1) g = parent.c8[(i >> 1) | ((j >> 1) << 1) | ((k >> 1) << 2)];
+            else g = field(parent.x + i * size, parent.y + j * size, parent.z + k * size);
+          }
+          parent.have27 = true;
+        }
+        const int ox = (x - parent.x) / size, oy = (y - parent.y) / size, oz = (z - parent.z) / size;
+        for (int d = 0; d < 8; ++d)
+          ctx.c8[d] = parent.g27[((oz + ((d >> 2) & 1)) * 3 + (oy + ((d >> 1) & 1))) * 3 + (ox + (d & 1))];
+      } else {
+        for (int d = 0; d < 8; ++d)
+          ctx.c8[d] = field(x + ((d & 1) ? size : 0), y + ((d & 2) ? size : 0), z + ((d & 4) ? size : 0));
       }
+      ctx.have8 = true;
+      for (int d = 0; d < 8; ++d) { lo = std::min(lo, ctx.c8[d]); hi = std::max(hi, ctx.c8[d]); }
     } else {
       double nlo = 0, nhi = 0;
       for (const Octave &oc : oct_) {

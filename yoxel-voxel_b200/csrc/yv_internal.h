@@ -156,7 +156,8 @@ struct yv_renderer {
   cudaEvent_t ev_join = nullptr;      // on a peer: its share of the frame (and its copy) is done
   cudaEvent_t ev_own0 = nullptr, ev_own1 = nullptr;   // device time of this member's own share of the last group frame
   bool own_timed = false;
-  double replicate_ms = 0.0;          // wall time of the last pool replication over peer copies
+  double replicate_ms = 0.0;          // wall time of the last pool replication: the concurrent peer copies alone
+  double replicate_alloc_ms = 0.0;    // ... and of the allocations on the peers that preceded them
   uint64_t replicate_bytes = 0;
   // ---- frames in flight -----------------------------------------------------------------------------------------
   static constexpr int kSlots = 4;

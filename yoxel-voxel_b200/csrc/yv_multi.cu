@@ -60,27 +60,40 @@ void copy_state(const yv_renderer *lead, yv_renderer *m) {
 }
 
 // Copy the packed pool of `svo` from src_dev to dst_dev with peer copies, asynchronously on `st` (a stream of dst_dev).
-int replicate_packed_async(yv_svo *svo, int src_dev, int dst_dev, cudaStream_t st, uint64_t *bytes) {
+// Two steps so that a group can allocate on every peer first and then run (and time) all the copies concurrently:
+// replicate_alloc returns 1 when a copy is needed, 0 when dst already holds this version.
+int replicate_alloc(yv_svo *svo, int src_dev, int dst_dev, bool *needed) {
   std::lock_guard<std::mutex> lock(svo->mu);
+  *needed = false;
   auto it = svo->dev.find(src_dev);
   if (it == svo->dev.end() || !it->second.recs) return fail(YV_ERR_ARG, "replicate: the scene is not resident on the source device");
   const DeviceSVO src = it->second;
   DeviceSVO &d = svo->dev[dst_dev];
-  if (d.recs && d.packed_version == src.packed_version && d.n_recs == src.n_recs) { if (bytes) *bytes = 0; return YV_OK; }
+  if (d.recs && d.packed_version == src.packed_version && d.n_recs == src.n_recs) return YV_OK;
   YV_CUDA(cudaSetDevice(dst_dev));
   YV_CUDA(cudaDeviceSynchronize());                          // nothing still reads the copy that is replaced
   cudaFree(d.recs); cudaFree(d.info); cudaFree(d.leaves); cudaFree(d.node_data);
   d.recs = nullptr; d.info = nullptr; d.leaves = nullptr; d.node_data = nullptr;
+  d.packed_version = 0; d.n_recs = 0;
   const size_t rb = std::max<size_t>(1, src.n_recs) * sizeof(uint4), lb = std::max<size_t>(1, src.n_leaves) * sizeof(uint32_t);
   YV_CUDA(cudaMalloc(&d.recs, rb));
   YV_CUDA(cudaMalloc(&d.info, std::max<size_t>(1, src.n_recs) * sizeof(uint2)));
   YV_CUDA(cudaMalloc(&d.leaves, lb));
+  if (src.node_data && src.n_recs) YV_CUDA(cudaMalloc(&d.node_data, src.n_recs * sizeof(uint32_t)));
+  *needed = true;
+  return YV_OK;
+}
+
+int replicate_copy_async(yv_svo *svo, int src_dev, int dst_dev, cudaStream_t st, uint64_t *bytes) {
+  std::lock_guard<std::mutex> lock(svo->mu);
+  const DeviceSVO src = svo->dev[src_dev];
+  DeviceSVO &d = svo->dev[dst_dev];
+  YV_CUDA(cudaSetDevice(dst_dev));
   uint64_t moved = 0;
   if (src.n_recs) { YV_CUDA(cudaMemcpyPeerAsync(d.recs, dst_dev, src.recs, src_dev, src.n_recs * sizeof(uint4), st)); moved += src.n_recs * sizeof(uint4); }
   if (src.n_recs) { YV_CUDA(cudaMemcpyPeerAsync(d.info, dst_dev, src.info, src_dev, src.n_recs * sizeof(uint2), st)); moved += src.n_recs * sizeof(uint2); }
   if (src.n_leaves) { YV_CUDA(cudaMemcpyPeerAsync(d.leaves, dst_dev, src.leaves, src_dev, src.n_leaves * sizeof(uint32_t), st)); moved += src.n_leaves * sizeof(uint32_t); }
-  if (src.node_data && src.n_recs) {
-    YV_CUDA(cudaMalloc(&d.node_data, src.n_recs * sizeof(uint32_t)));
+  if (d.node_data && src.node_data && src.n_recs) {
     YV_CUDA(cudaMemcpyPeerAsync(d.node_data, dst_dev, src.node_data, src_dev, src.n_recs * sizeof(uint32_t), st));
     moved += src.n_recs * sizeof(uint32_t);
   }
@@ -100,19 +113,33 @@ int group_prepare(yv_renderer *r, bool need_local_fb) {
     DeviceSVO *d0 = nullptr;
     int rc = ensure_uploaded(r->svo, r->device, &d0);
     if (rc) return rc;
-    bool any = false;
-    uint64_t total = 0;
-    const auto t0 = std::chrono::steady_clock::now();
+    // allocate on every peer, then run all the peer copies concurrently (every destination pulls over its own NVLink
+    // ports through the switch) and time just them
+    std::vector<yv_renderer *> todo;
+    const auto ta = std::chrono::steady_clock::now();
     for (yv_renderer *p : r->peers) {
-      uint64_t b = 0;
       if (p->device == r->device) continue;
-      rc = replicate_packed_async(r->svo, r->device, p->device, p->own_stream, &b);
+      bool dup = false;
+      for (yv_renderer *q : todo) dup = dup || q->device == p->device;
+      if (dup) continue;
+      bool needed = false;
+      rc = replicate_alloc(r->svo, r->device, p->device, &needed);
       if (rc) return rc;
-      any = any || b != 0; total += b;
+      if (needed) todo.push_back(p);
     }
-    if (any) {
-      for (yv_renderer *p : r->peers) { YV_CUDA(cudaSetDevice(p->device)); YV_CUDA(cudaStreamSynchronize(p->own_stream)); }
-      r->replicate_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (!todo.empty()) {
+      uint64_t total = 0;
+      const auto t0 = std::chrono::steady_clock::now();
+      for (yv_renderer *p : todo) {
+        uint64_t b = 0;
+        rc = replicate_copy_async(r->svo, r->device, p->device, p->own_stream, &b);
+        if (rc) return rc;
+        total += b;
+      }
+      for (yv_renderer *p : todo) { YV_CUDA(cudaSetDevice(p->device)); YV_CUDA(cudaStreamSynchronize(p->own_stream)); }
+      const auto t1 = std::chrono::steady_clock::now();
+      r->replicate_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+      r->replicate_alloc_ms = std::chrono::duration<double, std::milli>(t0 - ta).count();
       r->replicate_bytes = total;
     }
   }
@@ -380,8 +407,10 @@ int yv_svo_replicate(yv_svo *svo, int src_device, int dst_device) {
     int can = 0;
     cudaDeviceCanAccessPeer(&can, dst_device, src_device);
     if (can) { cudaDeviceEnablePeerAccess(src_device, 0); cudaGetLastError(); }     // without it the copy is staged through the host
-    rc = replicate_packed_async(svo, src_device, dst_device, nullptr, nullptr);
+    bool needed = false;
+    rc = replicate_alloc(svo, src_device, dst_device, &needed);
     if (rc) return rc;
+    if (needed) { rc = replicate_copy_async(svo, src_device, dst_device, nullptr, nullptr); if (rc) return rc; }
     YV_CUDA(cudaSetDevice(dst_device));
     YV_CUDA(cudaDeviceSynchronize());
     return YV_OK;
