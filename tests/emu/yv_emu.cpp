@@ -78,7 +78,7 @@ bool trace(const Fetch &fetch, bool root_valid, HostStack &stk, float ox, float 
       if (r == kStepMiss) return false;
       g_lod_hit = r == kStepLodHit;
       // present the result through the classic state the caller reads
-      s.t1x = ls.t1x; s.t1y = ls.t1y; s.t1z = ls.t1z; s.ch = ls.ch; s.flags = ls.flags; s.idx = ls.idx;
+      s.t1x = lean_t1x(ls); s.t1y = lean_t1y(ls); s.t1z = lean_t1z(ls); s.ch = lean_ch(ls); s.flags = ls.flags; s.idx = ls.idx;
       rec = fetch.recs[ls.idx];
       return true;
     }

@@ -15,7 +15,7 @@ def lib():
     if _lib is None:
         d = os.path.join(ROOT, "tests", "emu")
         subprocess.check_call(["make", "-s", "-C", d])
-        L = C.CDLL(os.path.join(d, "libyv_emu.so"))
+        L = C.CDLL(os.path.join(d, "libyv_emu%s.so" % os.environ.get("YVE_VARIANT", "")))
         vp, f3 = C.c_void_p, C.POINTER(C.c_float)
         L.yve_render.argtypes = [vp, vp, C.c_int, f3, f3, f3, f3, f3, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_uint32, C.c_float, C.c_float, vp, vp, vp, vp,

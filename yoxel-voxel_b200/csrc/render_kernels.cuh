@@ -120,6 +120,28 @@ struct LocalStack {
   __device__ __forceinline__ void pop(int sp, U4 &a, U4 &b) { a = to_u4(w[2 * sp]); b = to_u4(w[2 * sp + 1]); }
 };
 
+// YV_STACK_TOP (build-time variant, measured in profiles/README.md round 2): the newest entry stays in registers; it
+// is written to local memory only when another push follows, so a push that is popped again before the next push
+// (a child visit that finds nothing, 31 % of the visits on config 2) touches no memory at all.
+#ifndef YV_STACK_TOP
+#define YV_STACK_TOP 0
+#endif
+struct LocalStackTop {
+  uint4 w[2 * kMaxStack];
+  uint4 ta, tb;
+  bool has;
+  __device__ __forceinline__ LocalStackTop(uint4 *) : has(false) {}
+  __device__ __forceinline__ void reset() { has = false; }
+  __device__ __forceinline__ void push(int sp, const U4 &a, const U4 &b) {
+    if (has) { w[2 * (sp - 1)] = ta; w[2 * (sp - 1) + 1] = tb; }
+    ta = to_uint4(a); tb = to_uint4(b); has = true;
+  }
+  __device__ __forceinline__ void pop(int sp, U4 &a, U4 &b) {
+    if (has) { a = to_u4(ta); b = to_u4(tb); has = false; }
+    else { a = to_u4(w[2 * sp]); b = to_u4(w[2 * sp + 1]); }
+  }
+};
+
 // the K most recent entries in shared memory ([slot][half][thread]: a warp's 128-bit accesses never
 // bank-conflict), older ones spilled to local memory
 template <int K>
@@ -147,7 +169,11 @@ struct RingStack {
   }
 };
 
+#if YV_STACK_TOP
+template <int STACK> struct StackOf { using type = LocalStackTop; };
+#else
 template <int STACK> struct StackOf { using type = LocalStack; };
+#endif
 template <> struct StackOf<kStackRing4> { using type = RingStack<4>; };
 
 // shared-memory bytes the stack variant needs per CTA of `threads` threads
@@ -363,9 +389,9 @@ __global__ void __launch_bounds__(kFrameCta, kFrameMinBlocks) render_frame(const
       if (!SEC || stage == 0) {
         uint32_t hn = YV_MISS_NODE; int32_t hc = YV_MISS_CHILD; float ht = 0.0f;
         if (hit) {
-          const uint32_t c = s.ch ^ s.flags;
+          const uint32_t c = lean_ch(s) ^ s.flags;
           fetch.hit_info(p.leaves, p.node_data, s.idx, c, s.masks, lod_hit, hn, sdata);
-          hc = lod_hit ? -1 : (int32_t)c; ht = max3f(s.t1x, s.t1y, s.t1z);
+          hc = lod_hit ? -1 : (int32_t)c; ht = lean_hit_t(s);
           unpack_normal(sdata, nx, ny, nz);
           float dx, dy, dz;                                       // the primary direction, recomputed
           primary_dir(p.dir0, p.du, p.dv, x, y, dx, dy, dz);
@@ -390,7 +416,7 @@ __global__ void __launch_bounds__(kFrameCta, kFrameMinBlocks) render_frame(const
         if (!SEC && p.shade_rec && hit) p.shade_rec[pixel] = make_uint2(sdata, __float_as_uint(ht));
       } else {
         // a secondary ray came back
-        const float ts = max3f(s.t1x, s.t1y, s.t1z);
+        const float ts = lean_hit_t(s);
         if (stage == 1) { if (hit && ts > 0 && ts < slen) vis = 0.0f; }
         else if (hit && ts > 0 && ts < p.ao_max_t) ++occ;
         done = false;
@@ -528,7 +554,7 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_queue(const 
         s.t1z = __uint_as_float(slots[2 * kQueueRays + cur]); s.Tx = __uint_as_float(slots[3 * kQueueRays + cur]);
         s.Ty = __uint_as_float(slots[4 * kQueueRays + cur]);  s.Tz = __uint_as_float(slots[5 * kQueueRays + cur]);
         const uint32_t w = slots[6 * kQueueRays + cur];
-        s.ch = w & 7u; s.flags = w >> 3; s.idx = 0u; s.sp = 0; s.pend = 0u; s.tlimit = __builtin_huge_valf();
+        s.ch = w & 7u; s.flags = w >> 3; s.idx = 0u; s.sp = 0; s.pend = 0u; s.st = 0u; s.tlimit = __builtin_huge_valf();
         s.masks = root_masks; s.child_base = root_child_base;
         stk.reset();
         lean_eval_next(s);
@@ -544,8 +570,8 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_queue(const 
         if (r != kStepContinue) {
           const bool hit = r == kStepHit;
           slots[0 * kQueueRays + cur] = hit ? s.idx : 0xffffffffu;
-          slots[1 * kQueueRays + cur] = s.ch ^ s.flags;
-          slots[2 * kQueueRays + cur] = __float_as_uint(max3f(s.t1x, s.t1y, s.t1z));
+          slots[1 * kQueueRays + cur] = lean_ch(s) ^ s.flags;
+          slots[2 * kQueueRays + cur] = __float_as_uint(lean_hit_t(s));
           if (COUNT) slots[7 * kQueueRays + cur] = (fetch.visits & 0xffffu) | (fetch.revisits << 16);
           cur = -1;
         }
@@ -659,9 +685,9 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_sec_queue(co
   uint32_t sdata = 0u, hn = YV_MISS_NODE; int32_t hc = YV_MISS_CHILD; float ht = 0.0f;
   float nx = 0.f, ny = 0.f, nz = 0.f, Ox = 0.f, Oy = 0.f, Oz = 0.f, dl = 0.f, vis = 1.0f;
   if (hit) {
-    const uint32_t c = s.ch ^ s.flags;
+    const uint32_t c = lean_ch(s) ^ s.flags;
     fetch.hit_info(p.leaves, p.node_data, s.idx, c, s.masks, lod_hit, hn, sdata);
-    hc = lod_hit ? -1 : (int32_t)c; ht = max3f(s.t1x, s.t1y, s.t1z);
+    hc = lod_hit ? -1 : (int32_t)c; ht = lean_hit_t(s);
     unpack_normal(sdata, nx, ny, nz);
     float dx, dy, dz;
     primary_dir(p.dir0, p.du, p.dv, x, y, dx, dy, dz);
@@ -689,7 +715,7 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_sec_queue(co
   }
   run_lockstep(true);
   if (state == kLaneHit || (LOD && state == kLaneLodHit)) {
-    const float ts = max3f(s.t1x, s.t1y, s.t1z);
+    const float ts = lean_hit_t(s);
     if (ts > 0 && ts < slen) vis = 0.0f;
   }
 
@@ -737,7 +763,7 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_sec_queue(co
             s.t1x = __uint_as_float(slots[0 * kAoQueueRays + slot]); s.t1y = __uint_as_float(slots[1 * kAoQueueRays + slot]);
             s.t1z = __uint_as_float(slots[2 * kAoQueueRays + slot]); s.Tx = __uint_as_float(slots[3 * kAoQueueRays + slot]);
             s.Ty = __uint_as_float(slots[4 * kAoQueueRays + slot]);  s.Tz = __uint_as_float(slots[5 * kAoQueueRays + slot]);
-            s.ch = w & 7u; s.flags = (w >> 3) & 7u; s.idx = 0u; s.sp = 0; s.pend = 0u; s.level = 0u; s.tlimit = p.ao_max_t;
+            s.ch = w & 7u; s.flags = (w >> 3) & 7u; s.idx = 0u; s.sp = 0; s.pend = 0u; s.st = 0u; s.level = 0u; s.tlimit = p.ao_max_t;
             s.masks = root_masks; s.child_base = root_child_base;
             lean_eval_next(s);
             if (COUNT) { atomicAdd(&vis_cnt[owner], 1u); }
@@ -754,7 +780,7 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_sec_queue(co
           if (COUNT) { const uint32_t dv = fetch.visits - v0, dr = fetch.revisits - r0; if (dv | dr) atomicAdd(&vis_cnt[owner], dv | (dr << 16)); }
           if (r != kStepContinue) {
             if (r != kStepMiss) {
-              const float ts = max3f(s.t1x, s.t1y, s.t1z);
+              const float ts = lean_hit_t(s);
               if (ts > 0 && ts < p.ao_max_t) atomicAdd(&occ_cnt[owner], 1u);
             }
             cur = -1;
@@ -950,10 +976,10 @@ __global__ void __launch_bounds__(128) trace_rays_kernel(const uint4 *recs, cons
     }
   }
   uint32_t hn = YV_MISS_NODE, data;
-  if (hit) fetch.hit_info(leaves, nullptr, s.idx, s.ch ^ s.flags, s.masks, false, hn, data);
+  if (hit) fetch.hit_info(leaves, nullptr, s.idx, lean_ch(s) ^ s.flags, s.masks, false, hn, data);
   node[i] = hn;
-  child[i] = hit ? (int32_t)(s.ch ^ s.flags) : YV_MISS_CHILD;
-  t[i] = hit ? max3f(s.t1x, s.t1y, s.t1z) : 0.0f;
+  child[i] = hit ? (int32_t)(lean_ch(s) ^ s.flags) : YV_MISS_CHILD;
+  t[i] = hit ? lean_hit_t(s) : 0.0f;
 }
 
 }  // namespace yv

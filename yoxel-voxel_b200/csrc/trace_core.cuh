@@ -180,6 +180,7 @@ struct LeanState {
   uint32_t masks, child_base;
   uint32_t gm_lo, gm_hi; // octant occupancy of the current node's eight children (byte c = child c), culling fetch policies only
   uint32_t pend;         // exit axis (one-hot) of a sibling step chosen but not yet applied; 0 = none
+  uint32_t st;           // YV_LEAN_ABC: axes (one-hot, or-ed) stepped inside the current node; 0 otherwise
   uint32_t level;        // depth of the current node (root = 0); only maintained when LOD is on
   float tlimit;          // secondary rays: nothing at or beyond this ray parameter matters (shadow: distance to
                          // the light, AO: ao_max_t); cells are met in non-decreasing entry parameter, so the ray
@@ -198,6 +199,28 @@ YV_HD float yv_u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 #define YV_F2U(f) yv_f2u(f)
 #define YV_U2F(u) yv_u2f(u)
 #endif
+
+// YV_LEAN_ABC (build-time variant, measured in profiles/README.md round 2): a sibling step moves values, it computes
+// nothing — t1 <- T, T <- N on the stepped axis, and an axis is stepped at most once per node. So instead of moving
+// them (six selects per step), the three values an axis has at node entry stay where they are, A = t1, B = T,
+// C = N = B + (B - A), and a 3-bit mask `st` says which axes have been stepped: the current interval of an axis is
+// (A, B) before its step and (B, C) after. The exit parameters for the argmin are three selects, the entry parameters
+// are selected only where they are used (descent, hit, range limit), and a stack entry is (A, B, ch, st).
+#ifndef YV_LEAN_ABC
+#define YV_LEAN_ABC 0
+#endif
+
+// entry parameters of the current child cube / its logical child index, whatever the representation
+YV_HD float lean_t1x(const LeanState &s) { return (YV_LEAN_ABC && (s.st & 1u)) ? s.Tx : s.t1x; }
+YV_HD float lean_t1y(const LeanState &s) { return (YV_LEAN_ABC && (s.st & 2u)) ? s.Ty : s.t1y; }
+YV_HD float lean_t1z(const LeanState &s) { return (YV_LEAN_ABC && (s.st & 4u)) ? s.Tz : s.t1z; }
+YV_HD uint32_t lean_ch(const LeanState &s) { return YV_LEAN_ABC ? (s.ch | s.st) : s.ch; }
+// hit distance t = maxCoord(t1) in the reference's a > b ? a : b form (stored, so no FMNMX)
+YV_HD float lean_hit_t(const LeanState &s) {
+  const float a = lean_t1x(s), b = lean_t1y(s), c = lean_t1z(s);
+  const float m = a > b ? a : b;
+  return m > c ? m : c;
+}
 
 YV_HD void lean_eval_next(LeanState &s) {
   s.Nx = YV_FADD(s.Tx, YV_FSUB(s.Tx, s.t1x));
@@ -278,7 +301,7 @@ YV_HD bool lean_setup_root(LeanState &s, const bool root_valid,
   if (!setup_trace(px, py, pz, dx, dy, dz, r)) return false;
   if (!root_valid || fminf(fminf(r.t2x, r.t2y), r.t2z) <= 0.0f) return false;
   s.t1x = r.t1x; s.t1y = r.t1y; s.t1z = r.t1z; s.Tx = r.t2x; s.Ty = r.t2y; s.Tz = r.t2z;
-  s.flags = r.flags; s.sp = 0; s.idx = 0u; s.pend = 0u; s.level = 0u; s.tlimit = __builtin_huge_valf();
+  s.flags = r.flags; s.sp = 0; s.idx = 0u; s.pend = 0u; s.st = 0u; s.level = 0u; s.tlimit = __builtin_huge_valf();
   lean_first_child(s);
   return true;
 }
@@ -315,6 +338,75 @@ enum : int { kStepLodHit = 3 };
 // levels and treats a child node below level kMaxStack as empty, so neither a pool deeper than the explicit stack
 // nor a cyclic one can run the stack over or keep a ray descending for ever. (The packed layout is depth-checked
 // when it is made.)
+#if YV_LEAN_ABC
+template <bool LOD, class Fetch, class Stack>
+YV_HD int lean_step(LeanState &s, const Fetch &fetch, Stack &stk, const bool front_only, const float detail = 0.0f) {
+  constexpr bool GUARD = FetchTraits<Fetch>::kGuardDepth;
+  // (no culling form: a kCull policy is traversed as the reference traversal in this variant)
+  constexpr bool LEVELS = LOD || GUARD;
+  uint32_t bit, e, chc;
+  bool descend, can_adv;
+  float Tx, Ty, Tz;
+#pragma unroll
+  for (int k = 0;; ++k) {
+    s.st |= s.pend;                                                // deferred GoNext: mark the axis, move nothing
+    s.pend = 0u;
+    const bool px = (s.st & 1u) != 0u, py = (s.st & 2u) != 0u, pz = (s.st & 4u) != 0u;
+    Tx = px ? s.Nx : s.Tx; Ty = py ? s.Ny : s.Ty; Tz = pz ? s.Nz : s.Tz;
+    if (front_only && fmaxf(fmaxf(px ? s.Tx : s.t1x, py ? s.Ty : s.t1y), pz ? s.Tz : s.t1z) >= s.tlimit) return kStepMiss;
+    chc = s.ch | s.st;
+    bit = 1u << (chc ^ s.flags);
+    const bool xy = Tx > Ty;
+    const bool nz = xy ? (Ty < Tz) : (Tx < Tz);
+    e = nz ? (xy ? 2u : 1u) : 4u;                                  // argmin(t2), one-hot, the reference's tie order
+    const float tmin = fminf(fminf(Tx, Ty), Tz);                   // compared only
+    if (((s.masks & bit) != 0u) && (!front_only || tmin > 0.0f)) return kStepHit;           // :27
+    descend = (((s.masks >> 8) & bit) != 0u) && (tmin > 0.0f);                               // :20,:35
+    if (GUARD) descend = descend && s.level < (uint32_t)kMaxStack;
+    can_adv = (chc & e) == 0u;                                                               // :38
+    if (LOD) {
+      const float tent = fmaxf(fmaxf(px ? s.Tx : s.t1x, py ? s.Ty : s.t1y), pz ? s.Tz : s.t1z);
+      const float lodk = YV_U2F(YV_F2U(detail) + ((s.level + 1u) << 23));
+      if (descend && tent > 0.0f && YV_FMUL(tent, lodk) > 1.0f) {
+        s.idx = fetch.child_index(s.idx, s.child_base, s.masks, chc ^ s.flags);
+        return kStepLodHit;
+      }
+    }
+    if (descend || !can_adv) break;
+    s.pend = e;
+    if (k + 1 == YV_STEPS_PER_CALL) return kStepContinue;
+  }
+
+  if (descend) {
+    if (can_adv) {
+      const U4 a = { YV_F2U(s.t1x), YV_F2U(s.t1y), YV_F2U(s.t1z), s.idx };
+      const U4 b = { YV_F2U(s.Tx), YV_F2U(s.Ty), YV_F2U(s.Tz), s.ch | (e << 3) | (s.st << 6) | (LEVELS ? (s.level << 9) : 0u) };
+      stk.push(s.sp, a, b);
+      ++s.sp;
+    }
+    s.idx = fetch.child_index(s.idx, s.child_base, s.masks, chc ^ s.flags);
+    if (LEVELS) ++s.level;
+    // the child's own interval becomes (t1, T); FindFirstChild narrows it below
+    const bool px = (s.st & 1u) != 0u, py = (s.st & 2u) != 0u, pz = (s.st & 4u) != 0u;
+    s.t1x = px ? s.Tx : s.t1x; s.t1y = py ? s.Ty : s.t1y; s.t1z = pz ? s.Tz : s.t1z;
+    s.Tx = Tx; s.Ty = Ty; s.Tz = Tz;
+    s.st = 0u;
+  } else {
+    if (s.sp == 0) return kStepMiss;
+    --s.sp;
+    U4 a, b;
+    stk.pop(s.sp, a, b);
+    s.t1x = YV_U2F(a.x); s.t1y = YV_U2F(a.y); s.t1z = YV_U2F(a.z); s.idx = a.w;
+    s.Tx = YV_U2F(b.x); s.Ty = YV_U2F(b.y); s.Tz = YV_U2F(b.z);
+    s.ch = b.w & 7u; s.pend = (b.w >> 3) & 7u; s.st = (b.w >> 6) & 7u;       // the parent's GoNext, applied next trip
+    if (LEVELS) s.level = b.w >> 9;
+  }
+  lean_load_node(s, fetch, descend);                                                         // :23
+  if (descend) lean_first_child(s);                                                          // :24
+  lean_eval_next(s);
+  return kStepContinue;
+}
+#else
 template <bool LOD, class Fetch, class Stack>
 YV_HD int lean_step(LeanState &s, const Fetch &fetch, Stack &stk, const bool front_only, const float detail = 0.0f) {
   constexpr bool GUARD = FetchTraits<Fetch>::kGuardDepth;
@@ -399,6 +491,7 @@ YV_HD int lean_step(LeanState &s, const Fetch &fetch, Stack &stk, const bool fro
   lean_eval_next(s);
   return kStepContinue;
 }
+#endif  // YV_LEAN_ABC
 
 // Entry test of RecTrace(root): the caller has run setup_trace. Returns false on an immediate miss.
 template <class Fetch>
