@@ -229,7 +229,13 @@ def test_gpu_ssna_device_render_and_partition_errors():
         dst = torch.zeros(H, W, 4, dtype=torch.uint8, device="cuda:0")
         renderer.Render(dst.data_ptr())                                 # SVORenderer::Render(void* d_dstBuf)
         assert np.array_equal(dst.cpu().numpy(), host)
-        assert renderer.LastFrameLaunches() == 8                        # trace + z + 5 x BlurZ + ShadeSimple
+        assert renderer.LastFrameLaunches() == 7                        # trace (writes z itself) + 5 x BlurZ + ShadeSimple
+        renderer.SetOption("persistent", 1)                             # a schedule without the z epilogue: ssna_z_pass runs
+        try:
+            assert np.array_equal(_gpu_frame(renderer, OUTSIDE, W, H), host)
+            assert renderer.LastFrameLaunches() == 8                    # trace + z + 5 x BlurZ + ShadeSimple
+        finally:
+            renderer.SetOption("persistent", 0)
         renderer.SetRows(0, H // 2)
         with pytest.raises(yv.YVError):
             renderer.RenderFrame()

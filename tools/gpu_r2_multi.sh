@@ -1,9 +1,10 @@
 #!/bin/bash
 # round 2: the single-handle multi-GPU renderer and the N>1 bench line on a box with >= 2 GPUs
 #   usage: tools/gpu_r2_multi.sh N [strong-depth]
-N=${1:-2}; SD=${2:-12}
+N=${1:-2}; SD=${2:-0}     # strong-depth 0 = what the driver gets: auto (14 if the host has the cores and memory)
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/topo_n$N.txt 2>&1
+nvidia-smi nvlink -gt d -i 0 > gpurun_out/nvlink_gt_n$N.txt 2>&1; nvidia-smi nvlink -s -i 0 >> gpurun_out/nvlink_gt_n$N.txt 2>&1
 echo "== pytest multi-device" ; timeout 900 python -m pytest tests/test_multi_device.py tests/test_multi_gpu.py -q -x -m gpu > gpurun_out/pytest_multi_n$N.log 2>&1 ; echo "rc=$?" ; tail -5 gpurun_out/pytest_multi_n$N.log
 echo "== bench N=$N (torchrun)" ; timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
     bench.py --gpus $N --steps 20 --warmup 5 --strong-depth $SD > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err ; echo "rc=$?"

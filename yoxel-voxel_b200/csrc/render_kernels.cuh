@@ -39,8 +39,8 @@
 namespace yv {
 
 struct RenderParams {
-  const uint4 *recs;           // packed records, device form (svo_pack.h): { child_base, masks, octants lo, octants hi }
-  const uint2 *info;           // { leaf_base, orig_id } per record, read by hits only
+  const uint4 *recs;           // packed records, device form (svo_pack.h): { child_base, masks, leaf_base, orig_id }
+  const uint2 *octs;           // { octants lo, octants hi } per record, read by the culling traversal only
   const uint32_t *leaves;      // inline VoxData words
   const uint32_t *node_data;   // VoxNode::data per record (LOD hits only; NULL when detail == 0)
   float detail;                // rp.detailCoef (demo/SVORenderer.cpp:104); 0 = no LOD cut-off
@@ -55,6 +55,8 @@ struct RenderParams {
   int band_rows8, band_stride, band_phase;   // interleaved partition: blocks of band_rows8*8 rows, this launch
                                              // renders blocks b with b % band_stride == band_phase (stride 1 = all)
   uint32_t *out_rgba;          // full-frame addressed: out_rgba[y*width + x]
+  uint32_t *final_rgba;        // frames with a ShadeSimple pass: where that pass writes (NULL = in place). Lets the trace
+                               // kernel draw in HBM while the pass that finishes the frame stores into a pinned host frame.
   uint32_t *hit_node;          // optional TraceResult planes (ppu_renderer.cpp:7-12); NULL = off
   int32_t *hit_child;
   float *hit_t;
@@ -84,6 +86,7 @@ struct BlurParams {
   float *dst;
   int width, height;
   float zlimit;
+  float wsum;                  // ((0 + w[0]) + w[1]) + ... over all K*K taps in row-major order: wacc of a pixel whose taps all pass
   float taps[YV_BLURZ_KERN * YV_BLURZ_KERN];
 };
 
@@ -101,7 +104,8 @@ constexpr int kFrameMinBlocks = YV_MINBLOCKS * kCtaThreads / kFrameCta;      // 
 #define YV_WARP_W 8                    // pixels per warp: 8x4 (4 = 4x8, 16 = 16x2); 8x4 measured best (profiles/README.md)
 #endif
 #ifndef YV_STEPS_PER_VOTE
-#define YV_STEPS_PER_VOTE 4            // lean_steps between two warp votes on "anyone still traversing?"
+#define YV_STEPS_PER_VOTE 6            // lean_steps between two warp votes on "anyone still traversing?" (4 -> 6: -1.0..1.3 % frame
+                                       // time on configs 2, 3, 4 and at 8K, 8 no better: profiles/README.md round 2)
 #endif
 constexpr int kStepsPerVote = YV_STEPS_PER_VOTE;
 
@@ -208,12 +212,17 @@ struct NodeFetch {
   uint32_t staged_n;
   uint32_t root;                 // index of the root node (0 for the packed pool)
   mutable uint32_t visits, revisits;
-  const uint2 *info;             // { leaf_base, orig_id } per record (packed pool)
+  const uint2 *octs;             // CULL: octant occupancy of every record's children (packed pool)
   const uint8_t *lut;            // CULL: the box masks, staged in shared memory
   __device__ __forceinline__ const uint32_t *pool() const { return reinterpret_cast<const uint32_t *>(recs); }
   __device__ __forceinline__ uint4 load(uint32_t idx) const {
     if (STAGED && idx < staged_n) return staged[idx];
     return __ldg(recs + idx);
+  }
+  // the two words a descent needs: the first half of the record
+  __device__ __forceinline__ uint2 load2(uint32_t idx) const {
+    if (STAGED && idx < staged_n) { const uint4 v = staged[idx]; return make_uint2(v.x, v.y); }
+    return __ldg(reinterpret_cast<const uint2 *>(recs + idx));
   }
   __device__ __forceinline__ uint32_t root_index() const { return root; }
   // one node dereference: the two child masks (+ child base for the packed layout)
@@ -225,7 +234,7 @@ struct NodeFetch {
       masks = leaf | ((~(flags >> 8) & ~leaf & 0xffu) << 8);              // child = not leaf, not null
       child_base = 0u;
     } else {
-      const uint4 r = load(idx);
+      const uint2 r = load2(idx);
       child_base = r.x; masks = r.y;
     }
   }
@@ -233,8 +242,9 @@ struct NodeFetch {
   __device__ __forceinline__ void node(uint32_t idx, bool visit, uint32_t &masks, uint32_t &child_base,
                                        uint32_t &gm_lo, uint32_t &gm_hi) const {
     if (COUNT) { if (visit) ++visits; else ++revisits; }
-    const uint4 r = load(idx);
-    child_base = r.x; masks = r.y; gm_lo = r.z; gm_hi = r.w;
+    const uint2 r = load2(idx);
+    const uint2 g = __ldg(octs + idx);
+    child_base = r.x; masks = r.y; gm_lo = g.x; gm_hi = g.y;
   }
   __device__ __forceinline__ uint32_t box(uint32_t flags, uint32_t ch0, uint32_t chx) const {
     return lut[(flags << 6) | (ch0 << 3) | chx];
@@ -251,7 +261,7 @@ struct NodeFetch {
       orig_id = idx;
       data = __ldg(pool() + (size_t)idx * 10u + (lod_hit ? 1u : 2u + c));
     } else {
-      const uint2 in = __ldg(info + idx);
+      const uint2 in = __ldg(reinterpret_cast<const uint2 *>(recs + idx) + 1);     // { leaf_base, orig_id }: same sector as the descent's half
       orig_id = in.y;
       data = lod_hit ? __ldg(node_data + idx)
                      : __ldg(leaves + in.x + (uint32_t)__popc(masks & 0xffu & ((1u << c) - 1u)));
@@ -273,7 +283,10 @@ __device__ __forceinline__ int tile_row_y(const RenderParams &p, int ty) {
 
 enum : int { kLaneIdle = 0, kLaneActive = 1, kLaneHit = 2, kLaneMiss = 3, kLaneNew = 4, kLaneLodHit = 5 };
 
-template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED, bool LOD, bool RAW, bool JIT = false, bool CULL = false>
+// ZB (SSNA, the default schedule only): the hit epilogue also writes the view-space z-buffer BlurZ reads, so the frame
+// needs no ssna_z_pass. A template parameter, not a run-time test of p.zbuf: the test alone cost the plain primary
+// kernel 1.4 % (profiles/README.md, round 2).
+template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED, bool LOD, bool RAW, bool JIT = false, bool CULL = false, bool ZB = false>
 __global__ void __launch_bounds__(kFrameCta, kFrameMinBlocks) render_frame(const __grid_constant__ RenderParams p) {
   extern __shared__ uint4 smem[];
   __shared__ uint32_t box_lut[CULL ? 128 : 1];
@@ -287,7 +300,7 @@ __global__ void __launch_bounds__(kFrameCta, kFrameMinBlocks) render_frame(const
 
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  NodeFetch<COUNT, STAGED, RAW, CULL> fetch = { p.recs, staged, p.smem_nodes, p.root_index, 0u, 0u, p.info,
+  NodeFetch<COUNT, STAGED, RAW, CULL> fetch = { p.recs, staged, p.smem_nodes, p.root_index, 0u, 0u, p.octs,
                                                 reinterpret_cast<const uint8_t *>(box_lut) };
   typename StackOf<STACK>::type stk(stack_area);
   LeanState s;
@@ -387,7 +400,7 @@ __global__ void __launch_bounds__(kFrameCta, kFrameMinBlocks) render_frame(const
       uint32_t rgba = 0u;
       float nx = 0.f, ny = 0.f, nz = 0.f;
       if (!SEC || stage == 0) {
-        uint32_t hn = YV_MISS_NODE; int32_t hc = YV_MISS_CHILD; float ht = 0.0f;
+        uint32_t hn = YV_MISS_NODE; int32_t hc = YV_MISS_CHILD; float ht = 0.0f, zview = 0.0f;
         if (hit) {
           const uint32_t c = lean_ch(s) ^ s.flags;
           fetch.hit_info(p.leaves, p.node_data, s.idx, c, s.masks, lod_hit, hn, sdata);
@@ -402,6 +415,8 @@ __global__ void __launch_bounds__(kFrameCta, kFrameMinBlocks) render_frame(const
           const float Py = YV_FADD(ey, YV_FMUL(dy, ht));
           const float Pz = YV_FADD(ez, YV_FMUL(dz, ht));
           dl = lambert(nx, ny, nz, Px, Py, Pz, p.light[0], p.light[1], p.light[2]);
+          // SSNA: the view-space depth of the hit, z = t * (d . forward), goes straight into the z-buffer BlurZ reads
+          if (ZB) zview = YV_FMUL(ht, YV_FADD(YV_FADD(YV_FMUL(dx, p.fwd[0]), YV_FMUL(dy, p.fwd[1])), YV_FMUL(dz, p.fwd[2])));
           if (!SEC) {
             rgba = shade_rgba(sdata, YV_FADD(YV_SHADE_AMBIENT, YV_FMUL(YV_SHADE_DIFFUSE, YV_FMUL(dl, 1.0f))));
           } else {
@@ -414,6 +429,7 @@ __global__ void __launch_bounds__(kFrameCta, kFrameMinBlocks) render_frame(const
         }
         if (p.hit_node) { p.hit_node[pixel] = hn; p.hit_child[pixel] = hc; p.hit_t[pixel] = ht; }
         if (!SEC && p.shade_rec && hit) p.shade_rec[pixel] = make_uint2(sdata, __float_as_uint(ht));
+        if (ZB) p.zbuf[pixel] = zview;                // 0 = no hit (what ssna_z_pass wrote as a pass of its own)
       } else {
         // a secondary ray came back
         const float ts = lean_hit_t(s);
@@ -504,7 +520,7 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_queue(const 
   const int tx = blockIdx.x % tiles_x32, ty = blockIdx.x / tiles_x32;
   const int wx0 = tx * 32 + (warp & 1) * 16, wy0 = tile_row_y(p, ty * 2 + (warp >> 1));
 
-  NodeFetch<COUNT, false> fetch = { p.recs, nullptr, 0u, 0u, 0u, 0u, p.info, nullptr };
+  NodeFetch<COUNT, false> fetch = { p.recs, nullptr, 0u, 0u, 0u, 0u, p.octs, nullptr };
   typename StackOf<STACK>::type stk(stack_area);
   LeanState s;
   const bool root_valid = p.root_valid != 0u;
@@ -648,7 +664,7 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_sec_queue(co
   const bool in_frame = x < p.width && y < p.y1;
   const uint32_t pixel = (uint32_t)y * (uint32_t)p.width + (uint32_t)x;
 
-  NodeFetch<COUNT, false> fetch = { p.recs, nullptr, 0u, 0u, 0u, 0u, p.info, nullptr };
+  NodeFetch<COUNT, false> fetch = { p.recs, nullptr, 0u, 0u, 0u, 0u, p.octs, nullptr };
   LocalStack stk(nullptr);
   LeanState s;
   const bool root_valid = p.root_valid != 0u;
@@ -818,11 +834,15 @@ __global__ void __launch_bounds__(256) shade_pass(const __grid_constant__ Render
   const int y = tile_row_y(p, blockIdx.y) + (threadIdx.x >> 5);      // the rows of this launch's band / blocks
   if (x >= p.width || y >= p.y1) return;
   const uint32_t pixel = (uint32_t)y * (uint32_t)p.width + (uint32_t)x;
-  if (p.out_rgba[pixel] == 0u) return;                    // miss (hit pixels carry alpha 255)
+  uint32_t *dst = p.final_rgba ? p.final_rgba : p.out_rgba;
+  if (p.out_rgba[pixel] == 0u) {                          // miss (hit pixels carry alpha 255)
+    if (p.final_rgba) dst[pixel] = 0u;
+    return;
+  }
   const uint2 rec = p.shade_rec[pixel];
   const float t = __uint_as_float(rec.y);
-  float nx, ny, nz, dx, dy, dz;
-  unpack_normal(rec.x, nx, ny, nz);
+  float nx = 0.f, ny = 0.f, nz = 0.f, dx, dy, dz;
+  bool have_n = false;                                    // the stored normal is unpacked only where SSNA has none to offer
   if (p.ssna) {                                           // normal from the blurred z-buffer (yv_format.h "SSNA")
     const float z = p.zbuf[pixel];
     if (z != 0.0f) {
@@ -838,9 +858,11 @@ __global__ void __launch_bounds__(256) shade_pass(const __grid_constant__ Render
         nx = YV_FDIV(YV_FADD(YV_FADD(YV_FMUL(p.right[0], nvx), YV_FMUL(p.down[0], nvy)), YV_FMUL(p.fwd[0], nvz)), len);
         ny = YV_FDIV(YV_FADD(YV_FADD(YV_FMUL(p.right[1], nvx), YV_FMUL(p.down[1], nvy)), YV_FMUL(p.fwd[1], nvz)), len);
         nz = YV_FDIV(YV_FADD(YV_FADD(YV_FMUL(p.right[2], nvx), YV_FMUL(p.down[2], nvy)), YV_FMUL(p.fwd[2], nvz)), len);
+        have_n = true;
       }
     }
   }
+  if (!have_n) unpack_normal(rec.x, nx, ny, nz);
   uint32_t rgba;
   if (p.shade_mode == 2) rgba = shade_normal(nx, ny, nz);
   else {
@@ -857,7 +879,7 @@ __global__ void __launch_bounds__(256) shade_pass(const __grid_constant__ Render
       rgba = shade_rgba(rec.x, YV_FADD(YV_SHADE_AMBIENT, YV_FMUL(YV_SHADE_DIFFUSE, YV_FMUL(dl, 1.0f))));
     }
   }
-  p.out_rgba[pixel] = rgba;
+  dst[pixel] = rgba;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -887,7 +909,13 @@ __global__ void __launch_bounds__(256) ssna_z_pass(const __grid_constant__ Rende
 // for 196 taps). Invalid pixels are staged as +inf: |inf - zc| < zlimit is false, which folds the validity test into
 // the depth test. Per output the taps still arrive in row-major (ky, kx) order with separate multiply and add, so the
 // result matches the CPU statement bit for bit. 5 ALU instructions per tap: the pass is issue-bound, not HBM-bound
-// (245 instructions against 8 bytes per pixel).
+// (245 instructions against 8 bytes per pixel) — so a warp first finds out how much of that it needs (round 2):
+//   * background: none of the warp's 32x4 outputs is valid -> zeros, no taps (27 % of the warps on config 2);
+//   * smooth:     the 38x10 staged values the warp's taps can reach are all valid and max - min < zlimit. Then every
+//                 tap of every output passes its test — rounding is monotone, so fl(|zq - zc|) <= fl(max - min) — and
+//                 the pass is 2 instructions per tap; wacc is the constant the full row-major sum of the taps gives
+//                 (BlurParams::wsum, summed on the host in that order);
+//   * otherwise the tested form.
 constexpr int kBlurTile = 32, kBlurApron = YV_BLURZ_KERN / 2, kBlurSpan = kBlurTile + 2 * kBlurApron, kBlurRows = 4;
 __global__ void __launch_bounds__(256) blur_z_pass(const __grid_constant__ BlurParams b) {
   __shared__ float tile[kBlurSpan][kBlurSpan + 1];
@@ -903,10 +931,53 @@ __global__ void __launch_bounds__(256) blur_z_pass(const __grid_constant__ BlurP
   __syncthreads();
   const int lx = threadIdx.x & 31, gx = bx + lx;
   const int ly = (threadIdx.x >> 5) * kBlurRows;           // first of this thread's four output rows
-  if (gx >= b.width || by + ly >= b.height) return;
   float zc[kBlurRows], acc[kBlurRows], wacc[kBlurRows];
+  bool any_valid = false;
 #pragma unroll
-  for (int j = 0; j < kBlurRows; ++j) { zc[j] = tile[ly + j + kBlurApron][lx + kBlurApron]; acc[j] = 0.0f; wacc[j] = 0.0f; }
+  for (int j = 0; j < kBlurRows; ++j) {
+    zc[j] = tile[ly + j + kBlurApron][lx + kBlurApron]; acc[j] = 0.0f; wacc[j] = 0.0f;
+    any_valid = any_valid || zc[j] != kInvalid;            // outputs outside the frame were staged invalid
+  }
+  const bool in_x = gx < b.width;
+  if (__ballot_sync(kFullMask, any_valid) == 0u) {         // background warp
+#pragma unroll
+    for (int j = 0; j < kBlurRows; ++j)
+      if (in_x && by + ly + j < b.height) b.dst[(size_t)(by + ly + j) * b.width + gx] = 0.0f;
+    return;
+  }
+  // range of everything this warp's taps can reach: tile rows ly .. ly+9, columns 0 .. 37
+  float mn = kInvalid, mx = -kInvalid;
+#pragma unroll
+  for (int r = 0; r < kBlurRows + YV_BLURZ_KERN - 1; ++r) {
+    const float v = tile[ly + r][lx];
+    mn = fminf(mn, v); mx = fmaxf(mx, v);
+    if (lx < 2 * kBlurApron) { const float u = tile[ly + r][kBlurTile + lx]; mn = fminf(mn, u); mx = fmaxf(mx, u); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(kFullMask, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, o));
+  }
+  const bool smooth = YV_FSUB(mx, mn) < b.zlimit;           // false when anything is invalid (inf - x, inf - inf)
+  if (smooth) {
+#pragma unroll
+    for (int r = 0; r < kBlurRows + YV_BLURZ_KERN - 1; ++r) {
+      float zq[YV_BLURZ_KERN];
+#pragma unroll
+      for (int kx = 0; kx < YV_BLURZ_KERN; ++kx) zq[kx] = tile[ly + r][lx + kx];
+#pragma unroll
+      for (int j = 0; j < kBlurRows; ++j) {
+        const int ky = r - j;
+        if (ky < 0 || ky >= YV_BLURZ_KERN) continue;
+#pragma unroll
+        for (int kx = 0; kx < YV_BLURZ_KERN; ++kx) acc[j] = YV_FADD(acc[j], YV_FMUL(b.taps[ky * YV_BLURZ_KERN + kx], zq[kx]));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kBlurRows; ++j)
+      if (in_x && by + ly + j < b.height) b.dst[(size_t)(by + ly + j) * b.width + gx] = YV_FDIV(acc[j], b.wsum);
+    return;
+  }
 #pragma unroll
   for (int r = 0; r < kBlurRows + YV_BLURZ_KERN - 1; ++r) {           // tile row ly + r feeds output j as tap row ky = r - j
     float zq[YV_BLURZ_KERN];
@@ -928,7 +999,7 @@ __global__ void __launch_bounds__(256) blur_z_pass(const __grid_constant__ BlurP
 #pragma unroll
   for (int j = 0; j < kBlurRows; ++j) {
     const int gy = by + ly + j;
-    if (gy >= b.height) break;
+    if (!in_x || gy >= b.height) continue;
     float out = 0.0f;
     if (zc[j] != kInvalid) out = wacc[j] > 0.0f ? YV_FDIV(acc[j], wacc[j]) : zc[j];
     b.dst[(size_t)gy * b.width + gx] = out;
@@ -958,12 +1029,12 @@ __global__ void __launch_bounds__(256) resolve_frames(const uint4 *sum, uint32_t
 // arbitrary rays (DynamicSVO::TraceRay, ore/src/main.cpp:125)
 // ---------------------------------------------------------------------------------------------
 template <bool RAW>
-__global__ void __launch_bounds__(128) trace_rays_kernel(const uint4 *recs, const uint2 *info, const uint32_t *leaves, uint32_t root_valid, uint32_t root_index,
+__global__ void __launch_bounds__(128) trace_rays_kernel(const uint4 *recs, const uint2 *octs, const uint32_t *leaves, uint32_t root_valid, uint32_t root_index,
                                                          const float *pos, const float *dir, uint32_t count,
                                                          uint32_t *node, int32_t *child, float *t) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  NodeFetch<false, false, RAW> fetch = { recs, nullptr, 0u, root_index, 0u, 0u, info, nullptr };
+  NodeFetch<false, false, RAW> fetch = { recs, nullptr, 0u, root_index, 0u, 0u, octs, nullptr };
   LocalStack stk(nullptr);
   LeanState s;
   const float dx = adjust_dir1(dir[3 * i]), dy = adjust_dir1(dir[3 * i + 1]), dz = adjust_dir1(dir[3 * i + 2]);

@@ -116,13 +116,13 @@ int pack_svo(const HostSVO &svo, PackedSVO &out, std::string &err) {
   return 0;
 }
 
-void device_layout(const PackedSVO &p, std::vector<DeviceRecord> &trav, std::vector<DeviceRecordInfo> &info) {
-  trav.resize(p.records.size()); info.resize(p.records.size());
+void device_layout(const PackedSVO &p, std::vector<DeviceRecord> &trav, std::vector<DeviceRecordOctants> &octs) {
+  trav.resize(p.records.size()); octs.resize(p.records.size());
   for (size_t i = 0; i < p.records.size(); ++i) {
     const PackedRecord &r = p.records[i];
     const uint64_t g = i < p.octants.size() ? p.octants[i] : 0ull;
-    trav[i] = DeviceRecord{ r.child_base, r.masks, (uint32_t)g, (uint32_t)(g >> 32) };
-    info[i] = DeviceRecordInfo{ r.leaf_base, r.orig_id };
+    trav[i] = DeviceRecord{ r.child_base, r.masks, r.leaf_base, r.orig_id };
+    octs[i] = DeviceRecordOctants{ (uint32_t)g, (uint32_t)(g >> 32) };
   }
 }
 

@@ -15,8 +15,11 @@
 // Next to the records: octants[i], the 64-bit "grandchild mask" of record i — byte c holds, for child NODE c, which of
 // that child's eight octants contain anything (its leaf flags | child flags); 0 for leaf and empty slots. The traversal
 // reads it with the record and uses it to skip child nodes the ray crosses through empty octants only (trace_core.cuh).
-// On the device the four words a descent needs travel in one 16-byte load — { child_base, masks, octants lo, octants hi }
-// — and the two words only a hit needs — { leaf_base, orig_id } — live in a side array (device_layout below).
+// On the device a record is { child_base, masks, leaf_base, orig_id }: the descent reads the first 8 bytes (LDG.64), a hit
+// reads the other 8 of the same 32-byte sector (an L1 hit, the record was fetched a moment ago). The octant masks live in
+// a side array that only the culling traversal (an ablation, off by default) reads. (Round 2 first put the octant words
+// INTO the record and { leaf_base, orig_id } into the side array: every hit then paid a cold DRAM/L2 miss at the very end
+// of its warp's life, +1.2 % frame time on config 2 — profiles/README.md.)
 // Breadth-first order also puts the top of the tree at the lowest indices, so "stage the hot top
 // levels in shared memory" (SPU software cache precedent: cell/spu/trace_spu.cpp:15-35) is the
 // test `index < staged_count`.
@@ -42,11 +45,11 @@ struct PackedSVO {
   bool root_null = true;
 };
 
-// The device form of the records: trav[i] = { child_base, masks, octants lo, octants hi }, info[i] = { leaf_base, orig_id }
-struct DeviceRecord { uint32_t child_base, masks, oct_lo, oct_hi; };
-struct DeviceRecordInfo { uint32_t leaf_base, orig_id; };
-static_assert(sizeof(DeviceRecord) == 16 && sizeof(DeviceRecordInfo) == 8, "device record layout");
-void device_layout(const PackedSVO &p, std::vector<DeviceRecord> &trav, std::vector<DeviceRecordInfo> &info);
+// The device form of the records: trav[i] = { child_base, masks, leaf_base, orig_id }, octs[i] = { octants lo, octants hi }
+struct DeviceRecord { uint32_t child_base, masks, leaf_base, orig_id; };
+struct DeviceRecordOctants { uint32_t oct_lo, oct_hi; };
+static_assert(sizeof(DeviceRecord) == 16 && sizeof(DeviceRecordOctants) == 8, "device record layout");
+void device_layout(const PackedSVO &p, std::vector<DeviceRecord> &trav, std::vector<DeviceRecordOctants> &octs);
 
 // Shared sub-trees (a DAG) are duplicated; cyclic pools are rejected via the level limit.
 int pack_svo(const HostSVO &svo, PackedSVO &out, std::string &err);

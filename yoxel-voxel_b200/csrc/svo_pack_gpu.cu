@@ -38,7 +38,7 @@ __global__ void count_kernel(const yv_vox_node *raw, const uint32_t *frontier, u
 }
 
 __global__ void emit_kernel(const yv_vox_node *raw, const uint32_t *frontier, uint32_t n, const uint32_t *coff,
-                            const uint32_t *loff, uint32_t base, uint32_t leaf_base, uint4 *recs, uint2 *info, uint32_t *leaves,
+                            const uint32_t *loff, uint32_t base, uint32_t leaf_base, uint4 *recs, uint32_t *leaves,
                             uint32_t *node_data, uint32_t *next_frontier) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -47,8 +47,7 @@ __global__ void emit_kernel(const yv_vox_node *raw, const uint32_t *frontier, ui
   uint32_t lm, cm;
   node_masks(nd, lm, cm);
   uint32_t ci = coff[i], li = leaf_base + loff[i];
-  recs[base + i] = make_uint4(base + n + ci, lm | (cm << 8), 0u, 0u);     // octant words: octants_kernel
-  info[base + i] = make_uint2(li, id);
+  recs[base + i] = make_uint4(base + n + ci, lm | (cm << 8), li, id);
   node_data[base + i] = nd.data;
   for (int c = 0; c < 8; ++c) {
     if ((lm >> c) & 1u) leaves[li++] = nd.child[c];
@@ -57,7 +56,7 @@ __global__ void emit_kernel(const yv_vox_node *raw, const uint32_t *frontier, ui
 }
 
 // byte c of a record's grandchild mask = (leaf flags | child flags) of its child node c; children are contiguous
-__global__ void octants_kernel(uint4 *recs, uint32_t n) {
+__global__ void octants_kernel(const uint4 *recs, uint2 *octs, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint4 r = recs[i];
@@ -68,7 +67,7 @@ __global__ void octants_kernel(uint4 *recs, uint32_t n) {
       const uint32_t occ = (m | (m >> 8)) & 0xffu;
       if (c < 4) lo |= occ << (8 * c); else hi |= occ << (8 * (c - 4));
     }
-  recs[i].z = lo; recs[i].w = hi;
+  octs[i] = make_uint2(lo, hi);
 }
 
 #define PK_CUDA(call)                                                                   \
@@ -87,7 +86,7 @@ int pack_svo_on_device(const yv_vox_node *d_raw, size_t count, yv_node_id root, 
   uint32_t *front[2] = { nullptr, nullptr }, *cc = nullptr, *lc = nullptr, *coff = nullptr, *loff = nullptr;
   void *tmp = nullptr; size_t tmp_bytes = 0;
   int *d_bad = nullptr;
-  uint4 *recs = nullptr; uint2 *info = nullptr; uint32_t *leaves = nullptr, *node_data = nullptr;
+  uint4 *recs = nullptr; uint2 *octs = nullptr; uint32_t *leaves = nullptr, *node_data = nullptr;
   size_t leaves_cap = 0;
   // a tree has one record per reachable node: at most N records; leaves at most 8 per node, grown on demand
   PK_CUDA(cudaMalloc(&front[0], (size_t)N * 4)); PK_CUDA(cudaMalloc(&front[1], (size_t)N * 4));
@@ -97,7 +96,7 @@ int pack_svo_on_device(const yv_vox_node *d_raw, size_t count, yv_node_id root, 
   PK_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cc, coff, (int)N));
   PK_CUDA(cudaMalloc(&tmp, tmp_bytes));
   PK_CUDA(cudaMalloc(&recs, (size_t)N * sizeof(uint4)));
-  PK_CUDA(cudaMalloc(&info, (size_t)N * sizeof(uint2)));
+  PK_CUDA(cudaMalloc(&octs, (size_t)N * sizeof(uint2)));
   PK_CUDA(cudaMalloc(&node_data, (size_t)N * 4));
   leaves_cap = std::max<size_t>((size_t)N * 3, 1024);
   PK_CUDA(cudaMalloc(&leaves, leaves_cap * 4));
@@ -127,24 +126,24 @@ int pack_svo_on_device(const yv_vox_node *d_raw, size_t count, yv_node_id root, 
         PK_CUDA(cudaMemcpy(l2, leaves, (size_t)leaf_base * 4, cudaMemcpyDeviceToDevice));
         cudaFree(leaves); leaves = l2; leaves_cap = cap2;
       }
-      emit_kernel<<<grid, 256>>>(d_raw, front[cur], n, coff, loff, base, leaf_base, recs, info, leaves, node_data, front[cur ^ 1]);
+      emit_kernel<<<grid, 256>>>(d_raw, front[cur], n, coff, loff, base, leaf_base, recs, leaves, node_data, front[cur ^ 1]);
       PK_CUDA(cudaGetLastError());
       base += n; leaf_base += (uint32_t)n_leaves; n = (uint32_t)n_children; cur ^= 1; ++level;
     }
     int bad = 0;
     PK_CUDA(cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost));
     if (bad) { err = "child id outside node pool"; goto fail; }
-    octants_kernel<<<(base + 255) / 256, 256>>>(recs, base);      // (only the y word of other records is read: no race with the z/w writes)
+    octants_kernel<<<(base + 255) / 256, 256>>>(recs, octs, base);
     PK_CUDA(cudaGetLastError());
     PK_CUDA(cudaDeviceSynchronize());
-    out.recs = recs; out.info = info; out.leaves = leaves; out.node_data = node_data;
+    out.recs = recs; out.octs = octs; out.leaves = leaves; out.node_data = node_data;
     out.n_recs = base; out.n_leaves = leaf_base; out.levels = level;
   }
   cudaFree(front[0]); cudaFree(front[1]); cudaFree(cc); cudaFree(lc); cudaFree(coff); cudaFree(loff); cudaFree(tmp); cudaFree(d_bad);
   return 0;
 fail:
   cudaFree(front[0]); cudaFree(front[1]); cudaFree(cc); cudaFree(lc); cudaFree(coff); cudaFree(loff); cudaFree(tmp); cudaFree(d_bad);
-  cudaFree(recs); cudaFree(info); cudaFree(leaves); cudaFree(node_data);
+  cudaFree(recs); cudaFree(octs); cudaFree(leaves); cudaFree(node_data);
   out = DevicePacked();
   return -1;
 }

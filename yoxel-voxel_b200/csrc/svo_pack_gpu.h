@@ -13,8 +13,8 @@
 namespace yv {
 
 struct DevicePacked {
-  void *recs = nullptr;        // uint4[n_recs]: { child_base, masks, octants lo, octants hi } (svo_pack.h, device form)
-  void *info = nullptr;        // uint2[n_recs]: { leaf_base, orig_id }
+  void *recs = nullptr;        // uint4[n_recs]: { child_base, masks, leaf_base, orig_id } (svo_pack.h, device form)
+  void *octs = nullptr;        // uint2[n_recs]: { octants lo, octants hi } (culling traversal only)
   uint32_t *leaves = nullptr;  // [n_leaves]
   uint32_t *node_data = nullptr;  // [n_recs]
   size_t n_recs = 0, n_leaves = 0;

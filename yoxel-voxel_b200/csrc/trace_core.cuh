@@ -231,7 +231,21 @@ YV_HD void lean_eval_next(LeanState &s) {
 // The exit axis is carried one-hot (bit 0 = x, 1 = y, 2 = z; 0 = no step) so that "already in the
 // upper half" is one AND with ch and the step is six selects — branch-free on purpose: lanes of one
 // warp step different axes, selects keep them converged.
+// YV_STEP_IMAD (build-time variant, profiles/README.md round 2): the six selects as integer multiply-adds on the float
+// bits, x + m * (y - x) with m = 0 / 1 — exact, and issued to the FMA pipe instead of the ALU pipe the kernel saturates.
+#ifndef YV_STEP_IMAD
+#define YV_STEP_IMAD 0
+#endif
+YV_HD float lean_isel(uint32_t m, float y, float x) { return YV_U2F(YV_F2U(x) + m * (YV_F2U(y) - YV_F2U(x))); }
 YV_HD void lean_apply_step(LeanState &s, const uint32_t ebits) {
+#if YV_STEP_IMAD
+  const uint32_t mx = ebits & 1u, my = (ebits >> 1) & 1u, mz = ebits >> 2;
+  s.t1x = lean_isel(mx, s.Tx, s.t1x); s.Tx = lean_isel(mx, s.Nx, s.Tx);
+  s.t1y = lean_isel(my, s.Ty, s.t1y); s.Ty = lean_isel(my, s.Ny, s.Ty);
+  s.t1z = lean_isel(mz, s.Tz, s.t1z); s.Tz = lean_isel(mz, s.Nz, s.Tz);
+  s.ch |= ebits;
+  return;
+#endif
   const bool ex = (ebits & 1u) != 0u, ey = (ebits & 2u) != 0u, ez = (ebits & 4u) != 0u;
   s.t1x = ex ? s.Tx : s.t1x; s.Tx = ex ? s.Nx : s.Tx;
   s.t1y = ey ? s.Ty : s.t1y; s.Ty = ey ? s.Ny : s.Ty;

@@ -74,8 +74,8 @@ int upload_staged(void *dst, const void *src, size_t bytes) {
 }
 
 void free_packed_device(DeviceSVO &d) {
-  cudaFree(d.recs); cudaFree(d.info); cudaFree(d.leaves); cudaFree(d.node_data);
-  d.recs = nullptr; d.info = nullptr; d.leaves = nullptr; d.node_data = nullptr; d.n_recs = d.n_leaves = 0;
+  cudaFree(d.recs); cudaFree(d.octs); cudaFree(d.leaves); cudaFree(d.node_data);
+  d.recs = nullptr; d.octs = nullptr; d.leaves = nullptr; d.node_data = nullptr; d.n_recs = d.n_leaves = 0;
 }
 
 // CudaSVO::Update (demo/SVORenderer.cpp:33-53; paging: reaction/report/main.tex:71): bring the device's raw
@@ -147,14 +147,14 @@ int ensure_uploaded(yv_svo *svo, int device, DeviceSVO **out) {
       yv::DevicePacked dp; std::string err;
       if (yv::pack_svo_on_device(d->raw, svo->host.nodes.size(), svo->host.root, dp, err) == 0) {
         if (dp.levels > yv::kMaxStack + 1) {
-          cudaFree(dp.recs); cudaFree(dp.info); cudaFree(dp.leaves); cudaFree(dp.node_data);
+          cudaFree(dp.recs); cudaFree(dp.octs); cudaFree(dp.leaves); cudaFree(dp.node_data);
           return fail(YV_ERR_FORMAT, "tree deeper than the traversal stack supports");
         }
-        d->recs = (uint4 *)dp.recs; d->info = (uint2 *)dp.info; d->leaves = dp.leaves; d->node_data = dp.node_data;
+        d->recs = (uint4 *)dp.recs; d->octs = (uint2 *)dp.octs; d->leaves = dp.leaves; d->node_data = dp.node_data;
         d->n_recs = dp.n_recs; d->n_leaves = dp.n_leaves; d->levels = dp.levels;
         d->root_null = YV_IS_NULL(svo->host.root);
         if (!d->recs) {                            // null root: keep valid (dummy) pointers
-          YV_CUDA(cudaMalloc(&d->recs, sizeof(uint4))); YV_CUDA(cudaMalloc(&d->info, sizeof(uint2)));
+          YV_CUDA(cudaMalloc(&d->recs, sizeof(uint4))); YV_CUDA(cudaMalloc(&d->octs, sizeof(uint2)));
           YV_CUDA(cudaMalloc(&d->leaves, sizeof(uint32_t)));
         }
         d->packed_version = want;
@@ -178,13 +178,13 @@ int ensure_uploaded(yv_svo *svo, int device, DeviceSVO **out) {
       d.root_null = svo->packed.root_null;
       d.levels = (int)svo->packed.level_start.size() - 1;
       YV_CUDA(cudaMalloc(&d.recs, std::max<size_t>(1, d.n_recs) * sizeof(uint4)));
-      YV_CUDA(cudaMalloc(&d.info, std::max<size_t>(1, d.n_recs) * sizeof(uint2)));
+      YV_CUDA(cudaMalloc(&d.octs, std::max<size_t>(1, d.n_recs) * sizeof(uint2)));
       YV_CUDA(cudaMalloc(&d.leaves, std::max<size_t>(1, d.n_leaves) * sizeof(uint32_t)));
       if (d.n_recs) {
-        std::vector<yv::DeviceRecord> trav; std::vector<yv::DeviceRecordInfo> info;
-        yv::device_layout(svo->packed, trav, info);
+        std::vector<yv::DeviceRecord> trav; std::vector<yv::DeviceRecordOctants> octs;
+        yv::device_layout(svo->packed, trav, octs);
         int urc = upload_staged(d.recs, trav.data(), d.n_recs * sizeof(uint4));
-        if (!urc) urc = upload_staged(d.info, info.data(), d.n_recs * sizeof(uint2));
+        if (!urc) urc = upload_staged(d.octs, octs.data(), d.n_recs * sizeof(uint2));
         if (urc) return urc;
       }
       if (d.n_leaves) { int urc = upload_staged(d.leaves, svo->packed.leaves.data(), d.n_leaves * sizeof(uint32_t)); if (urc) return urc; }
@@ -288,9 +288,9 @@ void init_ray_dir(const yv_renderer *r, float dir0[3], float du[3], float dv[3],
   init_ray_dir_raw(r->dir, r->up, r->fov, r->width, r->height, dir0, du, dv, basis);
 }
 
-template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED, bool LOD = false, bool RAW = false, bool JIT = false, bool CULL = false>
+template <bool SEC, bool COUNT, int STACK, bool PERSISTENT, bool STAGED, bool LOD = false, bool RAW = false, bool JIT = false, bool CULL = false, bool ZB = false>
 int launch_kernel(yv_renderer *r, const yv::RenderParams &p, size_t smem) {
-  auto kern = yv::render_frame<SEC, COUNT, STACK, PERSISTENT, STAGED, LOD, RAW, JIT, CULL>;
+  auto kern = yv::render_frame<SEC, COUNT, STACK, PERSISTENT, STAGED, LOD, RAW, JIT, CULL, ZB>;
   if (smem > 48 * 1024) YV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long grid;
   if (PERSISTENT) {
@@ -394,7 +394,7 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
     p.root_valid = YV_IS_NULL(r->svo->host.root) ? 0u : 1u;
     p.root_index = p.root_valid ? r->svo->host.root : 0u;
   } else {
-    p.recs = ds->recs; p.info = ds->info; p.leaves = ds->leaves;
+    p.recs = ds->recs; p.octs = ds->octs; p.leaves = ds->leaves;
     p.root_valid = ds->root_null ? 0u : 1u;
   }
   p.smem_nodes = raw ? 0u : (uint32_t)std::min<size_t>((size_t)std::max(0, r->opt_smem_nodes), ds->n_recs);
@@ -443,6 +443,9 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
   if (p.shade_mode != 0 || ssna) {
     if (!r->d_shade_rec) YV_CUDA(cudaMalloc(&r->d_shade_rec, std::max<size_t>(1, r->fb_pixels) * sizeof(uint2)));
     p.shade_rec = r->d_shade_rec;
+    // the trace kernel draws into the renderer's own HBM frame; the pass that finishes the pixels writes them where the
+    // caller wants them (a pinned host frame for yv_render_frame: no D2H copy afterwards)
+    if (d_rgba != (void *)r->d_fb) { p.out_rgba = r->d_fb; p.final_rgba = (uint32_t *)d_rgba; }
   }
   const bool jitter = r->jitter_amp > 0.0f;
   if (jitter) {
@@ -511,6 +514,11 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
   } else if (r->opt_persistent == 2 && !sec) {        // per-warp ray queue (primary rays)
     if (r->opt_stack == yv::kStackRing4) rc = r->counters ? launch_queue<true, yv::kStackRing4>(r, p) : launch_queue<false, yv::kStackRing4>(r, p);
     else rc = r->counters ? launch_queue<true, yv::kStackLocal>(r, p) : launch_queue<false, yv::kStackLocal>(r, p);
+  } else if (ssna && key == 0 && r->opt_persistent == 0 && r->opt_stack == yv::kStackLocal && p.smem_nodes == 0) {
+    // SSNA on the default schedule: the trace kernel's hit epilogue writes the z-buffer (render_frame<..., ZB>); every
+    // other variant leaves it to ssna_z_pass below
+    p.zbuf = r->d_zbuf[0];
+    rc = launch_kernel<false, false, yv::kStackLocal, false, false, false, false, false, false, true>(r, p, smem);
   } else
   switch (key) {
     case 0: rc = launch_stack<false, false>(r, p, smem); break;
@@ -521,12 +529,16 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
   if (rc) return rc;
   int launches = 1;
   if (ssna && p.num_tiles > 0) {                    // z-buffer, then BlurZ x5 (demo/SVORenderer.cpp:126-141)
-    dim3 zgrid((p.width + 31) / 32, (p.height + 7) / 8);
-    p.zbuf = r->d_zbuf[0];
-    yv::ssna_z_pass<<<zgrid, 256, 0, r->stream>>>(p);
-    ++launches;
+    if (!p.zbuf) {
+      dim3 zgrid((p.width + 31) / 32, (p.height + 7) / 8);
+      p.zbuf = r->d_zbuf[0];
+      yv::ssna_z_pass<<<zgrid, 256, 0, r->stream>>>(p);
+      ++launches;
+    }
     yv::BlurParams b;
     std::memcpy(b.taps, r->blur_taps, sizeof b.taps);
+    b.wsum = 0.0f;
+    for (int i = 0; i < YV_BLURZ_KERN * YV_BLURZ_KERN; ++i) b.wsum += b.taps[i];      // float, in tap order: what the tested form accumulates
     b.width = p.width; b.height = p.height;
     const float pixel_ang = (r->fov * (float)(3.14159265358979323846 / 180.0)) / (float)r->width;    // rp.pixelAng (:105)
     float blur_size = 3;
@@ -639,7 +651,7 @@ static void free_device_copies(yv_svo *svo) {
     cudaSetDevice(kv.first);
     cudaDeviceSynchronize();                      // no renderer stream is still reading the copies
     cudaFree(kv.second.recs);
-    cudaFree(kv.second.info);
+    cudaFree(kv.second.octs);
     cudaFree(kv.second.leaves);
     cudaFree(kv.second.node_data);
     cudaFree(kv.second.raw);
@@ -788,11 +800,10 @@ int yv_svo_device_packed_copy(yv_svo *svo, int device, uint32_t *n_records, uint
   YV_CUDA(cudaSetDevice(device));
   if (records_out && d->n_recs) {                    // the canonical record { child_base, leaf_base, masks, orig_id } (svo_pack.h)
     return guarded([&]() -> int {
-      std::vector<uint4> trav(d->n_recs); std::vector<uint2> info(d->n_recs);
+      std::vector<uint4> trav(d->n_recs);
       YV_CUDA(cudaMemcpy(trav.data(), d->recs, d->n_recs * 16, cudaMemcpyDeviceToHost));
-      YV_CUDA(cudaMemcpy(info.data(), d->info, d->n_recs * 8, cudaMemcpyDeviceToHost));
       for (size_t i = 0; i < d->n_recs; ++i) {
-        records_out[4 * i] = trav[i].x; records_out[4 * i + 1] = info[i].x; records_out[4 * i + 2] = trav[i].y; records_out[4 * i + 3] = info[i].y;
+        records_out[4 * i] = trav[i].x; records_out[4 * i + 1] = trav[i].z; records_out[4 * i + 2] = trav[i].y; records_out[4 * i + 3] = trav[i].w;
       }
       if (leaves_out && d->n_leaves) YV_CUDA(cudaMemcpy(leaves_out, d->leaves, d->n_leaves * 4, cudaMemcpyDeviceToHost));
       if (node_data_out && d->node_data) YV_CUDA(cudaMemcpy(node_data_out, d->node_data, d->n_recs * 4, cudaMemcpyDeviceToHost));
@@ -820,10 +831,8 @@ int yv_svo_device_octant_masks(yv_svo *svo, int device, uint64_t *out) {
   int rc = guarded([&]() -> int { return ensure_uploaded(svo, device, &d); });
   if (rc) return rc;
   return guarded([&]() -> int {
-    std::vector<uint4> trav(d->n_recs);
     YV_CUDA(cudaSetDevice(device));
-    if (d->n_recs) YV_CUDA(cudaMemcpy(trav.data(), d->recs, d->n_recs * 16, cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < d->n_recs; ++i) out[i] = (uint64_t)trav[i].z | ((uint64_t)trav[i].w << 32);
+    if (d->n_recs) YV_CUDA(cudaMemcpy(out, d->octs, d->n_recs * 8, cudaMemcpyDeviceToHost));   // { lo, hi } = little-endian uint64
     return YV_OK;
   });
 }
@@ -1105,9 +1114,8 @@ int yv_render_frame(yv_renderer *r, const uint8_t **rgba) {
   int rc = guarded([&]() -> int { return ensure_frame_buffers(r); });
   if (rc) return rc;
   const bool ssna = single_pass_ssna(r);               // BlurZ reaches across row chunks: one launch
-  const bool second_pass = needs_second_pass(r);
-  if (r->opt_zero_copy && !second_pass) {       // (the ShadeSimple / SSNA passes read the frame back: keep it in HBM)
-    rc = launch_frame(r, r->h_fb);              // pinned memory is device-addressable under UVA
+  if (r->opt_zero_copy) {                       // (with a ShadeSimple / SSNA pass the trace kernel draws in HBM and that pass
+    rc = launch_frame(r, r->h_fb);              // stores the finished pixels) pinned memory is device-addressable under UVA
     if (rc) return rc;
     YV_CUDA(cudaStreamSynchronize(r->stream));
     *rgba = r->h_fb;
@@ -1338,7 +1346,7 @@ int yv_trace_rays(yv_renderer *r, const float *pos, const float *dir, uint32_t c
       yv::trace_rays_kernel<true><<<grid, 128, 0, r->stream>>>(reinterpret_cast<const uint4 *>(ds->raw), nullptr, nullptr, valid,
                                                                valid ? r->svo->host.root : 0u, d_pos, d_dir, count, d_node, d_child, d_t);
     } else {
-      yv::trace_rays_kernel<false><<<grid, 128, 0, r->stream>>>(ds->recs, ds->info, ds->leaves, ds->root_null ? 0u : 1u, 0u,
+      yv::trace_rays_kernel<false><<<grid, 128, 0, r->stream>>>(ds->recs, ds->octs, ds->leaves, ds->root_null ? 0u : 1u, 0u,
                                                                 d_pos, d_dir, count, d_node, d_child, d_t);
     }
     e = cudaGetLastError();

@@ -44,8 +44,8 @@ int guarded(F &&body) {
 }
 
 struct DeviceSVO {
-  uint4 *recs = nullptr;              // { child_base, masks, octants lo, octants hi } per record (svo_pack.h, device form)
-  uint2 *info = nullptr;              // { leaf_base, orig_id } per record: read by hits only
+  uint4 *recs = nullptr;              // { child_base, masks, leaf_base, orig_id } per record (svo_pack.h, device form)
+  uint2 *octs = nullptr;              // { octants lo, octants hi } per record: read by the culling traversal only
   uint32_t *leaves = nullptr;
   uint32_t *node_data = nullptr;      // uploaded on first use of the LOD cut-off
   size_t n_recs = 0, n_leaves = 0;

@@ -72,12 +72,12 @@ int replicate_alloc(yv_svo *svo, int src_dev, int dst_dev, bool *needed) {
   if (d.recs && d.packed_version == src.packed_version && d.n_recs == src.n_recs) return YV_OK;
   YV_CUDA(cudaSetDevice(dst_dev));
   YV_CUDA(cudaDeviceSynchronize());                          // nothing still reads the copy that is replaced
-  cudaFree(d.recs); cudaFree(d.info); cudaFree(d.leaves); cudaFree(d.node_data);
-  d.recs = nullptr; d.info = nullptr; d.leaves = nullptr; d.node_data = nullptr;
+  cudaFree(d.recs); cudaFree(d.octs); cudaFree(d.leaves); cudaFree(d.node_data);
+  d.recs = nullptr; d.octs = nullptr; d.leaves = nullptr; d.node_data = nullptr;
   d.packed_version = 0; d.n_recs = 0;
   const size_t rb = std::max<size_t>(1, src.n_recs) * sizeof(uint4), lb = std::max<size_t>(1, src.n_leaves) * sizeof(uint32_t);
   YV_CUDA(cudaMalloc(&d.recs, rb));
-  YV_CUDA(cudaMalloc(&d.info, std::max<size_t>(1, src.n_recs) * sizeof(uint2)));
+  YV_CUDA(cudaMalloc(&d.octs, std::max<size_t>(1, src.n_recs) * sizeof(uint2)));
   YV_CUDA(cudaMalloc(&d.leaves, lb));
   if (src.node_data && src.n_recs) YV_CUDA(cudaMalloc(&d.node_data, src.n_recs * sizeof(uint32_t)));
   *needed = true;
@@ -91,7 +91,7 @@ int replicate_copy_async(yv_svo *svo, int src_dev, int dst_dev, cudaStream_t st,
   YV_CUDA(cudaSetDevice(dst_dev));
   uint64_t moved = 0;
   if (src.n_recs) { YV_CUDA(cudaMemcpyPeerAsync(d.recs, dst_dev, src.recs, src_dev, src.n_recs * sizeof(uint4), st)); moved += src.n_recs * sizeof(uint4); }
-  if (src.n_recs) { YV_CUDA(cudaMemcpyPeerAsync(d.info, dst_dev, src.info, src_dev, src.n_recs * sizeof(uint2), st)); moved += src.n_recs * sizeof(uint2); }
+  if (src.n_recs) { YV_CUDA(cudaMemcpyPeerAsync(d.octs, dst_dev, src.octs, src_dev, src.n_recs * sizeof(uint2), st)); moved += src.n_recs * sizeof(uint2); }
   if (src.n_leaves) { YV_CUDA(cudaMemcpyPeerAsync(d.leaves, dst_dev, src.leaves, src_dev, src.n_leaves * sizeof(uint32_t), st)); moved += src.n_leaves * sizeof(uint32_t); }
   if (d.node_data && src.node_data && src.n_recs) {
     YV_CUDA(cudaMemcpyPeerAsync(d.node_data, dst_dev, src.node_data, src_dev, src.n_recs * sizeof(uint32_t), st));
