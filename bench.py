@@ -323,7 +323,7 @@ def run_reference(a, rank):
         "setup": {"scene_file": vox, "scene_nodes": int(len(nodes)),
                   "scene_from": "written once by a separate process (SVOData.Save), loaded here by the oracle's .vox reader"},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -599,7 +599,7 @@ def run_single(a):
         del svo
         line["configs"] = run_extras(yv, torch, a, local)
     line["wall_s"] = round(time.time() - T_START, 1)
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -844,7 +844,7 @@ def run_strong_only(a):
     import yoxel_voxel_b200 as yv
     n = max(1, min(a.gpus, torch.cuda.device_count()))
     rec = run_strong_8k(yv, torch, a, n)
-    print(json.dumps({"strong_8k": rec, "wall_s": round(time.time() - T_START, 1)}))
+    emit({"strong_8k": rec, "wall_s": round(time.time() - T_START, 1)})
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -1186,12 +1186,28 @@ def run_ranks(a):
         "gpu_launches": a.steps * world * launches_per_step, "e2e_gpu_launches_per_step": r.LastFrameLaunches(),
         "parity": parity, "batch_1gpu": batch_1gpu, "strong_8k": strong, "wall_s": round(time.time() - T_START, 1),
     }
-    print(json.dumps(line))
+    emit(line)
     dist.barrier()
     dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The one JSON line, on the process's original stdout."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # stdout carries the one JSON line and nothing else: whatever a library prints to fd 1 (NCCL's version banner when the
+    # box sets NCCL_DEBUG, a loader message) goes to stderr; the line itself is written to a private copy of the original fd
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

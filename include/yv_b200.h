@@ -258,8 +258,9 @@ int yv_set_stream(yv_renderer *r, void *cuda_stream);
  *                 lanes of the warp are still traversing (-1 = only when the whole warp has drained)
  *   "zero_copy"   1 (default) = yv_render_frame's kernel stores its pixels straight into the pinned host frame
  *                 (device-addressable under UVA): the posted PCIe writes overlap the traversal, there is no copy and
- *                 no second launch. Frames that need a second pass over the image (Phong / show-normals / SSNA)
- *                 and 0 use the copy paths below
+ *                 no second launch. With a second pass over the image (Phong / show-normals / SSNA) the trace kernel
+ *                 draws in HBM and the pass that finishes the pixels stores them into the host frame. 0 = the copy
+ *                 paths below
  *   "pipeline"    with zero_copy 0: number of row chunks (2..8, default 4) yv_render_frame cuts the frame into:
  *                 chunks render on two alternating streams and each chunk's device->host copy overlaps the next
  *                 chunk's kernel; 0 or 1 = one launch, then one copy
@@ -269,8 +270,12 @@ int yv_set_stream(yv_renderer *r, void *cuda_stream);
  *   "stack"       where the traversal stack lives: 0 local memory, 4 = four-entry
  *                 shared-memory ring spilling to local memory
  *   "slots"       frames in flight for yv_render_frame_async (2..4, default 2)
+ *   "ssna_fused"  1 = SSNA's BlurZ x5 + ShadeSimple (demo/SVORenderer.cpp:126-147) run as one persistent cooperative
+ *                 launch that pulls 32x32 tiles from a counter per pass, grid barriers between the passes; 0 (default) =
+ *                 six launches. Same pixels; measured 0.863 vs 0.850 ms per SSNA frame on config 2 (the tile fetch and
+ *                 the barriers cost what the launch boundaries did), so it is an option, not the default.
  *   "cull"        1 = octant culling: a child node is entered only if one of the octants the ray can touch in it holds
- *                 anything (the occupancy of every child's octants rides in the parent's 16-byte record). Conservative, so
+ *                 anything (the occupancy of every child's octants: a side array next to the records). Conservative, so
  *                 hit ids, t and pixels are those of the reference traversal; node fetches drop by ~30 %, but lanes of a
  *                 warp stop descending in lock-step and the frame gets SLOWER (0.92 vs 0.70 ms on config 2,
  *                 profiles/README.md) — so 0 is the default: enter every child node the reference enters

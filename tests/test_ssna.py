@@ -230,6 +230,17 @@ def test_gpu_ssna_device_render_and_partition_errors():
         renderer.Render(dst.data_ptr())                                 # SVORenderer::Render(void* d_dstBuf)
         assert np.array_equal(dst.cpu().numpy(), host)
         assert renderer.LastFrameLaunches() == 7                        # trace (writes z itself) + 5 x BlurZ + ShadeSimple
+        renderer.SetOption("ssna_fused", 1)                             # the same passes as one persistent cooperative launch
+        try:
+            assert np.array_equal(_gpu_frame(renderer, OUTSIDE, W, H), host)
+            assert renderer.LastFrameLaunches() == 2                    # trace + ssna_post
+            for mode in (1, 2):                                         # ... on the other schedules (ssna_z_pass runs: + 1)
+                renderer.SetOption("persistent", mode)
+                assert np.array_equal(_gpu_frame(renderer, OUTSIDE, W, H), host)
+                assert renderer.LastFrameLaunches() == 3
+        finally:
+            renderer.SetOption("ssna_fused", 0)
+            renderer.SetOption("persistent", 0)
         renderer.SetOption("persistent", 1)                             # a schedule without the z epilogue: ssna_z_pass runs
         try:
             assert np.array_equal(_gpu_frame(renderer, OUTSIDE, W, H), host)

@@ -33,6 +33,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 
 #include "trace_core.cuh"
 
@@ -829,9 +830,7 @@ __global__ void __launch_bounds__(kCtaThreads, YV_MINBLOCKS) render_sec_queue(co
 // per hit pixel, this pass re-derives the ray and overwrites the pixel. Keeping it out of the trace kernel
 // costs that kernel no registers.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) shade_pass(const __grid_constant__ RenderParams p) {
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y = tile_row_y(p, blockIdx.y) + (threadIdx.x >> 5);      // the rows of this launch's band / blocks
+__device__ __forceinline__ void shade_pixel(const RenderParams &p, const float *__restrict__ zbuf, const int x, const int y) {
   if (x >= p.width || y >= p.y1) return;
   const uint32_t pixel = (uint32_t)y * (uint32_t)p.width + (uint32_t)x;
   uint32_t *dst = p.final_rgba ? p.final_rgba : p.out_rgba;
@@ -844,10 +843,10 @@ __global__ void __launch_bounds__(256) shade_pass(const __grid_constant__ Render
   float nx = 0.f, ny = 0.f, nz = 0.f, dx, dy, dz;
   bool have_n = false;                                    // the stored normal is unpacked only where SSNA has none to offer
   if (p.ssna) {                                           // normal from the blurred z-buffer (yv_format.h "SSNA")
-    const float z = p.zbuf[pixel];
+    const float z = zbuf[pixel];
     if (z != 0.0f) {
-      const float zr = x + 1 < p.width ? p.zbuf[pixel + 1] : 0.0f, zl = x > 0 ? p.zbuf[pixel - 1] : 0.0f;
-      const float zd = y + 1 < p.height ? p.zbuf[pixel + p.width] : 0.0f, zu = y > 0 ? p.zbuf[pixel - p.width] : 0.0f;
+      const float zr = x + 1 < p.width ? zbuf[pixel + 1] : 0.0f, zl = x > 0 ? zbuf[pixel - 1] : 0.0f;
+      const float zd = y + 1 < p.height ? zbuf[pixel + p.width] : 0.0f, zu = y > 0 ? zbuf[pixel - p.width] : 0.0f;
       const float ddx = abs_min_diff(zr != 0.0f, YV_FSUB(zr, z), zl != 0.0f, YV_FSUB(z, zl));
       const float ddy = abs_min_diff(zd != 0.0f, YV_FSUB(zd, z), zu != 0.0f, YV_FSUB(z, zu));
       const float nvx = YV_FMUL(YV_FMUL(p.d2, ddx), z);
@@ -880,6 +879,11 @@ __global__ void __launch_bounds__(256) shade_pass(const __grid_constant__ Render
     }
   }
   dst[pixel] = rgba;
+}
+
+__global__ void __launch_bounds__(256) shade_pass(const __grid_constant__ RenderParams p) {
+  // a CTA = 32x8 pixels of the rows of this launch's band / blocks
+  shade_pixel(p, p.zbuf, blockIdx.x * 32 + (threadIdx.x & 31), tile_row_y(p, blockIdx.y) + (threadIdx.x >> 5));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -917,17 +921,33 @@ __global__ void __launch_bounds__(256) ssna_z_pass(const __grid_constant__ Rende
 //                 (BlurParams::wsum, summed on the host in that order);
 //   * otherwise the tested form.
 constexpr int kBlurTile = 32, kBlurApron = YV_BLURZ_KERN / 2, kBlurSpan = kBlurTile + 2 * kBlurApron, kBlurRows = 4;
-__global__ void __launch_bounds__(256) blur_z_pass(const __grid_constant__ BlurParams b) {
-  __shared__ float tile[kBlurSpan][kBlurSpan + 1];
+#ifndef YV_POST_MINB
+#define YV_POST_MINB 6
+#endif
+#ifndef YV_BLUR_INLINE
+#define YV_BLUR_INLINE __forceinline__
+#endif
+typedef float BlurTile[kBlurSpan][kBlurSpan + 1];
+// one 32x32 output tile at (bx, by) by one 256-thread CTA; contains one __syncthreads, threads return at different points after it
+__device__ YV_BLUR_INLINE void blur_tile(const BlurParams &b, const float *__restrict__ src, float *__restrict__ dst, const float zlimit,
+                                          BlurTile &tile, const int bx, const int by) {
   const float kInvalid = __int_as_float(0x7f800000);
-  const int bx = blockIdx.x * kBlurTile, by = blockIdx.y * kBlurTile;
-  for (int i = threadIdx.x; i < kBlurSpan * kBlurSpan; i += 256) {
-    const int ty = i / kBlurSpan, tx = i - ty * kBlurSpan;
-    const int gx = bx + tx - kBlurApron, gy = by + ty - kBlurApron;
-    float v = 0.0f;                                       // outside the frame = invalid
-    if (gx >= 0 && gx < b.width && gy >= 0 && gy < b.height) v = b.src[(size_t)gy * b.width + gx];
-    tile[ty][tx] = v != 0.0f ? v : kInvalid;
+  // every thread runs the same number of trips (the last one predicated): with `i < span*span` as the loop condition the
+  // lanes of one warp leave the loop at different trips, and inside ssna_post's tile loop ptxas then emitted the barrier
+  // below without re-converging them first — the early lanes ran on into the taps while lanes 0-3 of warps 0-5 were
+  // still staging (compute-sanitizer racecheck; an out-of-range address through a clobbered uniform register)
+#pragma unroll
+  for (int k = 0; k < (kBlurSpan * kBlurSpan + 255) / 256; ++k) {
+    const int i = (int)threadIdx.x + 256 * k;
+    if (i < kBlurSpan * kBlurSpan) {
+      const int ty = i / kBlurSpan, tx = i - ty * kBlurSpan;
+      const int gx = bx + tx - kBlurApron, gy = by + ty - kBlurApron;
+      float v = 0.0f;                                     // outside the frame = invalid
+      if (gx >= 0 && gx < b.width && gy >= 0 && gy < b.height) v = src[(size_t)gy * b.width + gx];
+      tile[ty][tx] = v != 0.0f ? v : kInvalid;
+    }
   }
+  __syncwarp();
   __syncthreads();
   const int lx = threadIdx.x & 31, gx = bx + lx;
   const int ly = (threadIdx.x >> 5) * kBlurRows;           // first of this thread's four output rows
@@ -942,7 +962,7 @@ __global__ void __launch_bounds__(256) blur_z_pass(const __grid_constant__ BlurP
   if (__ballot_sync(kFullMask, any_valid) == 0u) {         // background warp
 #pragma unroll
     for (int j = 0; j < kBlurRows; ++j)
-      if (in_x && by + ly + j < b.height) b.dst[(size_t)(by + ly + j) * b.width + gx] = 0.0f;
+      if (in_x && by + ly + j < b.height) dst[(size_t)(by + ly + j) * b.width + gx] = 0.0f;
     return;
   }
   // range of everything this warp's taps can reach: tile rows ly .. ly+9, columns 0 .. 37
@@ -958,7 +978,7 @@ __global__ void __launch_bounds__(256) blur_z_pass(const __grid_constant__ BlurP
     mn = fminf(mn, __shfl_xor_sync(kFullMask, mn, o));
     mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, o));
   }
-  const bool smooth = YV_FSUB(mx, mn) < b.zlimit;           // false when anything is invalid (inf - x, inf - inf)
+  const bool smooth = YV_FSUB(mx, mn) < zlimit;           // false when anything is invalid (inf - x, inf - inf)
   if (smooth) {
 #pragma unroll
     for (int r = 0; r < kBlurRows + YV_BLURZ_KERN - 1; ++r) {
@@ -975,7 +995,7 @@ __global__ void __launch_bounds__(256) blur_z_pass(const __grid_constant__ BlurP
     }
 #pragma unroll
     for (int j = 0; j < kBlurRows; ++j)
-      if (in_x && by + ly + j < b.height) b.dst[(size_t)(by + ly + j) * b.width + gx] = YV_FDIV(acc[j], b.wsum);
+      if (in_x && by + ly + j < b.height) dst[(size_t)(by + ly + j) * b.width + gx] = YV_FDIV(acc[j], b.wsum);
     return;
   }
 #pragma unroll
@@ -990,7 +1010,7 @@ __global__ void __launch_bounds__(256) blur_z_pass(const __grid_constant__ BlurP
 #pragma unroll
       for (int kx = 0; kx < YV_BLURZ_KERN; ++kx) {
         const float w = b.taps[ky * YV_BLURZ_KERN + kx];
-        const bool ok = fabsf(YV_FSUB(zq[kx], zc[j])) < b.zlimit;
+        const bool ok = fabsf(YV_FSUB(zq[kx], zc[j])) < zlimit;
         acc[j] = ok ? YV_FADD(acc[j], YV_FMUL(w, zq[kx])) : acc[j];
         wacc[j] = ok ? YV_FADD(wacc[j], w) : wacc[j];
       }
@@ -1002,8 +1022,57 @@ __global__ void __launch_bounds__(256) blur_z_pass(const __grid_constant__ BlurP
     if (!in_x || gy >= b.height) continue;
     float out = 0.0f;
     if (zc[j] != kInvalid) out = wacc[j] > 0.0f ? YV_FDIV(acc[j], wacc[j]) : zc[j];
-    b.dst[(size_t)gy * b.width + gx] = out;
+    dst[(size_t)gy * b.width + gx] = out;
   }
+}
+
+__global__ void __launch_bounds__(256) blur_z_pass(const __grid_constant__ BlurParams b) {
+  __shared__ BlurTile tile;
+  blur_tile(b, b.src, b.dst, b.zlimit, tile, blockIdx.x * kBlurTile, blockIdx.y * kBlurTile);
+}
+
+// SSNA after the trace kernel as ONE persistent cooperative launch (round 2): the five BlurZ passes and the ShadeSimple pass
+// used to be six launches of 2040 equal-sized CTAs whose cost differs tenfold (background / smooth / tested tiles), each
+// with its own ramp and tail at 51 % of the issue slots. Here a grid that exactly fills the GPU pulls tiles from one
+// atomic counter per pass (cheap tiles no longer hold a slot for as long as expensive ones), passes are separated by a
+// grid barrier instead of a launch boundary, and the pixels are shaded by the same CTAs after the last barrier.
+// Arithmetic per pixel is blur_tile / shade_pixel unchanged.
+struct SsnaPostParams {
+  RenderParams p;                         // as for shade_pass; p.zbuf is set by the kernel
+  BlurParams b;                           // width, height, taps, wsum (src / dst / zlimit come from the fields below)
+  float *zbuf[2];                         // ping-pong; pass i reads zbuf[i & 1]
+  float zlimit[YV_BLURZ_PASSES];
+  unsigned int *counters;                 // [YV_BLURZ_PASSES], zero on entry, zero again on exit
+  int tiles_x, tiles_y;                   // 32x32 blur tiles
+};
+
+__global__ void __launch_bounds__(256, YV_POST_MINB) ssna_post(const __grid_constant__ SsnaPostParams q) {
+  __shared__ BlurTile tile;
+  __shared__ unsigned int s_next;
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const unsigned int ntiles = (unsigned int)(q.tiles_x * q.tiles_y);
+#pragma unroll 1
+  for (int pass = 0; pass < YV_BLURZ_PASSES; ++pass) {
+    const float *src = q.zbuf[pass & 1];
+    float *dst = q.zbuf[(pass & 1) ^ 1];
+    const float zlimit = q.zlimit[pass];
+    for (;;) {
+      __syncthreads();                                     // the previous tile's readers are done with `tile` and s_next
+      if (threadIdx.x == 0) s_next = atomicAdd(&q.counters[pass], 1u);
+      __syncthreads();
+      const unsigned int t = s_next;
+      if (t >= ntiles) break;
+      blur_tile(q.b, src, dst, zlimit, tile, (int)(t % (unsigned int)q.tiles_x) * kBlurTile, (int)(t / (unsigned int)q.tiles_x) * kBlurTile);
+    }
+    grid.sync();
+  }
+  if (blockIdx.x == 0 && threadIdx.x < YV_BLURZ_PASSES) q.counters[threadIdx.x] = 0u;      // for the next frame
+  // ShadeSimple with the normals of the blurred z-buffer (five passes: the result sits in zbuf[1])
+  const RenderParams &p = q.p;
+  const float *zfinal = q.zbuf[YV_BLURZ_PASSES & 1];
+  const int bw = (p.width + 31) / 32, bh = p.num_tiles / p.tiles_x;       // 32x8-pixel blocks over the rows of this launch
+  for (int blk = (int)blockIdx.x; blk < bw * bh; blk += (int)gridDim.x)
+    shade_pixel(p, zfinal, (blk % bw) * 32 + (threadIdx.x & 31), tile_row_y(p, blk / bw) + (threadIdx.x >> 5));
 }
 
 // ---------------------------------------------------------------------------------------------

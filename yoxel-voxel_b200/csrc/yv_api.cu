@@ -205,6 +205,7 @@ void free_frame_buffers(yv_renderer *r) {
   cudaFree(r->d_shade_rec); r->d_shade_rec = nullptr;
   cudaFree(r->d_zbuf[0]); cudaFree(r->d_zbuf[1]); r->d_zbuf[0] = r->d_zbuf[1] = nullptr;
   cudaFree(r->d_accum); r->d_accum = nullptr;
+  cudaFree(r->d_ssna_counters); r->d_ssna_counters = nullptr;
   r->d_hit_node = nullptr; r->d_hit_child = nullptr; r->d_hit_t = nullptr; r->d_counters = nullptr;
   r->fb_pixels = 0;
 }
@@ -541,21 +542,46 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
     for (int i = 0; i < YV_BLURZ_KERN * YV_BLURZ_KERN; ++i) b.wsum += b.taps[i];      // float, in tap order: what the tested form accumulates
     b.width = p.width; b.height = p.height;
     const float pixel_ang = (r->fov * (float)(3.14159265358979323846 / 180.0)) / (float)r->width;    // rp.pixelAng (:105)
+    float zlimit[YV_BLURZ_PASSES];
     float blur_size = 3;
-    int src = 0;
-    dim3 bgrid((p.width + yv::kBlurTile - 1) / yv::kBlurTile, (p.height + yv::kBlurTile - 1) / yv::kBlurTile);
-    for (int i = 0; i < YV_BLURZ_PASSES; ++i) {
-      b.zlimit = (5.0f * r->ssna_voxel_size) / (pixel_ang * blur_size);
-      b.src = r->d_zbuf[src]; b.dst = r->d_zbuf[1 - src];
-      yv::blur_z_pass<<<bgrid, 256, 0, r->stream>>>(b);
+    for (int i = 0; i < YV_BLURZ_PASSES; ++i, blur_size += 3) zlimit[i] = (5.0f * r->ssna_voxel_size) / (pixel_ang * blur_size);
+    const int tiles_x = (p.width + yv::kBlurTile - 1) / yv::kBlurTile, tiles_y = (p.height + yv::kBlurTile - 1) / yv::kBlurTile;
+    if (r->opt_ssna_fused) {
+      // BlurZ x5 + ShadeSimple as one persistent cooperative launch (render_kernels.cuh, ssna_post)
+      if (!r->d_ssna_counters) {
+        YV_CUDA(cudaMalloc(&r->d_ssna_counters, YV_BLURZ_PASSES * sizeof(unsigned int)));
+        YV_CUDA(cudaMemsetAsync(r->d_ssna_counters, 0, YV_BLURZ_PASSES * sizeof(unsigned int), r->stream));
+      }
+      if (r->ssna_post_grid == 0) {
+        int per_sm = 0;
+        YV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, yv::ssna_post, 256, 0));
+        r->ssna_post_grid = std::max(1, per_sm) * r->sm_count;
+      }
+      yv::SsnaPostParams q;
+      q.p = p; q.b = b; q.b.src = nullptr; q.b.dst = nullptr; q.b.zlimit = 0.0f;
+      q.zbuf[0] = r->d_zbuf[0]; q.zbuf[1] = r->d_zbuf[1];
+      for (int i = 0; i < YV_BLURZ_PASSES; ++i) q.zlimit[i] = zlimit[i];
+      q.counters = r->d_ssna_counters;
+      q.tiles_x = tiles_x; q.tiles_y = tiles_y;
+      const int grid = std::max(1, std::min(r->ssna_post_grid, tiles_x * tiles_y));
+      void *args[] = { (void *)&q };
+      YV_CUDA(cudaLaunchCooperativeKernel((const void *)yv::ssna_post, dim3((unsigned)grid), dim3(256), args, 0, r->stream));
       ++launches;
-      src = 1 - src;
-      blur_size += 3;
+    } else {
+      int src = 0;
+      dim3 bgrid(tiles_x, tiles_y);
+      for (int i = 0; i < YV_BLURZ_PASSES; ++i) {
+        b.zlimit = zlimit[i];
+        b.src = r->d_zbuf[src]; b.dst = r->d_zbuf[1 - src];
+        yv::blur_z_pass<<<bgrid, 256, 0, r->stream>>>(b);
+        ++launches;
+        src = 1 - src;
+      }
+      YV_CUDA(cudaGetLastError());
+      p.zbuf = r->d_zbuf[src];
     }
-    YV_CUDA(cudaGetLastError());
-    p.zbuf = r->d_zbuf[src];
   }
-  if ((p.shade_mode != 0 || ssna) && p.num_tiles > 0) {       // ShadeSimple pass over the rows this launch rendered
+  if ((p.shade_mode != 0 || ssna) && !(ssna && r->opt_ssna_fused) && p.num_tiles > 0) {       // ShadeSimple pass over the rows this launch rendered
     dim3 grid((p.width + 31) / 32, p.num_tiles / p.tiles_x);
     yv::shade_pass<<<grid, 256, 0, r->stream>>>(p);
     YV_CUDA(cudaGetLastError());
@@ -1282,6 +1308,7 @@ int yv_set_option(yv_renderer *r, const char *name, int value) {
   else if (n == "sec_queue") r->opt_sec_queue = value ? 1 : 0;
   else if (n == "sec_threshold") { if (value < -1 || value > 31) return fail(YV_ERR_ARG, "sec_threshold must be -1..31"); r->opt_sec_threshold = value; }
   else if (n == "zero_copy") r->opt_zero_copy = value != 0;
+  else if (n == "ssna_fused") r->opt_ssna_fused = value != 0;
   else if (n == "pipeline_taper") { if (value < 10 || value > 100) return fail(YV_ERR_ARG, "pipeline_taper must be 10..100 percent"); r->opt_pipeline_taper = value; }
   else if (n == "pipeline") { if (value < 0 || value > yv_renderer::kChunks) return fail(YV_ERR_ARG, "pipeline must be 0..8 chunks"); r->opt_pipeline = value; }
   else if (n == "layout") { if (value != 0 && value != 1) return fail(YV_ERR_ARG, "layout must be 0 (packed) or 1 (raw)"); r->opt_layout = value; }
@@ -1311,6 +1338,7 @@ int yv_get_option(const yv_renderer *r, const char *name, int *value) {
   else if (n == "pipeline") *value = r->opt_pipeline;
   else if (n == "pipeline_taper") *value = r->opt_pipeline_taper;
   else if (n == "zero_copy") *value = r->opt_zero_copy;
+  else if (n == "ssna_fused") *value = r->opt_ssna_fused;
   else if (n == "layout") *value = r->opt_layout;
   else if (n == "cull") *value = r->opt_cull;
   else if (n == "refill") *value = r->opt_refill;
