@@ -270,6 +270,9 @@ int yv_set_stream(yv_renderer *r, void *cuda_stream);
  *   "stack"       where the traversal stack lives: 0 local memory, 4 = four-entry
  *                 shared-memory ring spilling to local memory
  *   "slots"       frames in flight for yv_render_frame_async (2..4, default 2)
+ *   "group_threads" multi-device handles: 1 (default) = every peer GPU's share of a frame is issued by its own persistent
+ *                 host thread (SPURenderer's one thread per SPE, cell/spu_renderer.cpp:76-87), so the N launches start
+ *                 together; 0 = one loop on the calling thread (the launches of 8 GPUs then start ~18 us apart)
  *   "ssna_fused"  1 = SSNA's BlurZ x5 + ShadeSimple (demo/SVORenderer.cpp:126-147) run as one persistent cooperative
  *                 launch that pulls 32x32 tiles from a counter per pass, grid barriers between the passes; 0 (default) =
  *                 six launches. Same pixels; measured 0.863 vs 0.850 ms per SSNA frame on config 2 (the tile fetch and

@@ -78,6 +78,11 @@ def test_group_frame_equals_single_gpu_frame_and_oracle(single, devs, size):
                 assert (node == rn).all() and (child == rc).all() and t.tobytes() == rt.tobytes()
         ms = g.MemberFrameMs()
         assert len(ms) == len(devs) and all(m > 0 for m in ms) and g.LastFrameMs() > 0
+        assert g.GetOption("group_threads") == 1          # every peer's share is launched by its own host thread ...
+        g.SetOption("group_threads", 0)                   # ... or all of them by one loop on the calling thread
+        assert (g.RenderFrame() == ref).all()
+        g.SetOption("group_threads", 1)
+        assert (g.RenderFrame() == ref).all()
     finally:
         g.close()
 

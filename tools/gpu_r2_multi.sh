@@ -19,3 +19,11 @@ try:
     print("strong e2e", s.get("e2e")); print("one_gpu", s.get("one_gpu")); print("wall", j.get("wall_s"))
 except Exception as e: print("ERR", e)
 P
+echo "== host ingest ceiling"; timeout 120 python tools/host_ingest.py
+if [ "$N" == "2" ]; then
+echo "== ncu: NVLink bytes of the fused peer stores (small strong-only run, 2 GPUs, one process)"
+ncu --query-metrics 2>/dev/null | grep -i "nvl" | head -40 > gpurun_out/ncu_nvlink_metrics.txt
+timeout 600 ncu --devices 1 --metrics nvltx__bytes.sum,nvlrx__bytes.sum,gpu__time_duration.sum --clock-control none -k regex:render_frame -c 6 --csv --log-file gpurun_out/ncu_nvlink_n2.csv \
+    python bench.py --strong-only --gpus 2 --strong-depth 9 --strong-frames 2 --strong-width 1920 --strong-height 1088 > gpurun_out/ncu_nvlink_n2.log 2>&1 ; echo "rc=$?"
+head -5 gpurun_out/ncu_nvlink_metrics.txt; grep -c render_frame gpurun_out/ncu_nvlink_n2.csv
+fi

@@ -1309,6 +1309,7 @@ int yv_set_option(yv_renderer *r, const char *name, int value) {
   else if (n == "sec_threshold") { if (value < -1 || value > 31) return fail(YV_ERR_ARG, "sec_threshold must be -1..31"); r->opt_sec_threshold = value; }
   else if (n == "zero_copy") r->opt_zero_copy = value != 0;
   else if (n == "ssna_fused") r->opt_ssna_fused = value != 0;
+  else if (n == "group_threads") r->opt_group_threads = value != 0;
   else if (n == "pipeline_taper") { if (value < 10 || value > 100) return fail(YV_ERR_ARG, "pipeline_taper must be 10..100 percent"); r->opt_pipeline_taper = value; }
   else if (n == "pipeline") { if (value < 0 || value > yv_renderer::kChunks) return fail(YV_ERR_ARG, "pipeline must be 0..8 chunks"); r->opt_pipeline = value; }
   else if (n == "layout") { if (value != 0 && value != 1) return fail(YV_ERR_ARG, "layout must be 0 (packed) or 1 (raw)"); r->opt_layout = value; }
@@ -1339,6 +1340,7 @@ int yv_get_option(const yv_renderer *r, const char *name, int *value) {
   else if (n == "pipeline_taper") *value = r->opt_pipeline_taper;
   else if (n == "zero_copy") *value = r->opt_zero_copy;
   else if (n == "ssna_fused") *value = r->opt_ssna_fused;
+  else if (n == "group_threads") *value = r->opt_group_threads;
   else if (n == "layout") *value = r->opt_layout;
   else if (n == "cull") *value = r->opt_cull;
   else if (n == "refill") *value = r->opt_refill;

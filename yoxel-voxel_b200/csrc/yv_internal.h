@@ -155,6 +155,10 @@ struct yv_renderer {
   std::vector<yv_renderer *> peers;
   yv_renderer *leader = nullptr;      // set on peers
   bool peer_access = true;            // every member can store into the leader's HBM (NVLink / PCIe P2P)
+  void *worker = nullptr;             // peers: the host thread that issues this member's launches (yv_multi.cu, MemberWorker) —
+                                      // SPURenderer's one thread per SPE (cell/spu_renderer.cpp:76-87)
+  int opt_group_threads = 1;          // leader: 1 = every peer's share is launched by its own host thread, concurrently;
+                                      // 0 = one loop on the calling thread (the launches of 8 GPUs then start ~18 us apart)
   int part_rows = 32;                 // rows per interleaved block (multiple of 16)
   int part_mode = 0;                  // 0 = interleaved blocks, 1 = contiguous bands
   cudaEvent_t ev_join = nullptr;      // on a peer: its share of the frame (and its copy) is done

@@ -19,13 +19,65 @@
 // No collective library is involved: the frame shards into disjoint pixels and the only exchange is the final store.
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <thread>
 
 #include "yv_internal.h"
 
 using namespace yvi;
 
 namespace {
+
+// One host thread per peer GPU, alive as long as the peer (the reference starts one thread per SPE for every frame,
+// cell/spu_renderer.cpp:76-87; here the threads persist and a frame costs them one condition-variable round trip).
+// Issued from one loop, the launches of 8 GPUs start ~18 us apart (cudaSetDevice, events, parameter set-up, launch),
+// which at 8K / 8 GPUs is 15 % of a member's 0.84 ms share; issued by 8 threads they start together.
+struct MemberWorker {
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::function<int()> job;
+  bool has_job = false, done = true, quit = false;
+  int rc = 0;
+  std::string err;
+  MemberWorker() {
+    th = std::thread([this] {
+      for (;;) {
+        std::function<int()> j;
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [this] { return has_job || quit; });
+          if (quit) return;
+          j = std::move(job); has_job = false;
+        }
+        int r;
+        std::string e;
+        try { r = j(); if (r) e = yv_last_error(); }
+        catch (const std::exception &ex) { r = YV_ERR_CUDA; e = ex.what(); }
+        catch (...) { r = YV_ERR_CUDA; e = "exception in a member launch"; }
+        { std::lock_guard<std::mutex> lk(mu); rc = r; err = e; done = true; }
+        cv.notify_all();
+      }
+    });
+  }
+  void submit(std::function<int()> j) {
+    { std::lock_guard<std::mutex> lk(mu); job = std::move(j); has_job = true; done = false; }
+    cv.notify_all();
+  }
+  int wait(std::string &why) {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [this] { return done; });
+    why = err;
+    return rc;
+  }
+  ~MemberWorker() {
+    { std::lock_guard<std::mutex> lk(mu); quit = true; }
+    cv.notify_all();
+    if (th.joinable()) th.join();
+  }
+};
 
 // the partition of member k of n: interleaved blocks (default) or contiguous bands of rows rounded to the tile height
 void set_partition(yv_renderer *lead, yv_renderer *m, int k, int n) {
@@ -226,6 +278,7 @@ void free_slots(yv_renderer *r) {
 }
 
 void group_destroy_peers(yv_renderer *r) {
+  for (yv_renderer *p : r->peers) { delete static_cast<MemberWorker *>(p->worker); p->worker = nullptr; }
   for (yv_renderer *p : r->peers) { p->leader = nullptr; yv_renderer_destroy(p); }
   r->peers.clear();
 }
@@ -242,30 +295,53 @@ int group_launch(yv_renderer *r, void *target, bool staged, int slot, cudaStream
   YV_CUDA(cudaSetDevice(r->device));
   YV_CUDA(cudaEventRecord(r->ev0, r->stream));
   YV_CUDA(cudaEventRecord(r->ev_fork, r->stream));          // peers start after whatever precedes the frame on the leader
-  int launches = 0;
-  for (int k = 0; k < n && rc == YV_OK; ++k) {
+  // member k's share: its kernel(s) on its own stream, then (staged) its rows on its copy engine; ev_join marks the end
+  std::vector<int> member_launches((size_t)n, 0);
+  auto member_job = [&](int k) -> int {
     yv_renderer *m = group_member(r, k);
     YV_CUDA(cudaSetDevice(m->device));
     if (k > 0) YV_CUDA(cudaStreamWaitEvent(m->stream, r->ev_fork, 0));
     uint32_t *local = slot >= 0 ? m->slots[slot].d_fb : m->d_fb;
     m->suppress_events = true;
     YV_CUDA(cudaEventRecord(m->ev_own0, m->stream));
-    rc = launch_frame(m, staged ? (void *)local : target);
+    const int mrc = launch_frame(m, staged ? (void *)local : target);
     m->suppress_events = false;
-    if (rc) break;
+    if (mrc) return mrc;
     YV_CUDA(cudaEventRecord(m->ev_own1, m->stream));
     m->own_timed = true;
-    launches += m->last_launches;
+    member_launches[(size_t)k] = m->last_launches;
     cudaStream_t tail = m->stream;
     if (staged) {                                            // this member's rows: its HBM -> the frame, on its copy engine
       YV_CUDA(cudaEventRecord(m->ev_copy, m->stream));
       YV_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_copy, 0));
-      rc = copy_member_rows(r, k, n, target, local, m->copy_stream);
-      if (rc) break;
+      const int crc = copy_member_rows(r, k, n, target, local, m->copy_stream);
+      if (crc) return crc;
       tail = m->copy_stream;
     }
     if (k > 0) YV_CUDA(cudaEventRecord(m->ev_join, tail));
+    return YV_OK;
+  };
+  const bool threaded = r->opt_group_threads != 0 && n > 1;
+  std::string why;
+  if (threaded) {                                            // peers on their own threads, the leader's share on this one
+    for (int k = 1; k < n; ++k) {
+      yv_renderer *m = group_member(r, k);
+      if (!m->worker) m->worker = new MemberWorker();
+      static_cast<MemberWorker *>(m->worker)->submit([&member_job, k] { return member_job(k); });
+    }
+    rc = member_job(0);
+    if (rc) why = yv_last_error();
+    for (int k = 1; k < n; ++k) {
+      std::string w;
+      const int wrc = static_cast<MemberWorker *>(group_member(r, k)->worker)->wait(w);
+      if (wrc && !rc) { rc = wrc; why = w; }
+    }
+    if (rc) fail(rc, why);                                   // the message of the member that failed, on this thread
+  } else {
+    for (int k = 0; k < n && rc == YV_OK; ++k) rc = member_job(k);
   }
+  int launches = 0;
+  for (int k = 0; k < n; ++k) launches += member_launches[(size_t)k];
   for (int k = 0; k < n; ++k) clear_partition(group_member(r, k));
   if (rc) { for (int k = 0; k < n; ++k) { cudaSetDevice(group_member(r, k)->device); cudaDeviceSynchronize(); } return rc; }
   YV_CUDA(cudaSetDevice(r->device));
