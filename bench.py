@@ -1079,6 +1079,65 @@ def run_ranks(a):
                "api": "yv_set_view_* + yv_render_frame_device into one pinned host %s shared by the ranks (yv_host_register): "
                       "every GPU stores its pixels over its own PCIe link" % ("frame" if tiles_mode else "batch of %d frames" % world),
                "identical_to_nvlink_gathered": same}
+        if not tiles_mode:
+            # the same batch with frames in flight: every rank keeps three frames outstanding (yv_render_frame_async /
+            # yv_wait_frame), drawn in HBM and moved to renderer-owned pinned host frames by the GPU's copy engine while the
+            # next frame traverses. No barrier and no L2 flush inside the timed region (the kernel is insensitive to it:
+            # profiles/README.md); barrier + synchronize on both sides, max over ranks.
+            # (collectives stay outside the try blocks: a rank that fails still meets the others at every barrier / reduce)
+            pipe_ok, pipe_t, same_local, pipe_err = 1, 0.0, 0, ""
+            try:
+                r.SetOption("slots", 3)
+                r.SetOption("zero_copy", 0)
+            except Exception as ex:
+                pipe_ok, pipe_err = 0, "%s: %s" % (type(ex).__name__, ex)
+            for rep in range(2):                                       # the first repetition warms the slots up
+                torch.cuda.synchronize()
+                dist.barrier()
+                if not pipe_ok:
+                    continue
+                try:
+                    t0 = time.perf_counter()
+                    tickets, last_ptr = [], None
+                    for i in range(a.steps):
+                        fpos, fdir = camera_for(frame_of(i), a.scene)
+                        r.SetViewPos(fpos); r.SetViewDir(fdir); r.SetViewUp(UP); r.SetFOV(FOV)
+                        tickets.append(r.RenderFrameAsync())
+                        if len(tickets) == 3:
+                            last_ptr = r.WaitFrame(tickets.pop(0), as_array=False)
+                    while tickets:
+                        last_ptr = r.WaitFrame(tickets.pop(0), as_array=False)
+                    pipe_t = time.perf_counter() - t0
+                    if rep == 1:
+                        # the last frame delivered this way == the frame this rank stored into the shared batch (same camera)
+                        last_img = np.frombuffer((ctypes.c_uint8 * frame_bytes).from_address(last_ptr), np.uint8)
+                        mine = np.frombuffer((ctypes.c_uint8 * frame_bytes).from_address(h_dst), np.uint8)
+                        same_local = 1 if bool((mine == last_img).all()) else 0
+                except Exception as ex:
+                    pipe_ok, pipe_err = 0, "%s: %s" % (type(ex).__name__, ex)
+            try:
+                r.SetOption("zero_copy", 1)
+            except Exception:
+                pass
+            ps = torch.tensor([pipe_t], dtype=torch.float64, device=dev)
+            dist.all_reduce(ps, op=dist.ReduceOp.MAX)
+            okp = torch.tensor([pipe_ok, same_local], device=dev)
+            dist.all_reduce(okp, op=dist.ReduceOp.MIN)
+            sync_val = e2e["value"]
+            e2e["sync"] = {"value": sync_val, "ms_per_step": e2e["ms_per_step"],
+                           "what": "one synchronous call per step, kernels store into the shared host batch, barrier per step"}
+            if int(okp[0].item()) == 1 and float(ps.item()) > 0:
+                e2e["frames_in_flight"] = {"value": rays_all / float(ps.item()) / 1e6, "ms_per_step": 1e3 * float(ps.item()) / a.steps,
+                                           "identical_to_sync_delivery": bool(int(okp[1].item()) == 1),
+                                           "what": "3 frames outstanding per GPU, copy-engine delivery into renderer-owned pinned "
+                                                   "host frames, no barrier or L2 flush inside the timed region"}
+                if e2e["frames_in_flight"]["value"] > sync_val and e2e["frames_in_flight"]["identical_to_sync_delivery"]:
+                    e2e["value"] = e2e["frames_in_flight"]["value"]
+                    e2e["ms_per_step"] = e2e["frames_in_flight"]["ms_per_step"]
+                    e2e["api"] = ("yv_set_view_* + yv_render_frame_async / yv_wait_frame per rank, 3 frames in flight, copy-engine "
+                                  "delivery into pinned host frames (the synchronous shared-batch form is in `sync`)")
+            else:
+                e2e["frames_in_flight"] = {"error": pipe_err or "failed on another rank"}
     if shared is not None:
         dist.barrier()
         shared.close()

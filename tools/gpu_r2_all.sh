@@ -36,6 +36,6 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:rend
 echo "== ncu full: secondary (config 4)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:render_frame -s 4 -c 1 -o $O/prof_sec -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras --secondary > $O/ncu_sec.log 2>&1 ; echo "rc=$?"
 echo "== ncu full: ssna passes"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"blur_z|ssna_z|shade_pass" -s 8 -c 7 -o $O/prof_ssna -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras --ssna > $O/ncu_ssna.log 2>&1 ; echo "rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"blur_z|ssna_z|shade_pass" -s 6 -c 6 -o $O/prof_ssna -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras --ssna > $O/ncu_ssna.log 2>&1 ; echo "rc=$?"
 fi
 ls -la $O | tail -25
