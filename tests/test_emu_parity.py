@@ -128,6 +128,10 @@ def test_lod_cutoff(coef):
         e = yve.render(recs, leaves, 1, pos, d0, du, dv, pos, W, H, detail=float(detail), node_data=node_data)
         assert (o["node"] == e["node"]).all() and (o["child"] == e["child"]).all()
         assert o["t"].tobytes() == e["t"].tobytes() and (o["rgba"] == e["rgba"]).all()
+        # ... and with the closed-form descent in front (the level travels in the stack word; the cut-off cannot fire there)
+        f = yve.render(recs, leaves, 1, pos, d0, du, dv, pos, W, H, detail=float(detail), node_data=node_data, mode=5)
+        assert (f["node"] == e["node"]).all() and (f["child"] == e["child"]).all() and f["t"].tobytes() == e["t"].tobytes()
+        assert (f["rgba"] == e["rgba"]).all() and f["visits"] == e["visits"] and f["fetches"] == e["fetches"]
         lod = (o["child"] == -1) & (o["node"] != yvo.MISS_NODE)
         n_lod += int(lod.sum())
         if lod.any():
