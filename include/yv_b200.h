@@ -273,16 +273,12 @@ int yv_set_stream(yv_renderer *r, void *cuda_stream);
  *   "group_threads" multi-device handles: 1 (default) = every peer GPU's share of a frame is issued by its own persistent
  *                 host thread (SPURenderer's one thread per SPE, cell/spu_renderer.cpp:76-87), so the N launches start
  *                 together; 0 = one loop on the calling thread (the launches of 8 GPUs then start ~18 us apart)
- *   "ssna_fused"  1 = SSNA's BlurZ x5 + ShadeSimple (demo/SVORenderer.cpp:126-147) run as one persistent cooperative
- *                 launch that pulls 32x32 tiles from a counter per pass, grid barriers between the passes; 0 (default) =
- *                 six launches. Same pixels; measured 0.863 vs 0.850 ms per SSNA frame on config 2 (the tile fetch and
- *                 the barriers cost what the launch boundaries did), so it is an option, not the default.
- *   "cull"        1 = octant culling: a child node is entered only if one of the octants the ray can touch in it holds
- *                 anything (the occupancy of every child's octants: a side array next to the records). Conservative, so
- *                 hit ids, t and pixels are those of the reference traversal; node fetches drop by ~30 %, but lanes of a
- *                 warp stop descending in lock-step and the frame gets SLOWER (0.92 vs 0.70 ms on config 2,
- *                 profiles/README.md) — so 0 is the default: enter every child node the reference enters
- *                 (cell/ppu_renderer.cpp:35); yv_get_counters then returns exactly the reference's node-fetch counts.
+ *   "ssna_fused"  SSNA's BlurZ x5 + ShadeSimple (demo/SVORenderer.cpp:126-147) as ONE persistent cooperative launch that
+ *                 pulls 32x32 tiles from a counter per pass, grid barriers between the passes: 1 = with the next tile
+ *                 prefetched into a second shared-memory buffer by a 2-D TMA load (needs width % 4 == 0, else as 2),
+ *                 2 = with plain staging loads; 0 (default) = six launches. Same pixels in all three; measured per SSNA
+ *                 frame on config 2: 0.841 (six launches) / 0.846 (TMA) / 0.861 ms (plain) — the grid barriers and the
+ *                 per-tile hand-shake cost what the launch boundaries did, so the fused forms stay options.
  *                 Packed layout, local stack, no staging. */
 int yv_set_option(yv_renderer *r, const char *name, int value);
 int yv_get_option(const yv_renderer *r, const char *name, int *value);

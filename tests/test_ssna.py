@@ -189,6 +189,11 @@ def test_gpu_ssna_matches_oracle(renderer, mode, size):
         o = yvo.render(svo.nodes(), svo.GetRoot(), _cam(spec, W, H, **kw), threads=8)
         assert np.abs(img.astype(int) - o["rgba"].astype(int)).max() <= 1
         assert (img == o["rgba"]).all(), "%d pixels differ" % (img != o["rgba"]).any(-1).sum()
+        for fused in (1, 2):                                            # ssna_post: TMA-prefetched tiles / plain staging
+            renderer.SetOption("ssna_fused", fused)
+            again = _gpu_frame(renderer, spec, W, H)
+            renderer.SetOption("ssna_fused", 0)
+            assert (again == img).all(), "ssna_fused %d: %d pixels differ" % (fused, (again != img).any(-1).sum())
         renderer.SetSSNA(False)
         plain = _gpu_frame(renderer, spec, W, H)
         assert (plain != img).any() and np.array_equal(plain[..., 3], img[..., 3])
@@ -230,14 +235,23 @@ def test_gpu_ssna_device_render_and_partition_errors():
         renderer.Render(dst.data_ptr())                                 # SVORenderer::Render(void* d_dstBuf)
         assert np.array_equal(dst.cpu().numpy(), host)
         assert renderer.LastFrameLaunches() == 7                        # trace (writes z itself) + 5 x BlurZ + ShadeSimple
-        renderer.SetOption("ssna_fused", 1)                             # the same passes as one persistent cooperative launch
         try:
-            assert np.array_equal(_gpu_frame(renderer, OUTSIDE, W, H), host)
-            assert renderer.LastFrameLaunches() == 2                    # trace + ssna_post
+            for fused in (1, 2):                                        # the same passes as one persistent cooperative launch:
+                renderer.SetOption("ssna_fused", fused)                 # 1 = tiles prefetched by TMA, 2 = plain staging loads
+                assert np.array_equal(_gpu_frame(renderer, OUTSIDE, W, H), host)
+                assert renderer.LastFrameLaunches() == 2                # trace + ssna_post
+                assert np.array_equal(_gpu_frame(renderer, OUTSIDE, W, H), host)     # ... again: the tile counters were reset
+            renderer.SetOption("ssna_fused", 1)
             for mode in (1, 2):                                         # ... on the other schedules (ssna_z_pass runs: + 1)
                 renderer.SetOption("persistent", mode)
                 assert np.array_equal(_gpu_frame(renderer, OUTSIDE, W, H), host)
                 assert renderer.LastFrameLaunches() == 3
+            renderer.SetOption("persistent", 0)
+            for (w2, h2) in ((333, 217), (644, 36), (1000, 500)):       # a row pitch that is no 16-byte multiple (no TMA), odd shapes
+                renderer.SetOption("ssna_fused", 0)
+                want = _gpu_frame(renderer, OUTSIDE, w2, h2)
+                renderer.SetOption("ssna_fused", 1)
+                assert np.array_equal(_gpu_frame(renderer, OUTSIDE, w2, h2), want), (w2, h2)
         finally:
             renderer.SetOption("ssna_fused", 0)
             renderer.SetOption("persistent", 0)

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Key metrics of an .ncu-rep (first kernel instance per report): time, DRAM/L2 traffic, occupancy,
+"""Key metrics of an .ncu-rep (first instance of every distinct kernel in the report): time, DRAM/L2 traffic, occupancy,
 SIMD efficiency, issue utilisation and the warp-stall breakdown. Usage: ncu_summary.py rep [rep...]"""
 import csv
 import io
@@ -43,9 +43,13 @@ def summarize(rep):
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
-    res = []
-    for r in rows[2:3]:
-        res.append("kernel: " + r[hdr.index("Kernel Name")][:100])
+    res, seen = [], set()
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")]
+        if name in seen:
+            continue
+        seen.add(name)
+        res.append("kernel: " + name[:100])
         for key, name in WANT:
             if key in hdr:
                 i = hdr.index(key)

@@ -32,6 +32,7 @@
 // them (PERSISTENT refill, render_queue, render_sec_queue) executes fewer instructions and still loses.
 #pragma once
 
+#include <cuda.h>                      // CUtensorMap (types only: the encode function is fetched through the runtime)
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
 
@@ -948,6 +949,10 @@ constexpr int kBlurTile = 32, kBlurApron = YV_BLURZ_KERN / 2, kBlurSpan = kBlurT
 #define YV_BLUR_INLINE __forceinline__
 #endif
 typedef float BlurTile[kBlurSpan][kBlurSpan + 1];
+template <int PITCH, int XOFF>
+__device__ YV_BLUR_INLINE void blur_compute(const BlurParams &b, float *__restrict__ dst, const float zlimit,
+                                            const float (&tile)[kBlurSpan][PITCH], const int bx, const int by);
+
 // one 32x32 output tile at (bx, by) by one 256-thread CTA; contains one __syncthreads, threads return at different points after it
 __device__ YV_BLUR_INLINE void blur_tile(const BlurParams &b, const float *__restrict__ src, float *__restrict__ dst, const float zlimit,
                                           BlurTile &tile, const int bx, const int by) {
@@ -969,13 +974,22 @@ __device__ YV_BLUR_INLINE void blur_tile(const BlurParams &b, const float *__res
   }
   __syncwarp();
   __syncthreads();
+  blur_compute<kBlurSpan + 1, 0>(b, dst, zlimit, tile, bx, by);
+}
+
+// the taps of one staged tile (invalid pixels hold +inf; tile column XOFF is frame column bx - 3); no barrier inside,
+// threads return at different points
+template <int PITCH, int XOFF>
+__device__ YV_BLUR_INLINE void blur_compute(const BlurParams &b, float *__restrict__ dst, const float zlimit,
+                                            const float (&tile)[kBlurSpan][PITCH], const int bx, const int by) {
+  const float kInvalid = __int_as_float(0x7f800000);
   const int lx = threadIdx.x & 31, gx = bx + lx;
   const int ly = (threadIdx.x >> 5) * kBlurRows;           // first of this thread's four output rows
   float zc[kBlurRows], acc[kBlurRows], wacc[kBlurRows];
   bool any_valid = false;
 #pragma unroll
   for (int j = 0; j < kBlurRows; ++j) {
-    zc[j] = tile[ly + j + kBlurApron][lx + kBlurApron]; acc[j] = 0.0f; wacc[j] = 0.0f;
+    zc[j] = tile[ly + j + kBlurApron][lx + kBlurApron + XOFF]; acc[j] = 0.0f; wacc[j] = 0.0f;
     any_valid = any_valid || zc[j] != kInvalid;            // outputs outside the frame were staged invalid
   }
   const bool in_x = gx < b.width;
@@ -989,9 +1003,9 @@ __device__ YV_BLUR_INLINE void blur_tile(const BlurParams &b, const float *__res
   float mn = kInvalid, mx = -kInvalid;
 #pragma unroll
   for (int r = 0; r < kBlurRows + YV_BLURZ_KERN - 1; ++r) {
-    const float v = tile[ly + r][lx];
+    const float v = tile[ly + r][lx + XOFF];
     mn = fminf(mn, v); mx = fmaxf(mx, v);
-    if (lx < 2 * kBlurApron) { const float u = tile[ly + r][kBlurTile + lx]; mn = fminf(mn, u); mx = fmaxf(mx, u); }
+    if (lx < 2 * kBlurApron) { const float u = tile[ly + r][kBlurTile + lx + XOFF]; mn = fminf(mn, u); mx = fmaxf(mx, u); }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -1004,7 +1018,7 @@ __device__ YV_BLUR_INLINE void blur_tile(const BlurParams &b, const float *__res
     for (int r = 0; r < kBlurRows + YV_BLURZ_KERN - 1; ++r) {
       float zq[YV_BLURZ_KERN];
 #pragma unroll
-      for (int kx = 0; kx < YV_BLURZ_KERN; ++kx) zq[kx] = tile[ly + r][lx + kx];
+      for (int kx = 0; kx < YV_BLURZ_KERN; ++kx) zq[kx] = tile[ly + r][lx + kx + XOFF];
 #pragma unroll
       for (int j = 0; j < kBlurRows; ++j) {
         const int ky = r - j;
@@ -1022,7 +1036,7 @@ __device__ YV_BLUR_INLINE void blur_tile(const BlurParams &b, const float *__res
   for (int r = 0; r < kBlurRows + YV_BLURZ_KERN - 1; ++r) {           // tile row ly + r feeds output j as tap row ky = r - j
     float zq[YV_BLURZ_KERN];
 #pragma unroll
-    for (int kx = 0; kx < YV_BLURZ_KERN; ++kx) zq[kx] = tile[ly + r][lx + kx];
+    for (int kx = 0; kx < YV_BLURZ_KERN; ++kx) zq[kx] = tile[ly + r][lx + kx + XOFF];
 #pragma unroll
     for (int j = 0; j < kBlurRows; ++j) {
       const int ky = r - j;
@@ -1051,12 +1065,10 @@ __global__ void __launch_bounds__(256) blur_z_pass(const __grid_constant__ BlurP
   blur_tile(b, b.src, b.dst, b.zlimit, tile, blockIdx.x * kBlurTile, blockIdx.y * kBlurTile);
 }
 
-// SSNA after the trace kernel as ONE persistent cooperative launch (round 2): the five BlurZ passes and the ShadeSimple pass
-// used to be six launches of 2040 equal-sized CTAs whose cost differs tenfold (background / smooth / tested tiles), each
-// with its own ramp and tail at 51 % of the issue slots. Here a grid that exactly fills the GPU pulls tiles from one
-// atomic counter per pass (cheap tiles no longer hold a slot for as long as expensive ones), passes are separated by a
-// grid barrier instead of a launch boundary, and the pixels are shaded by the same CTAs after the last barrier.
-// Arithmetic per pixel is blur_tile / shade_pixel unchanged.
+constexpr int kTmaPitch = kBlurSpan + 2;            // the TMA box is 40 x 38 floats: its inner extent must be a multiple of 16 bytes,
+constexpr int kTmaXoff = 1;                         // and so must its start: the box begins at column bx - 4 (an unaligned inner
+                                                    // coordinate is an illegal-instruction fault), tile column 1 = frame column bx - 3
+constexpr unsigned kTmaTileBytes = kBlurSpan * kTmaPitch * sizeof(float);
 struct SsnaPostParams {
   RenderParams p;                         // as for shade_pass; p.zbuf is set by the kernel
   BlurParams b;                           // width, height, taps, wsum (src / dst / zlimit come from the fields below)
@@ -1064,27 +1076,123 @@ struct SsnaPostParams {
   float zlimit[YV_BLURZ_PASSES];
   unsigned int *counters;                 // [YV_BLURZ_PASSES], zero on entry, zero again on exit
   int tiles_x, tiles_y;                   // 32x32 blur tiles
+  alignas(64) CUtensorMap tmap[2];        // 2-D maps of zbuf[0] / zbuf[1], box 40 x 38, out-of-frame elements read as 0
 };
 
+// ---- TMA / mbarrier plumbing (PTX: cp.async.bulk.tensor, mbarrier) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}"
+      :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one 2-D tile: box corner (x, y) in elements, may lie outside the tensor (those elements arrive as zeros)
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int x, int y, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               :: "r"(smem_u32(smem_dst)), "l"((unsigned long long)map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// ssna_post: the five BlurZ passes and the ShadeSimple pass as ONE persistent cooperative launch. A grid that exactly fills
+// the GPU pulls 32x32 tiles from one atomic counter per pass, passes are separated by grid barriers, the pixels are shaded
+// by the same CTAs after the last barrier. With use_tma the staging of a tile — 38 % of a BlurZ pass's stall samples sit on
+// the global -> shared copy in front of the barrier (profiles/r02_prof_ssna.lines.txt) — is taken off the critical path:
+// one thread issues a 2-D TMA load of the NEXT tile into the other shared-memory buffer (the hardware fills what lies
+// outside the frame with zeros, completion is counted on an mbarrier) while the CTA computes the current one.
+// Arithmetic per pixel is blur_compute / shade_pixel unchanged.
+template <bool TMA>
 __global__ void __launch_bounds__(256, YV_POST_MINB) ssna_post(const __grid_constant__ SsnaPostParams q) {
-  __shared__ BlurTile tile;
-  __shared__ unsigned int s_next;
+  // TMA destinations / the plain tile; every buffer starts on a 128-byte boundary (38 * 40 * 4 = 6080 bytes is no multiple)
+  constexpr int kTileFloats = (kBlurSpan * kTmaPitch + 31) / 32 * 32;
+  __shared__ alignas(128) float tile_mem[TMA ? 2 : 1][kTileFloats];
+  typedef float TmaTile[kBlurSpan][kTmaPitch];
+  __shared__ alignas(8) unsigned long long mbar[2];
+  __shared__ unsigned int s_next[2];
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   const unsigned int ntiles = (unsigned int)(q.tiles_x * q.tiles_y);
+  const unsigned int tx_n = (unsigned int)q.tiles_x;
+  const float kInvalid = __int_as_float(0x7f800000);
+  if (TMA) {
+    if (threadIdx.x == 0) {
+      mbar_init(&mbar[0], 1u); mbar_init(&mbar[1], 1u);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  unsigned int phase0 = 0u, phase1 = 0u;                   // parity of the next completion of mbar[0] / mbar[1]
 #pragma unroll 1
   for (int pass = 0; pass < YV_BLURZ_PASSES; ++pass) {
     const float *src = q.zbuf[pass & 1];
     float *dst = q.zbuf[(pass & 1) ^ 1];
     const float zlimit = q.zlimit[pass];
-    for (;;) {
-      __syncthreads();                                     // the previous tile's readers are done with `tile` and s_next
-      if (threadIdx.x == 0) s_next = atomicAdd(&q.counters[pass], 1u);
+    if (TMA) {
+      const CUtensorMap *map = &q.tmap[pass & 1];
+      // prologue: this CTA's first tile of the pass
+      if (threadIdx.x == 0) {
+        const unsigned int t0 = atomicAdd(&q.counters[pass], 1u);
+        s_next[0] = t0;
+        if (t0 < ntiles) {
+          fence_proxy_async();
+          mbar_expect_tx(&mbar[0], kTmaTileBytes);
+          tma_load_2d(&tile_mem[0][0], map, (int)(t0 % tx_n) * kBlurTile - kBlurApron - kTmaXoff, (int)(t0 / tx_n) * kBlurTile - kBlurApron, &mbar[0]);
+        }
+      }
       __syncthreads();
-      const unsigned int t = s_next;
-      if (t >= ntiles) break;
-      blur_tile(q.b, src, dst, zlimit, tile, (int)(t % (unsigned int)q.tiles_x) * kBlurTile, (int)(t / (unsigned int)q.tiles_x) * kBlurTile);
+      unsigned int t = s_next[0];
+      int buf = 0;
+      while (t < ntiles) {
+        // the next tile's load goes out before this one is touched; its buffer was last read before barrier (B) below
+        if (threadIdx.x == 0) {
+          const unsigned int t2 = atomicAdd(&q.counters[pass], 1u);
+          s_next[buf ^ 1] = t2;
+          if (t2 < ntiles) {
+            fence_proxy_async();
+            mbar_expect_tx(&mbar[buf ^ 1], kTmaTileBytes);
+            tma_load_2d(&tile_mem[buf ^ 1][0], map, (int)(t2 % tx_n) * kBlurTile - kBlurApron - kTmaXoff, (int)(t2 / tx_n) * kBlurTile - kBlurApron, &mbar[buf ^ 1]);
+          }
+        }
+        mbar_wait(&mbar[buf], buf ? phase1 : phase0);
+        if (buf) phase1 ^= 1u; else phase0 ^= 1u;
+        // invalid pixels (0 in the z-buffer, and everything the TMA filled in outside the frame) become +inf
+        float *flat = &tile_mem[buf][0];
+#pragma unroll
+        for (int k = 0; k < (kBlurSpan * kTmaPitch + 255) / 256; ++k) {
+          const int i = (int)threadIdx.x + 256 * k;
+          if (i < kBlurSpan * kTmaPitch && flat[i] == 0.0f) flat[i] = kInvalid;
+        }
+        __syncwarp();
+        __syncthreads();                                   // (A) the tile is ready; s_next[buf ^ 1] is visible
+        blur_compute<kTmaPitch, kTmaXoff>(q.b, dst, zlimit, *reinterpret_cast<const TmaTile *>(&tile_mem[buf][0]), (int)(t % tx_n) * kBlurTile, (int)(t / tx_n) * kBlurTile);
+        t = s_next[buf ^ 1];
+        __syncwarp();
+        __syncthreads();                                   // (B) nobody reads tiles[buf] any more
+        buf ^= 1;
+      }
+      fence_proxy_async();                                 // this pass's stores (generic proxy) before the next pass's TMA reads
+    } else {
+      BlurTile &tile = *reinterpret_cast<BlurTile *>(&tile_mem[0][0]);
+      for (;;) {
+        __syncthreads();                                   // the previous tile's readers are done with `tile` and s_next
+        if (threadIdx.x == 0) s_next[0] = atomicAdd(&q.counters[pass], 1u);
+        __syncthreads();
+        const unsigned int t = s_next[0];
+        if (t >= ntiles) break;
+        blur_tile(q.b, src, dst, zlimit, tile, (int)(t % tx_n) * kBlurTile, (int)(t / tx_n) * kBlurTile);
+      }
     }
     grid.sync();
+    if (TMA) fence_proxy_async();
   }
   if (blockIdx.x == 0 && threadIdx.x < YV_BLURZ_PASSES) q.counters[threadIdx.x] = 0u;      // for the next frame
   // ShadeSimple with the normals of the blurred z-buffer (five passes: the result sits in zbuf[1])

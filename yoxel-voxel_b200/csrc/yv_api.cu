@@ -285,6 +285,34 @@ void init_blur_taps(float *taps) {
   for (int i = 0; i < K * K; ++i) taps[i] /= sum;
 }
 
+// 2-D TMA descriptor of a z-buffer (width x height floats, dense rows): box = one staged BlurZ tile, 40 x 38 elements (the
+// inner extent must be a multiple of 16 bytes), elements outside the tensor are delivered as zeros = "invalid". The encode
+// function belongs to the driver API; it is fetched through the runtime, so nothing links against libcuda.
+bool make_zbuf_tensor_map(CUtensorMap *map, float *zbuf, int width, int height) {
+  typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiled encode = nullptr;
+  static bool looked = false;
+  if (!looked) {
+    looked = true;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      encode = (EncodeTiled)fn;
+    else
+      cudaGetLastError();
+  }
+  if (!encode || !zbuf || width <= 0 || height <= 0 || width % 4 != 0) return false;
+  const cuuint64_t gdim[2] = { (cuuint64_t)width, (cuuint64_t)height };
+  const cuuint64_t gstride[1] = { (cuuint64_t)width * sizeof(float) };
+  const cuuint32_t box[2] = { (cuuint32_t)yv::kTmaPitch, (cuuint32_t)yv::kBlurSpan };
+  const cuuint32_t estride[2] = { 1u, 1u };
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2u, zbuf, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 void init_ray_dir(const yv_renderer *r, float dir0[3], float du[3], float dv[3], ViewBasis *basis = nullptr) {
   init_ray_dir_raw(r->dir, r->up, r->fov, r->width, r->height, dir0, du, dv, basis);
 }
@@ -547,25 +575,35 @@ int launch_frame(yv_renderer *r, void *d_rgba) {
     for (int i = 0; i < YV_BLURZ_PASSES; ++i, blur_size += 3) zlimit[i] = (5.0f * r->ssna_voxel_size) / (pixel_ang * blur_size);
     const int tiles_x = (p.width + yv::kBlurTile - 1) / yv::kBlurTile, tiles_y = (p.height + yv::kBlurTile - 1) / yv::kBlurTile;
     if (r->opt_ssna_fused) {
-      // BlurZ x5 + ShadeSimple as one persistent cooperative launch (render_kernels.cuh, ssna_post)
+      // BlurZ x5 + ShadeSimple as one persistent cooperative launch (render_kernels.cuh, ssna_post); tiles staged by TMA
+      // when the rows of the z-buffers are 16-byte multiples (the tensor map's pitch rule), otherwise by plain loads
       if (!r->d_ssna_counters) {
         YV_CUDA(cudaMalloc(&r->d_ssna_counters, YV_BLURZ_PASSES * sizeof(unsigned int)));
         YV_CUDA(cudaMemsetAsync(r->d_ssna_counters, 0, YV_BLURZ_PASSES * sizeof(unsigned int), r->stream));
       }
-      if (r->ssna_post_grid == 0) {
-        int per_sm = 0;
-        YV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, yv::ssna_post, 256, 0));
-        r->ssna_post_grid = std::max(1, per_sm) * r->sm_count;
-      }
       yv::SsnaPostParams q;
+      std::memset(&q, 0, sizeof q);
+      bool tma = r->opt_ssna_fused == 1 && p.width % 4 == 0;
+      if (tma) {
+        for (int i = 0; i < 2 && tma; ++i) tma = make_zbuf_tensor_map(&q.tmap[i], r->d_zbuf[i], p.width, p.height);
+        if (!tma) cudaGetLastError();
+      }
+      int &grid_cap = tma ? r->ssna_post_grid_tma : r->ssna_post_grid;
+      if (grid_cap == 0) {
+        int per_sm = 0;
+        if (tma) YV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, yv::ssna_post<true>, 256, 0));
+        else YV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, yv::ssna_post<false>, 256, 0));
+        grid_cap = std::max(1, per_sm) * r->sm_count;
+      }
       q.p = p; q.b = b; q.b.src = nullptr; q.b.dst = nullptr; q.b.zlimit = 0.0f;
       q.zbuf[0] = r->d_zbuf[0]; q.zbuf[1] = r->d_zbuf[1];
       for (int i = 0; i < YV_BLURZ_PASSES; ++i) q.zlimit[i] = zlimit[i];
       q.counters = r->d_ssna_counters;
       q.tiles_x = tiles_x; q.tiles_y = tiles_y;
-      const int grid = std::max(1, std::min(r->ssna_post_grid, tiles_x * tiles_y));
+      const int grid = std::max(1, std::min(grid_cap, tiles_x * tiles_y));
       void *args[] = { (void *)&q };
-      YV_CUDA(cudaLaunchCooperativeKernel((const void *)yv::ssna_post, dim3((unsigned)grid), dim3(256), args, 0, r->stream));
+      const void *kern = tma ? (const void *)yv::ssna_post<true> : (const void *)yv::ssna_post<false>;
+      YV_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(256), args, 0, r->stream));
       ++launches;
     } else {
       int src = 0;
@@ -935,6 +973,7 @@ int yv_renderer_create(int device, yv_renderer **out) {
   r->stream = r->own_stream;
   r->width = 640; r->height = 480;            // renderer_base.h:25
   init_blur_taps(r->blur_taps);               // InitBlur in the constructor (demo/SVORenderer.cpp:22)
+  if (const char *e = std::getenv("YV_SSNA_FUSED")) r->opt_ssna_fused = std::max(0, std::min(2, std::atoi(e)));   // A/B runs of bench.py
   *out = r;
   return YV_OK;
 }
@@ -1308,7 +1347,7 @@ int yv_set_option(yv_renderer *r, const char *name, int value) {
   else if (n == "sec_queue") r->opt_sec_queue = value ? 1 : 0;
   else if (n == "sec_threshold") { if (value < -1 || value > 31) return fail(YV_ERR_ARG, "sec_threshold must be -1..31"); r->opt_sec_threshold = value; }
   else if (n == "zero_copy") r->opt_zero_copy = value != 0;
-  else if (n == "ssna_fused") r->opt_ssna_fused = value != 0;
+  else if (n == "ssna_fused") r->opt_ssna_fused = value < 0 ? 0 : (value > 2 ? 2 : value);
   else if (n == "group_threads") r->opt_group_threads = value != 0;
   else if (n == "pipeline_taper") { if (value < 10 || value > 100) return fail(YV_ERR_ARG, "pipeline_taper must be 10..100 percent"); r->opt_pipeline_taper = value; }
   else if (n == "pipeline") { if (value < 0 || value > yv_renderer::kChunks) return fail(YV_ERR_ARG, "pipeline must be 0..8 chunks"); r->opt_pipeline = value; }

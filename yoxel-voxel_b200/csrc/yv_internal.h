@@ -116,8 +116,9 @@ struct yv_renderer {
   uint2 *d_shade_rec = nullptr;       // (VoxData, t) per pixel for the ShadeSimple pass
   float *d_zbuf[2] = { nullptr, nullptr };   // m_zbuf[2] (demo/SVORenderer.cpp:85-86): BlurZ ping-pong
   unsigned int *d_ssna_counters = nullptr;   // ssna_post: one tile counter per BlurZ pass (zero between frames)
-  int ssna_post_grid = 0;                    // resident CTAs of ssna_post on this device
-  int opt_ssna_fused = 0;                    // 1 = BlurZ x5 + ShadeSimple as one persistent cooperative launch (measured 1.5 % slower
+  int ssna_post_grid = 0, ssna_post_grid_tma = 0;   // resident CTAs of ssna_post<false> / <true> on this device
+  int opt_ssna_fused = 0;                    // 1 = BlurZ x5 + ShadeSimple as one persistent cooperative launch, tiles prefetched by TMA;
+                                             // 2 = the same with plain staging loads (measured 1.5 % slower
                                              // per frame than the six launches it replaces: profiles/README.md); 0 = six launches
   unsigned int *d_tile_counter = nullptr;
   bool hits = false, counters = false;
