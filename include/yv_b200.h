@@ -272,7 +272,9 @@ int yv_set_stream(yv_renderer *r, void *cuda_stream);
  *   "slots"       frames in flight for yv_render_frame_async (2..4, default 2)
  *   "group_threads" multi-device handles: 1 (default) = every peer GPU's share of a frame is issued by its own persistent
  *                 host thread (SPURenderer's one thread per SPE, cell/spu_renderer.cpp:76-87), so the N launches start
- *                 together; 0 = one loop on the calling thread (the launches of 8 GPUs then start ~18 us apart)
+ *                 together; 0 = one loop on the calling thread (the launches of 8 GPUs then start ~18 us apart). The
+ *                 threads poll for the next frame for YV_WORKER_SPIN_US microseconds (environment, default 2000, 0 = off)
+ *                 before they sleep: a condition-variable wake-up is 10-30 us of launch skew
  *   "ssna_fused"  SSNA's BlurZ x5 + ShadeSimple (demo/SVORenderer.cpp:126-147) as ONE persistent cooperative launch that
  *                 pulls 32x32 tiles from a counter per pass, grid barriers between the passes: 1 = with the next tile
  *                 prefetched into a second shared-memory buffer by a 2-D TMA load (needs width % 4 == 0, else as 2),

@@ -18,8 +18,10 @@
 //
 // No collective library is involved: the frame shards into disjoint pixels and the only exchange is the final store.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <thread>
@@ -39,18 +41,34 @@ struct MemberWorker {
   std::mutex mu;
   std::condition_variable cv;
   std::function<int()> job;
+  std::atomic<bool> posted{ false };      // a job is waiting (what a spinning worker polls)
   bool has_job = false, done = true, quit = false;
   int rc = 0;
   std::string err;
+  // After a frame the worker polls for the next one for a while before it goes to sleep on the condition variable: in a
+  // flythrough the next frame's share arrives within a millisecond, and a condition-variable wake-up (10-30 us) would be
+  // most of the launch skew between the members of a group. YV_WORKER_SPIN_US sets the polling time (default 2000, 0 = off).
+  static long spin_us() {
+    static const long v = [] { const char *e = std::getenv("YV_WORKER_SPIN_US"); return e ? std::max(0l, std::atol(e)) : 2000l; }();
+    return v;
+  }
   MemberWorker() {
     th = std::thread([this] {
       for (;;) {
         std::function<int()> j;
+        if (spin_us() > 0) {
+          const auto until = std::chrono::steady_clock::now() + std::chrono::microseconds(spin_us());
+          while (!posted.load(std::memory_order_acquire) && std::chrono::steady_clock::now() < until) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+          }
+        }
         {
           std::unique_lock<std::mutex> lk(mu);
           cv.wait(lk, [this] { return has_job || quit; });
           if (quit) return;
-          j = std::move(job); has_job = false;
+          j = std::move(job); has_job = false; posted.store(false, std::memory_order_relaxed);
         }
         int r;
         std::string e;
@@ -63,7 +81,7 @@ struct MemberWorker {
     });
   }
   void submit(std::function<int()> j) {
-    { std::lock_guard<std::mutex> lk(mu); job = std::move(j); has_job = true; done = false; }
+    { std::lock_guard<std::mutex> lk(mu); job = std::move(j); has_job = true; done = false; posted.store(true, std::memory_order_release); }
     cv.notify_all();
   }
   int wait(std::string &why) {
