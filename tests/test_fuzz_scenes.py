@@ -92,6 +92,50 @@ def test_emu_matches_oracle_on_random_pools(spec):
     assert hits > 0
 
 
+@pytest.mark.parametrize("spec", POOLS, ids=lambda s: "seed%d_d%d_n%g" % (s[0], s[1], s[2]))
+def test_emu_closed_form_descent_on_random_pools(spec):
+    """lean_descend_once (trace_core.cuh) in front of primary and secondary rays on ragged pools, DAGs and pools full of
+    leaves — eyes and secondary origins inside the cube, on its faces, on cell boundaries: pixels, ids, t bits equal to the
+    oracle's, node fetches / pop re-fetches / stack depth equal to the general loop's, with and without the LOD cut-off."""
+    root, nodes = _random_pool(*spec)
+    svo = yv.SVOData.FromNodes(root, nodes)
+    pool = svo.nodes()
+    recs, leaves = svo.packed()
+    node_data = pool["data"][recs[:, 3]]
+    cams = _cams(spec[0] * 31 + spec[1], 6)
+    # eyes on cell boundaries and cube faces: the closed form must hand exactly these cases back to the general loop
+    cams += [((0.5, 0.5, 0.5), (0.3, -0.7, 0.2), (0.0, 0.0, 1.0), 70.0), ((0.25, 0.75, 0.5), (-0.4, 0.1, 0.9), (0.0, 1.0, 0.0), 90.0),
+             ((0.0, 0.5, 0.5), (1.0, 0.1, 0.05), (0.0, 0.0, 1.0), 70.0), ((1.0, 1.0, 1.0), (-1.0, -0.9, -0.8), (0.0, 0.0, 1.0), 50.0)]
+    fast_levels = 0
+    for i, (pos, d, up, fov) in enumerate(cams):
+        W, H = [(40, 32), (29, 23)][i % 2]
+        detail = [0.0, 4.0][i % 2]
+        d0, du, dv = yv.init_ray_dir(d, up, fov, W, H)
+        half_rad = np.float32(np.float32(fov) / np.float32(2)) * np.float32(np.pi / 180.0)
+        det = float(np.float32(np.float32(detail) * half_rad) / np.float32(W))
+        o = yvo.render(pool, svo.GetRoot(), yvo.camera(pos, d, up, fov, W, H, detail_coef=detail))
+        plain = yve.render(recs, leaves, 1, pos, d0, du, dv, pos, W, H, detail=det, node_data=node_data, mode=2)
+        fast = yve.render(recs, leaves, 1, pos, d0, du, dv, pos, W, H, detail=det, node_data=node_data, mode=5)
+        for e in (plain, fast):
+            assert (o["node"] == e["node"]).all() and (o["child"] == e["child"]).all(), (spec, i)
+            assert o["t"].tobytes() == e["t"].tobytes() and (o["rgba"] == e["rgba"]).all(), (spec, i)
+        assert (fast["visits"], fast["fetches"], fast["max_sp"]) == (plain["visits"], plain["fetches"], plain["max_sp"]), (spec, i)
+        fast_levels += fast["fast_levels"]
+        # secondary rays from the same camera (no LOD): shadow + AO, origins a voxel off the surface, on it, and far off it
+        for vs, amax in ((2.0 ** -spec[1], 0.05), (0.0, 0.3), (0.11, 0.0)):
+            kw = dict(shadow=1, ao_samples=2, seed=3 + i, voxel_size=vs, ao_max_t=amax)
+            light = (0.6, 0.4, 1.2)
+            os_ = yvo.render(pool, svo.GetRoot(), yvo.camera(pos, d, up, fov, W, H),
+                             sec=yvo.secondary(light_pos=light, **kw))
+            p2 = yve.render(recs, leaves, 1, pos, d0, du, dv, light, W, H, mode=2, **kw)
+            f2 = yve.render(recs, leaves, 1, pos, d0, du, dv, light, W, H, mode=5, **kw)
+            assert (os_["rgba"] == p2["rgba"]).all() and (os_["rgba"] == f2["rgba"]).all(), (spec, i, vs)
+            assert (f2["visits"], f2["fetches"], f2["max_sp"]) == (p2["visits"], p2["fetches"], p2["max_sp"]), (spec, i, vs)
+            fast_levels += f2["fast_levels"]
+    if spec[1] >= 4:
+        assert fast_levels > 0
+
+
 @pytest.mark.gpu
 def test_cuda_matches_oracle_on_random_pools():
     r = yv.SVORenderer(0)
